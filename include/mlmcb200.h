@@ -1,0 +1,135 @@
+/*
+ * mlmcb200.h -- C ABI of the B200-native MLMC estimation hot path (libmlmcb200.so).
+ *
+ * The reference (GeoMop/MLMC v1.0.2) is pure Python and has no FFI; its de-facto operator interface for
+ * this path is duck-typed Python.  Each entry point below names the reference
+ * code it replaces (paths relative to the reference root).  All `double*` / `uint8_t*` data arguments are
+ * DEVICE pointers owned by the caller (torch tensors in the Python host layer); `stream` is a
+ * `cudaStream_t` passed as `void*`; every call is asynchronous on that stream and keeps no global state.
+ * Return value: 0 = OK, negative = error (text via mlmcb200_last_error(), thread-local).
+ *
+ * Sample layout ("level chunk"): element (sample n, side s, component m) lives at
+ *     pairs[n * stride_n + s * stride_side + m * stride_m]        (strides in doubles)
+ * side 0 = fine, side 1 = coarse.  The storage row order of the reference, float64[N, 2, M]
+ * (mlmc/sample_storage_hdf.py:169-184, mlmc/tool/hdf5.py:311-320), is stride_n = 2M, stride_side = M,
+ * stride_m = 1.  Level 0 has no coarse part: pass has_coarse = 0 (the zero coarse row is then never read).
+ */
+#ifndef MLMCB200_H
+#define MLMCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLMCB200_ABI_VERSION 1
+
+/* mlmcb200_basis_t.kind */
+#define MLMCB200_RAW       0   /* identity, size 1: phi_0(x) = x, no transform (plain estimate_mean of a quantity) */
+#define MLMCB200_LEGENDRE  1   /* mlmc/moments.py:174-197  (numpy legvander recurrence)  */
+#define MLMCB200_MONOMIAL  2   /* mlmc/moments.py:111-126  (numpy polyvander recurrence) */
+#define MLMCB200_FOURIER   3   /* mlmc/moments.py:133-162  (1, cos t, sin t, cos 2t, ...) */
+
+#define MLMCB200_MAX_MOMENTS 256
+
+/* One `mlmc.moments.Moments` object: mlmc/moments.py:10-39 (transform) and :58-73 (clip / linear). */
+typedef struct {
+    int32_t kind;      /* MLMCB200_* above                                                     */
+    int32_t size;      /* number of base functions R                                           */
+    int32_t is_log;    /* Moments._is_log : value <- ln(value) before the affine map           */
+    int32_t is_clip;   /* Moments._is_clip (safe_eval): t outside [ref_lo, ref_hi] -> NaN      */
+    double  shift;     /* Moments._linear_shift                                                */
+    double  scale;     /* Moments._linear_scale                                                */
+    double  ref_lo;    /* Moments.ref_domain[0]                                                */
+    double  ref_hi;    /* Moments.ref_domain[1]                                                */
+} mlmcb200_basis_t;
+
+int         mlmcb200_abi_version(void);
+const char* mlmcb200_last_error(void);
+
+/* Number of SMs of the current device (grid sizing is done inside the library; exported for reports). */
+int mlmcb200_sm_count(void);
+
+/*
+ * Moments.eval_all / __call__  (mlmc/moments.py:75-93, :122-126, :145-162, :195-197; TransformedMoments :256-259)
+ * x[n] -> out[n][n_out].  `matrix` == NULL: out[:, r] = phi_r(x), n_out <= basis->size functions are written.
+ * `matrix` != NULL ([n_rows][basis->size], row-major, device): out = Phi @ matrix^T truncated to n_out <= n_rows.
+ * Legendre / Monomial tables are bit-identical to numpy's legvander / polyvander.
+ */
+int mlmcb200_basis_eval(const mlmcb200_basis_t* basis, const double* x, int64_t n,
+                        const double* matrix, int32_t n_rows, int32_t n_out,
+                        double* out, void* stream);
+
+/*
+ * mask_nan_samples for vector quantities (mlmc/quantity/quantity_estimate.py:6-14 applied to the moments of
+ * all M components): valid[n] = 1 iff every component of the fine (and, if has_coarse, coarse) row maps to a
+ * non-NaN moment vector.  Scalar quantities (M == 1) do not need it: the accumulate calls test inline.
+ */
+int mlmcb200_sample_mask(const mlmcb200_basis_t* basis, const double* pairs, int64_t n, int32_t n_comp,
+                         int64_t stride_n, int64_t stride_side, int64_t stride_m, int32_t has_coarse,
+                         uint8_t* valid, void* stream);
+
+/*
+ * Level accumulator of the fused moments + mean/variance reduction.  Replaces the chunk loop of
+ * estimate_mean over a `moments` quantity: mlmc/quantity/quantity_estimate.py:43-65 with the operation
+ * of :105-110 and the difference of :59-62.  Layout (doubles):
+ *     acc[0] = n_samples (valid), acc[1] = n_rm_samples (masked), acc[2 + k] = sum_n d_k,
+ *     acc[2 + K + k] = sum_n d_k^2,   K = n_comp * size,  k = m * size + r  (mom_at_bottom order)
+ * where d = phi_r(fine_m) - phi_r(coarse_m) (level 0: phi_r(fine_m)).  The call ADDS the chunk into acc,
+ * so a level may be streamed in any number of chunks; zero acc first.
+ * `valid` (from mlmcb200_sample_mask) is required when n_comp > 1 and may be NULL when n_comp == 1.
+ * `workspace` must hold mlmcb200_moments_workspace_bytes(...) bytes.
+ */
+int64_t mlmcb200_moments_workspace_bytes(int32_t size, int32_t n_comp);
+int mlmcb200_moments_accumulate(const mlmcb200_basis_t* basis, const double* pairs, int64_t n, int32_t n_comp,
+                                int64_t stride_n, int64_t stride_side, int64_t stride_m, int32_t has_coarse,
+                                const uint8_t* valid, double* acc, void* workspace, int64_t workspace_bytes,
+                                void* stream);
+
+/*
+ * Level accumulator of the moment-covariance estimate (scalar quantity).  Replaces estimate_mean over a
+ * `covariance` quantity: mlmc/quantity/quantity_estimate.py:131-147 + :43-65.  With R = basis->size:
+ *     acc[0] = n_samples, acc[1] = n_rm_samples,
+ *     acc[2 + i*R + j]       = sum_n d_ij,   d_ij = phi_i(f) phi_j(f) - phi_i(c) phi_j(c)   (level 0: fine only)
+ *     acc[2 + R*R + i*R + j] = sum_n d_ij^2  (only when want_var != 0; otherwise untouched)
+ * Both are dense contractions Phi^T Phi and run on FP64 tensor-core tiles (DMMA m8n8k4).
+ * mode: 0 = covariance (above); 1 = Gram of the differences, sum_n d_i d_j with d = phi(f) - phi(c),
+ * which is what TransformedMoments needs for its variances (var(L d) = L G L^T), want_var ignored.
+ */
+int64_t mlmcb200_gram_workspace_bytes(int32_t size);
+int mlmcb200_gram_accumulate(const mlmcb200_basis_t* basis, const double* pairs, int64_t n,
+                             int64_t stride_n, int64_t stride_side, int32_t has_coarse,
+                             int32_t mode, int32_t want_var, double* acc,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * l_means / l_vars of estimate_mean (mlmc/quantity/quantity_estimate.py:70-77) and QuantityMean.mean / .var
+ * (mlmc/quantity/quantity.py:588-593) for n_levels accumulators of K sums each, laid out back to back
+ * with a stride of acc_stride doubles:  mean_l = s/n,  var_l = (sq - s^2/n)/(n-1)  (n <= 1 -> +inf).
+ * out: l_means[L][K], l_vars[L][K], mean[K], var[K] (any may be NULL).
+ */
+int mlmcb200_finalize_levels(const double* acc, int64_t acc_stride, int32_t n_levels, int64_t K,
+                             double* l_means, double* l_vars, double* mean, double* var, void* stream);
+
+/*
+ * Max-entropy functional pieces on a fixed node set (mlmc/tool/simple_distribution.py:254-327):
+ *     rho_q = exp(clip(-phi_q . lam_scaled, -200, 200)),   lam_scaled = lambda / sigma
+ *     out[0]               = sum_q w_q rho_q                       (integral term of _calculate_functional)
+ *     out[1 + i]           = sum_q w_q rho_q phi_qi                (integral term of _calculate_gradient, before /sigma)
+ *     out[1 + R + i*R + j] = sum_q w_q rho_q phi_qi phi_qj         (_calculate_jacobian_matrix, before /sigma_i sigma_j)
+ * phi is [Q][ld] row-major with R <= ld.  what: bit 0 = F, bit 1 = g, bit 2 = H (unrequested parts are left untouched).
+ */
+int64_t mlmcb200_maxent_workspace_bytes(int64_t n_nodes, int32_t size);
+int mlmcb200_maxent_fgh(const double* phi, int64_t ld, const double* w, const double* lam_scaled,
+                        int64_t n_nodes, int32_t size, int32_t what, double* out,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* FP64 pipe micro-benchmarks used by bench.py for the roofline denominators (not on the data path):
+ * sustained DFMA (kind 0) or DMMA m8n8k4 (kind 1) throughput in FLOP/s (FMA = 2) measured with CUDA events. */
+int mlmcb200_fp64_peak(int32_t kind, double* flops_per_s, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLMCB200_H */

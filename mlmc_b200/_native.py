@@ -1,0 +1,276 @@
+"""ctypes binding of libmlmcb200.so (C ABI: include/mlmcb200.h).
+
+PyTorch is used for device memory and streams only; every function here takes ``torch`` CUDA tensors (or raw
+device pointers), passes plain pointers + sizes across the C ABI and launches on torch's current stream.
+There is NO fallback: if the shared library is missing and cannot be built, importing the product path raises.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+from . import build as _build
+
+_c_i32, _c_i64, _c_dbl, _c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+
+RAW, LEGENDRE, MONOMIAL, FOURIER = 0, 1, 2, 3
+MAX_MOMENTS = 256
+
+
+class BasisStruct(ctypes.Structure):
+    """mlmcb200_basis_t"""
+    _fields_ = [("kind", _c_i32), ("size", _c_i32), ("is_log", _c_i32), ("is_clip", _c_i32),
+                ("shift", _c_dbl), ("scale", _c_dbl), ("ref_lo", _c_dbl), ("ref_hi", _c_dbl)]
+
+
+RAW_BASIS = BasisStruct(RAW, 1, 0, 0, 0.0, 1.0, 0.0, 0.0)
+
+_SIGNATURES = {
+    "mlmcb200_abi_version": (ctypes.c_int, []),
+    "mlmcb200_last_error": (ctypes.c_char_p, []),
+    "mlmcb200_sm_count": (ctypes.c_int, []),
+    "mlmcb200_basis_eval": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_vp, _c_i32, _c_i32,
+                                           _c_vp, _c_vp]),
+    "mlmcb200_sample_mask": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_i32, _c_i64, _c_i64,
+                                            _c_i64, _c_i32, _c_vp, _c_vp]),
+    "mlmcb200_moments_workspace_bytes": (_c_i64, [_c_i32, _c_i32]),
+    "mlmcb200_moments_accumulate": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_i32, _c_i64,
+                                                   _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
+    "mlmcb200_gram_workspace_bytes": (_c_i64, [_c_i32]),
+    "mlmcb200_gram_accumulate": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_i64, _c_i64,
+                                                _c_i32, _c_i32, _c_i32, _c_vp, _c_vp, _c_i64, _c_vp]),
+    "mlmcb200_finalize_levels": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp,
+                                                _c_vp]),
+    "mlmcb200_maxent_workspace_bytes": (_c_i64, [_c_i64, _c_i32]),
+    "mlmcb200_maxent_fgh": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp, _c_vp,
+                                           _c_i64, _c_vp]),
+    "mlmcb200_fp64_peak": (ctypes.c_int, [_c_i32, ctypes.POINTER(_c_dbl), _c_vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_lock = threading.Lock()
+#: number of kernel launches issued through this binding (bench.py reports it as ``gpu_launches``)
+launch_count = 0
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if the .so is absent).  Raises if neither works -- never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            path = library_path()
+            if not os.path.exists(path):
+                try:
+                    _build.build()
+                except Exception as exc:  # pragma: no cover - depends on toolchain
+                    raise NativeError("libmlmcb200.so is missing and could not be built: %s" % exc)
+            lib = ctypes.CDLL(path)
+            for name, (res, args) in _SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            if lib.mlmcb200_abi_version() != 1:
+                raise NativeError("libmlmcb200.so ABI version mismatch")
+            _lib = lib
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise NativeError("%s failed (%d): %s" % (what, rc, load().mlmcb200_last_error().decode()))
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _require_cuda(t, name, dtype=torch.float64):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype):
+        raise NativeError("%s must be a CUDA tensor of dtype %s" % (name, dtype))
+
+
+def sm_count():
+    return load().mlmcb200_sm_count()
+
+
+# ---------------------------------------------------------------------------------------------------------
+def basis_eval(basis, x, n_out, matrix=None):
+    """x: flat CUDA float64 tensor [n] -> Phi [n, n_out]."""
+    global launch_count
+    _require_cuda(x, "x")
+    x = x.contiguous()
+    out = torch.empty((x.numel(), n_out), dtype=torch.float64, device=x.device)
+    n_rows = 0
+    if matrix is not None:
+        _require_cuda(matrix, "matrix")
+        matrix = matrix.contiguous()
+        n_rows = matrix.shape[0]
+    with torch.cuda.device(x.device):
+        _check(load().mlmcb200_basis_eval(ctypes.byref(basis), _ptr(x), x.numel(), _ptr(matrix), n_rows, n_out,
+                                          _ptr(out), _stream()), "basis_eval")
+    launch_count += 1
+    return out
+
+
+def _chunk_layout(x):
+    """x: CUDA float64 tensor view [M, n, S] (S = 1 or 2) -> (M, n, has_coarse, stride_n, stride_side, stride_m)."""
+    _require_cuda(x, "chunk")
+    if x.dim() != 3 or x.shape[2] not in (1, 2):
+        raise NativeError("chunk must have shape [M, n, 1|2], got %s" % (tuple(x.shape),))
+    sm, sn, ss = x.stride()
+    return x.shape[0], x.shape[1], int(x.shape[2] == 2), sn, ss, sm
+
+
+class LevelAccumulator:
+    """Device-side level sums for ``n_levels`` levels of ``K`` statistics each: [L, 2 + 2K] float64."""
+
+    def __init__(self, n_levels, K, device):
+        self.n_levels, self.K = n_levels, K
+        self.acc = torch.zeros((n_levels, 2 + 2 * K), dtype=torch.float64, device=device)
+
+    def level(self, l):
+        return self.acc[l]
+
+    def finalize(self):
+        """-> dict of CUDA tensors l_means [L,K], l_vars [L,K], mean [K], var [K] (one launch)."""
+        global launch_count
+        dev = self.acc.device
+        L, K = self.n_levels, self.K
+        out = torch.empty((2 * L + 2, K), dtype=torch.float64, device=dev)
+        l_means, l_vars, mean, var = out[:L], out[L:2 * L], out[2 * L], out[2 * L + 1]
+        with torch.cuda.device(dev):
+            _check(load().mlmcb200_finalize_levels(_ptr(self.acc), self.acc.stride(0), L, K, _ptr(l_means),
+                                                   _ptr(l_vars), _ptr(mean), _ptr(var), _stream()),
+                   "finalize_levels")
+        launch_count += 1
+        return {"l_means": l_means, "l_vars": l_vars, "mean": mean, "var": var, "packed": out}
+
+
+_workspaces = {}
+
+
+def _workspace(device, n_bytes):
+    key = (device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < n_bytes:
+        ws = torch.empty(max(int(n_bytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def sample_mask(basis, x):
+    """valid[n] (uint8) for a vector chunk x [M, n, S]."""
+    global launch_count
+    M, n, has_coarse, sn, ss, sm = _chunk_layout(x)
+    valid = torch.empty(n, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(load().mlmcb200_sample_mask(ctypes.byref(basis), _ptr(x), n, M, sn, ss, sm, has_coarse,
+                                           _ptr(valid), _stream()), "sample_mask")
+    launch_count += 1
+    return valid
+
+
+def moments_accumulate(basis, x, acc_row, valid=None):
+    """Add the chunk x [M, n, S] to ``acc_row`` ([2 + 2*M*R] float64, contiguous)."""
+    global launch_count
+    M, n, has_coarse, sn, ss, sm = _chunk_layout(x)
+    _require_cuda(acc_row, "acc")
+    K = M * basis.size
+    if acc_row.numel() != 2 + 2 * K or not acc_row.is_contiguous():
+        raise NativeError("accumulator must be contiguous with %d entries" % (2 + 2 * K))
+    if n == 0:
+        return
+    lib = load()
+    if M > 1 and valid is None:
+        valid = sample_mask(basis, x)
+    with torch.cuda.device(x.device):
+        ws_bytes = lib.mlmcb200_moments_workspace_bytes(basis.size, M)
+        if ws_bytes < 0:
+            raise NativeError("moments workspace: %s" % lib.mlmcb200_last_error().decode())
+        ws = _workspace(x.device, ws_bytes)
+        _check(lib.mlmcb200_moments_accumulate(ctypes.byref(basis), _ptr(x), n, M, sn, ss, sm, has_coarse,
+                                               _ptr(valid), _ptr(acc_row), _ptr(ws), ws.numel(), _stream()),
+               "moments_accumulate")
+    launch_count += 2
+
+
+def gram_accumulate(basis, x, acc_row, mode=0, want_var=True):
+    """Add the chunk x [1, n, S] to the covariance accumulator ``acc_row`` ([2 + 2*R*R])."""
+    global launch_count
+    M, n, has_coarse, sn, ss, sm = _chunk_layout(x)
+    if M != 1:
+        raise NativeError("gram_accumulate handles scalar quantities (M == 1), got M = %d" % M)
+    _require_cuda(acc_row, "acc")
+    R = basis.size
+    if acc_row.numel() != 2 + 2 * R * R or not acc_row.is_contiguous():
+        raise NativeError("accumulator must be contiguous with %d entries" % (2 + 2 * R * R))
+    if n == 0:
+        return
+    lib = load()
+    with torch.cuda.device(x.device):
+        ws_bytes = lib.mlmcb200_gram_workspace_bytes(R)
+        if ws_bytes < 0:
+            raise NativeError("gram workspace: %s" % lib.mlmcb200_last_error().decode())
+        ws = _workspace(x.device, ws_bytes)
+        _check(lib.mlmcb200_gram_accumulate(ctypes.byref(basis), _ptr(x), n, sn, ss, has_coarse, mode,
+                                            int(bool(want_var)), _ptr(acc_row), _ptr(ws), ws.numel(), _stream()),
+               "gram_accumulate")
+    launch_count += 2
+
+
+def maxent_fgh(phi, w, lam_scaled, what=7, out=None):
+    """phi [Q, ld] (R = len(lam_scaled) <= ld), w [Q] -> out [1 + R + R*R] (F, g, H integral terms)."""
+    global launch_count
+    _require_cuda(phi, "phi")
+    _require_cuda(w, "w")
+    _require_cuda(lam_scaled, "lam_scaled")
+    Q, ld = phi.shape
+    R = lam_scaled.numel()
+    if phi.stride(1) != 1 or phi.stride(0) != ld or R > ld:
+        raise NativeError("phi must be row-major [Q, ld] with R <= ld")
+    if out is None:
+        out = torch.zeros(1 + R + R * R, dtype=torch.float64, device=phi.device)
+    lib = load()
+    with torch.cuda.device(phi.device):
+        ws_bytes = lib.mlmcb200_maxent_workspace_bytes(Q, R)
+        ws = _workspace(phi.device, ws_bytes)
+        _check(lib.mlmcb200_maxent_fgh(_ptr(phi), ld, _ptr(w), _ptr(lam_scaled), Q, R, what, _ptr(out), _ptr(ws),
+                                       ws.numel(), _stream()), "maxent_fgh")
+    launch_count += 2
+    return out
+
+
+def fp64_peak(kind):
+    """Measured FP64 pipe throughput in FLOP/s: kind 0 = DFMA, 1 = DMMA m8n8k4."""
+    val = _c_dbl(0.0)
+    _check(load().mlmcb200_fp64_peak(kind, ctypes.byref(val), _stream()), "fp64_peak")
+    return val.value
+
+
+def make_basis(kind, size, domain, ref_domain, log=False, safe_eval=True):
+    """mlmcb200_basis_t from ``Moments.__init__`` parameters (mlmc/moments.py:10-26)."""
+    import math
+    lo, hi = (math.log(domain[0]), math.log(domain[1])) if log else (float(domain[0]), float(domain[1]))
+    width = hi - lo
+    assert width > 0
+    width = max(width, 1e-15)
+    scale = (ref_domain[1] - ref_domain[0]) / width
+    return BasisStruct(kind, int(size), int(bool(log)), int(bool(safe_eval)), lo, scale,
+                       float(ref_domain[0]), float(ref_domain[1]))

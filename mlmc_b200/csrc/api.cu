@@ -1,0 +1,129 @@
+// Library-wide pieces of the C ABI: error text, device query, FP64 pipe micro-benchmarks.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace mlmcb200 {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached = v;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+int check_basis(const mlmcb200_basis_t* b) {
+    MB_REQUIRE(b != nullptr, "null basis");
+    MB_REQUIRE(b->kind >= MLMCB200_RAW && b->kind <= MLMCB200_FOURIER, "unknown basis kind %d", b->kind);
+    MB_REQUIRE(b->size >= 1 && b->size <= MLMCB200_MAX_MOMENTS, "basis size %d outside [1, %d]", b->size,
+               MLMCB200_MAX_MOMENTS);
+    MB_REQUIRE(b->kind != MLMCB200_RAW || b->size == 1, "RAW basis must have size 1");
+    return 0;
+}
+
+namespace {
+
+// 8 independent DFMA chains per thread
+__global__ void dfma_peak_kernel(double* sink, int iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6,
+           a7 = seed + 7;
+    const double m = 1.0000001, c = 1e-9;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 123.456) sink[0] = r;
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// 8 independent 8x8 accumulator tiles per warp
+__global__ void dmma_peak_kernel(double* sink, int iters, double seed) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = seed + i;
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-9 * (threadIdx.x & 3);
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) dmma884(c[2 * t], c[2 * t + 1], a, b);
+        }
+    }
+    double r = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r += c[i];
+    if (r == 123.456) sink[0] = r;
+}
+
+}  // namespace
+}  // namespace mlmcb200
+
+using namespace mlmcb200;
+
+extern "C" int mlmcb200_abi_version(void) { return MLMCB200_ABI_VERSION; }
+
+extern "C" const char* mlmcb200_last_error(void) { return g_error; }
+
+extern "C" int mlmcb200_sm_count(void) { return sm_count(); }
+
+extern "C" int mlmcb200_fp64_peak(int32_t kind, double* flops_per_s, void* stream) {
+    MB_REQUIRE(flops_per_s != nullptr && (kind == 0 || kind == 1), "fp64_peak: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* sink = nullptr;
+    MB_CUDA_OK(cudaMalloc(&sink, 8));
+    cudaEvent_t e0, e1;
+    MB_CUDA_OK(cudaEventCreate(&e0));
+    MB_CUDA_OK(cudaEventCreate(&e1));
+    const int blocks = sm_count() * 8, threads = 256, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        MB_CUDA_OK(cudaEventRecord(e0, st));
+        if (kind == 0)
+            dfma_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, 0.5);
+        else
+            dmma_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, 0.5);
+        MB_CUDA_OK(cudaGetLastError());
+        MB_CUDA_OK(cudaEventRecord(e1, st));
+        MB_CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        MB_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        double flops;
+        if (kind == 0)
+            flops = (double)blocks * threads * iters * 64.0 * 2.0;                   // 64 DFMA per thread-iteration
+        else
+            flops = (double)blocks * (threads / 32) * iters * 32.0 * (8 * 8 * 4) * 2.0;  // 32 DMMA per warp-iteration
+        const double rate = flops / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;                                        // rep 0 = warm-up
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *flops_per_s = best;
+    return 0;
+}

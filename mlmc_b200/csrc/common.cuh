@@ -1,0 +1,89 @@
+// Shared host/device helpers of libmlmcb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/mlmcb200.h"
+
+namespace mlmcb200 {
+
+void set_error(const char* fmt, ...);
+int  sm_count();
+
+#define MB_CUDA_OK(expr)                                                                     \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::mlmcb200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
+                                  __FILE__, __LINE__);                                       \
+            return -2;                                                                       \
+        }                                                                                    \
+    } while (0)
+
+#define MB_REQUIRE(cond, ...)                                                                \
+    do {                                                                                     \
+        if (!(cond)) {                                                                       \
+            ::mlmcb200::set_error(__VA_ARGS__);                                              \
+            return -1;                                                                       \
+        }                                                                                    \
+    } while (0)
+
+int check_basis(const mlmcb200_basis_t* b);
+
+// Coefficients of the monic Legendre recurrence W_i = t W_{i-1} - kLegCoef[i] W_{i-2}, P_i = kLegAlpha[i] W_i
+// (gen_tables.py).  Statically initialised __constant__ data, one copy per translation unit (no -rdc).
+#include "legendre_tables.inc"
+static __constant__ double kLegCoef[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_COEF_INIT;
+static __constant__ double kLegAlpha[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_ALPHA_INIT;
+// P_i = (kLegA[i] t) P_{i-1} - kLegB[i] P_{i-2}: the un-scaled recurrence with correctly rounded ratios
+static __constant__ double kLegA[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_A_INIT;
+static __constant__ double kLegB[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_B_INIT;
+
+// defined in moments.cu: acc[j] += sum_b partial[b * stride + j], j < len, fixed order (bitwise reproducible)
+int launch_reduce_partials(const double* partial, int n_partials, int64_t stride, int64_t len, double* acc,
+                           cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
+// Moments.transform (mlmc/moments.py:28-39, 58-73).  The affine map is evaluated with the same three
+// IEEE operations as the reference ((v - shift) * scale + ref_lo, no FMA contraction) so that the
+// closed-interval domain test makes the same decision for every finite input.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double map_to_ref(const mlmcb200_basis_t& b, double v) {
+    if (b.is_log) v = log(v);
+    double t = __dadd_rn(__dmul_rn(__dsub_rn(v, b.shift), b.scale), b.ref_lo);
+    if (b.is_clip && (t < b.ref_lo || t > b.ref_hi)) t = __longlong_as_double(0x7ff8000000000000LL);
+    return t;
+}
+
+// numpy legvander step, exactly: (p1 * t * (2i-1) - p0 * (i-1)) / i
+__device__ __forceinline__ double legendre_step_exact(double p1, double p0, double t, int i) {
+    return __ddiv_rn(__dsub_rn(__dmul_rn(__dmul_rn(p1, t), (double)(2 * i - 1)), __dmul_rn(p0, (double)(i - 1))),
+                     (double)i);
+}
+
+// Does the moment vector of the mapped value t contain no NaN?  (mask_nan_samples,
+// mlmc/quantity/quantity_estimate.py:6-14, applied to Moments.eval_all of this value.)
+__device__ __forceinline__ bool moments_finite(const mlmcb200_basis_t& b, double t) {
+    if (b.kind == MLMCB200_RAW) return !isnan(t);
+    if (b.kind == MLMCB200_FOURIER) return b.size == 1 || isfinite(t);   // column 0 is the literal 1
+    if (!isfinite(t)) return false;                   // numpy: v[0] = t*0 + 1 is NaN for NaN and +-inf
+    if (b.kind == MLMCB200_MONOMIAL || b.is_clip || fabs(t) <= 4.0) return true;
+    // unclipped Legendre far outside the domain: overflow gives inf - inf = NaN two steps after the first inf
+    double p0 = 1.0, p1 = t;
+    for (int i = 2; i < b.size; ++i) {
+        double p2 = legendre_step_exact(p1, p0, t, i);
+        if (isnan(p2)) return false;
+        p0 = p1;
+        p1 = p2;
+    }
+    return true;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace mlmcb200

@@ -1,0 +1,304 @@
+"""Parity of the CUDA kernels (through the C ABI) with the oracle and the reference's golden outputs.
+
+Tolerances (BASELINE.json north_star): moment means / variances rel <= 1e-10, covariance rel <= 1e-8,
+max-ent pieces rel <= 1e-10 here (multipliers / pdf 1e-6 in test_api_gpu.py); sample counts exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mlmc_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+KINDS = {"raw": 0, "legendre": 1, "monomial": 2, "fourier": 3}
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def native():
+    from mlmc_b200 import _native
+    return _native
+
+
+def to_struct(b: orc.Basis):
+    return native().make_basis(KINDS[b.kind], b.size, b.domain, b.ref_domain, b.log, b.safe_eval)
+
+
+def rel_close(got, want, rtol, atol_scale=1e-15):
+    got, want = np.asarray(got, dtype=float), np.asarray(want, dtype=float)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    scale = np.max(np.abs(want[np.isfinite(want)])) if np.isfinite(want).any() else 1.0
+    ok = np.isclose(got, want, rtol=rtol, atol=atol_scale * max(scale, 1e-300), equal_nan=True)
+    assert ok.all(), "max abs err %.3e (scale %.3e) at %s" % (
+        np.nanmax(np.abs(got - want)[~ok]), scale, np.argwhere(~ok)[:5].tolist())
+
+
+def run_moments(basis, levels, chunk_rows=None):
+    """levels: list of float64[N,2,M] -> dict of numpy arrays (l_means, l_vars, mean, var, n, n_rm)."""
+    nat = native()
+    M = levels[0].shape[2]
+    acc = nat.LevelAccumulator(len(levels), M * basis.size, dev())
+    for l, rows in enumerate(levels):
+        d_rows = torch.from_numpy(np.ascontiguousarray(rows)).to(dev())
+        step = chunk_rows or max(len(rows), 1)
+        for start in range(0, len(rows), step):
+            part = d_rows[start:start + step]
+            x = part.permute(2, 0, 1)                 # [M, n, 2] view, storage strides
+            if l == 0:
+                x = x[:, :, :1]
+            nat.moments_accumulate(basis, x, acc.level(l))
+    res = {k: v.cpu().numpy() for k, v in acc.finalize().items()}
+    a = acc.acc.cpu().numpy()
+    res["n"], res["n_rm"] = a[:, 0].astype(np.int64), a[:, 1].astype(np.int64)
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------
+def test_library_loads_on_gpu():
+    nat = native()
+    assert nat.load().mlmcb200_abi_version() == 1
+    assert nat.sm_count() > 0
+
+
+def test_basis_tables_match_reference(golden):
+    nat = native()
+    g = golden("basis_tables")
+    for i in range(int(g["n_cases"])):
+        kind, size, dom, log, safe = g["case%02d_meta" % i]
+        b = orc.Basis(str(kind), int(size), eval(str(dom)), log=bool(int(log)), safe_eval=bool(int(safe)))
+        x = torch.from_numpy(g["case%02d_x" % i]).to(dev())
+        got = nat.basis_eval(to_struct(b), x, b.size).cpu().numpy()
+        want = g["case%02d_ref" % i]
+        if b.kind == "fourier" or b.log:
+            rel_close(got, want, rtol=1e-13, atol_scale=4e-15)
+            assert np.array_equal(np.isnan(got), np.isnan(want))
+        else:   # Legendre / Monomial follow numpy operation by operation: bit-identical
+            assert np.array_equal(got, want, equal_nan=True), (kind, size)
+    # TransformedMoments
+    b = orc.Basis("legendre", 9, (-3.0, 5.0))
+    mat = torch.from_numpy(g["transformed_matrix"]).to(dev())
+    got = nat.basis_eval(to_struct(b), torch.from_numpy(g["transformed_x"]).to(dev()), mat.shape[0], mat).cpu().numpy()
+    rel_close(got, g["transformed_ref"], rtol=1e-12, atol_scale=1e-14)
+    # truncated evaluation (eval_all(value, size))
+    got = nat.basis_eval(to_struct(b), torch.from_numpy(g["transformed_x"]).to(dev()), 4).cpu().numpy()
+    assert np.array_equal(got, orc.basis_eval(b, g["transformed_x"], 4), equal_nan=True)
+
+
+def test_reference_golden_means(golden):
+    """test/test_sampling_pools.py:18,85-87: ref_means (atol 1e-5), means[0] == 1 and vars[0] == 0 exactly."""
+    g = golden("sampling_pools")
+    col = int(g["column"])
+    levels = [g["rows%d" % l] for l in range(3)]
+    basis = to_struct(orc.Basis("legendre", 5, tuple(g["domain"])))
+    nat = native()
+    acc = nat.LevelAccumulator(3, 5, dev())
+    for l, rows in enumerate(levels):
+        d_rows = torch.from_numpy(rows).to(dev())                       # [10, 2, 24]
+        x = d_rows.permute(2, 0, 1)[col:col + 1]                        # strided column view
+        if l == 0:
+            x = x[:, :, :1]
+        nat.moments_accumulate(basis, x, acc.level(l))
+    out = acc.finalize()
+    mean, var = out["mean"].cpu().numpy(), out["var"].cpu().numpy()
+    assert mean[0] == 1.0 and var[0] == 0.0
+    assert np.allclose(mean, g["ref_means"], atol=1e-5)
+    rel_close(mean, g["means"], rtol=1e-10)
+    rel_close(var, g["vars"], rtol=1e-10)
+
+
+@pytest.mark.parametrize("tag,kind,size,dom,safe", [
+    ("leg", "legendre", 12, None, True), ("mono", "monomial", 6, None, True),
+    ("four", "fourier", 7, None, True), ("legraw", "legendre", 8, (-20.0, 20.0), False)])
+@pytest.mark.parametrize("chunk_rows", [None, 512])
+def test_moments_three_levels(golden, tag, kind, size, dom, safe, chunk_rows):
+    g = golden("estimates")
+    dom = tuple(g["A_domain"]) if dom is None else dom
+    levels = [g["A_rows%d" % l] for l in range(3)]
+    res = run_moments(to_struct(orc.Basis(kind, size, dom, safe_eval=safe)), levels, chunk_rows)
+    assert np.array_equal(res["n"], g["A_%s_n" % tag]) and np.array_equal(res["n_rm"], g["A_%s_n_rm" % tag])
+    rel_close(res["l_means"], g["A_%s_l_means" % tag], rtol=1e-10)
+    rel_close(res["l_vars"], g["A_%s_l_vars" % tag], rtol=1e-10)
+    rel_close(res["mean"], g["A_%s_mean" % tag], rtol=1e-10)
+    rel_close(res["var"], g["A_%s_var" % tag], rtol=1e-10)
+    assert res["mean"][0] == 1.0 and res["var"][0] == 0.0
+
+
+def test_moments_log_domain(golden):
+    g = golden("estimates")
+    res = run_moments(to_struct(orc.Basis("legendre", 25, tuple(g["B_domain"]), log=True)), [g["B_rows0"]], 4096)
+    assert np.array_equal(res["n"], g["B_n"]) and np.array_equal(res["n_rm"], g["B_n_rm"])
+    rel_close(res["mean"], g["B_mean"], rtol=1e-10)
+    rel_close(res["var"], g["B_var"], rtol=1e-10)
+
+
+def test_moments_vector_quantity(golden):
+    g = golden("estimates")
+    levels = [g["C_rows%d" % l] for l in range(4)]
+    res = run_moments(to_struct(orc.Basis("legendre", 5, tuple(g["C_domain"]))), levels, 256)
+    assert np.array_equal(res["n"], g["C_bottom_n"]) and np.array_equal(res["n_rm"], g["C_bottom_n_rm"])
+    rel_close(res["l_means"], g["C_bottom_l_means"].reshape(4, -1), rtol=1e-10)
+    rel_close(res["l_vars"], g["C_bottom_l_vars"].reshape(4, -1), rtol=1e-10)
+    # identity operation (plain estimate_mean of the quantity)
+    raw = run_moments(native().RAW_BASIS, levels, 100)
+    rel_close(raw["mean"], g["C_raw_mean"].reshape(-1), rtol=1e-10)
+    rel_close(raw["var"], g["C_raw_var"].reshape(-1), rtol=1e-10)
+
+
+@pytest.mark.parametrize("M", [130, 300])
+def test_moments_wide_vector_vs_oracle(M):
+    """More components than threads per CTA (component-tiled grid) against the oracle."""
+    rng = np.random.default_rng(7)
+    steps = orc.level_steps(2, (0.3, 0.03))
+    levels = []
+    for l, n in enumerate([257, 64]):
+        rows = orc.synth_level_rows(rng.normal(size=n), steps[l], steps[l - 1] if l else None)
+        rows = np.repeat(rows, M, axis=2) + np.arange(M)[None, None, :] * 1e-3
+        if l == 0:
+            rows[:, 1, :] = 0
+        levels.append(rows)
+    levels[1][3, 1, M - 1] = np.nan
+    b = orc.Basis("fourier", 6, (-4.0, 4.5))
+    want = orc.estimate_moments(levels, b)
+    res = run_moments(to_struct(b), levels, 100)
+    assert np.array_equal(res["n"], want.n_samples) and np.array_equal(res["n_rm"], want.n_rm_samples)
+    rel_close(res["l_means"], want.l_means, rtol=1e-10)
+    rel_close(res["l_vars"], want.l_vars, rtol=1e-10)
+
+
+def run_gram(basis, levels, want_var=True, chunk_rows=None, mode=0):
+    nat = native()
+    R = basis.size
+    acc = nat.LevelAccumulator(len(levels), R * R, dev())
+    for l, rows in enumerate(levels):
+        d_rows = torch.from_numpy(np.ascontiguousarray(rows)).to(dev())
+        step = chunk_rows or max(len(rows), 1)
+        for start in range(0, len(rows), step):
+            x = d_rows[start:start + step].permute(2, 0, 1)
+            if l == 0:
+                x = x[:, :, :1]
+            nat.gram_accumulate(basis, x, acc.level(l), mode=mode, want_var=want_var)
+    res = {k: v.cpu().numpy() for k, v in acc.finalize().items()}
+    a = acc.acc.cpu().numpy()
+    res["n"], res["n_rm"] = a[:, 0].astype(np.int64), a[:, 1].astype(np.int64)
+    return res
+
+
+@pytest.mark.parametrize("chunk_rows", [None, 700])
+def test_covariance_three_levels(golden, chunk_rows):
+    g = golden("estimates")
+    levels = [g["A_rows%d" % l] for l in range(3)]
+    res = run_gram(to_struct(orc.Basis("legendre", 8, tuple(g["A_domain"]))), levels, True, chunk_rows)
+    assert np.array_equal(res["n"], g["A_leg_n"])
+    rel_close(res["mean"].reshape(8, 8), g["A_cov_mean"], rtol=1e-8)
+    rel_close(res["var"].reshape(8, 8), g["A_cov_var"], rtol=1e-8)
+    rel_close(res["l_means"].reshape(3, 8, 8), g["A_cov_l_means"], rtol=1e-8)
+    rel_close(res["l_vars"].reshape(3, 8, 8), g["A_cov_l_vars"], rtol=1e-8)
+    # structural identity of test/test_quantity_concept.py:613: first column of the covariance = moment means
+    rel_close(res["mean"].reshape(8, 8)[:, 0], g["A_leg_mean"][:8], rtol=1e-10)
+
+
+@pytest.mark.parametrize("kind,R", [("legendre", 25), ("legendre", 50), ("legendre", 100), ("monomial", 9),
+                                    ("fourier", 32)])
+def test_covariance_sizes_vs_oracle(kind, R):
+    rng = np.random.default_rng(R)
+    steps = orc.level_steps(2, (0.2, 0.02))
+    levels = [orc.synth_level_rows(rng.normal(size=n), steps[l], steps[l - 1] if l else None)
+              for l, n in enumerate([1500, 900])]
+    b = orc.Basis(kind, R, (-3.0, 3.2))
+    want = orc.estimate_covariance(levels, b, chunk_rows=256)
+    res = run_gram(to_struct(b), levels, True, 1000)
+    assert np.array_equal(res["n"], want.n_samples) and np.array_equal(res["n_rm"], want.n_rm_samples)
+    rel_close(res["l_means"], want.l_means, rtol=1e-8, atol_scale=1e-13)
+    rel_close(res["l_vars"], want.l_vars, rtol=1e-8, atol_scale=1e-13)
+    mean_only = run_gram(to_struct(b), levels, False, 1000)
+    assert np.array_equal(mean_only["l_means"], res["l_means"])
+
+
+def test_difference_gram_vs_oracle():
+    rng = np.random.default_rng(5)
+    rows = orc.synth_level_rows(rng.normal(size=1200), 0.05, 0.3)
+    b = orc.Basis("legendre", 14, (-3.0, 3.0))
+    phi = orc.basis_eval(b, rows[:, :, 0])                      # [n, 2, R]
+    good = ~np.isnan(phi).any(axis=(1, 2))
+    d = phi[good, 0] - phi[good, 1]
+    nat = native()
+    acc = nat.LevelAccumulator(1, 14 * 14, dev())
+    x = torch.from_numpy(rows).to(dev()).permute(2, 0, 1)
+    nat.gram_accumulate(to_struct(b), x, acc.level(0), mode=1, want_var=False)
+    a = acc.acc.cpu().numpy()[0]
+    assert a[0] == good.sum() and a[1] == (~good).sum()
+    rel_close(a[2:2 + 196].reshape(14, 14), d.T @ d, rtol=1e-9, atol_scale=1e-14)
+
+
+@pytest.mark.parametrize("size", [5, 15, 25])
+def test_maxent_pieces_match_reference(golden, size):
+    g = golden("maxent")
+    nat = native()
+    domain = tuple(g["domain"])
+    nodes, w = orc.gauss_panels(domain, int(g["n_panels"]))
+    t = "R%d_" % size
+    b = orc.Basis("legendre", size, domain, safe_eval=False)
+    l_mat = torch.from_numpy(g[t + "L"]).to(dev())
+    phi = nat.basis_eval(to_struct(b), torch.from_numpy(nodes).to(dev()), l_mat.shape[0], l_mat)
+    lam = g[t + "lam"]
+    out = nat.maxent_fgh(phi, torch.from_numpy(w).to(dev()), torch.from_numpy(lam).to(dev())).cpu().numpy()
+    R = len(lam)
+    mu = g[t + "mu"]
+    f = np.sum(mu * lam) + out[0]
+    grad = mu - out[1:1 + R]
+    hess = out[1 + R:].reshape(R, R)
+    rel_close(f, g[t + "F"], rtol=1e-10)
+    rel_close(grad, g[t + "g"], rtol=1e-9, atol_scale=1e-12)
+    rel_close(hess, g[t + "H"], rtol=1e-9, atol_scale=1e-13)
+    assert np.array_equal(hess, hess.T)
+    fg = nat.maxent_fgh(phi, torch.from_numpy(w).to(dev()), torch.from_numpy(lam).to(dev()), what=3).cpu().numpy()
+    assert np.array_equal(fg[:1 + R], out[:1 + R])
+
+
+def test_all_samples_masked_counts():
+    nat = native()
+    b = to_struct(orc.Basis("legendre", 4, (0.0, 1.0)))
+    rows = np.full((40, 2, 1), 7.0)
+    acc = nat.LevelAccumulator(1, 4, dev())
+    nat.moments_accumulate(b, torch.from_numpy(rows).to(dev()).permute(2, 0, 1), acc.level(0))
+    a = acc.acc.cpu().numpy()[0]
+    assert a[0] == 0 and a[1] == 40 and np.all(a[2:] == 0)
+
+
+def test_large_run_properties():
+    """Size-independent properties at a size the oracle would not finish quickly: linearity in the sample set
+    (two halves add up), determinism (bitwise repeatable) and moment 0 exactness."""
+    nat = native()
+    gen = torch.Generator(device=dev()).manual_seed(11)
+    n = 3_000_000
+    x = torch.randn(n, generator=gen, device=dev(), dtype=torch.float64)
+    root = torch.sqrt(1e-4 + x.abs())
+    rows = torch.stack([x + 0.05 * root, x + 0.5 * root], dim=1).unsqueeze(2).contiguous()     # [n, 2, 1]
+    b = to_struct(orc.Basis("legendre", 50, (-3.7, 3.7)))
+
+    def run(parts):
+        acc = nat.LevelAccumulator(1, 50, dev())
+        for p in parts:
+            nat.moments_accumulate(b, p.permute(2, 0, 1), acc.level(0))
+        return acc.acc.clone()
+
+    whole = run([rows])
+    again = run([rows])
+    assert torch.equal(whole, again)
+    halves = run([rows[: n // 2], rows[n // 2:]])
+    assert torch.equal(whole[:, :2], halves[:, :2])
+    assert torch.allclose(whole, halves, rtol=1e-11, atol=1e-9)
+    a = whole.cpu().numpy()[0]
+    assert a[0] + a[1] == n and a[2] == 0.0 and a[2 + 50] == 0.0
+    # cross-check a 200k-sample slice against the oracle
+    sl = rows[:200_000].cpu().numpy()
+    want = orc.estimate_moments([np.zeros((1, 2, 1)), sl], orc.Basis("legendre", 50, (-3.7, 3.7)))
+    acc = nat.LevelAccumulator(2, 50, dev())
+    nat.moments_accumulate(b, rows[:200_000].permute(2, 0, 1), acc.level(1))
+    nat.moments_accumulate(b, torch.zeros(1, 1, 1, dtype=torch.float64, device=dev()), acc.level(0))
+    out = acc.finalize()
+    rel_close(out["l_means"][1].cpu().numpy(), want.l_means[1], rtol=1e-10)
+    rel_close(out["l_vars"][1].cpu().numpy(), want.l_vars[1], rtol=1e-10)
