@@ -1,0 +1,77 @@
+"""Sample-axis sharding across GPUs.
+
+The reference has no distributed estimation path at all (its only parallelism is task-parallel sample
+PRODUCTION, ``mlmc/sampling_pool.py``).  Samples of a level are i.i.d. rows and every statistic on the path is a
+sum over rows, so each rank reduces a contiguous row range of every level and ONE small all-reduce (SUM, fp64)
+of the packed level accumulators ``[L, 2 + 2K]`` combines them: counts ride in the same buffer (exact below
+2^53), sums of a plain SUM all-reduce are exact up to fp64 rounding of P <= 8 partials.
+
+One process per GPU, ``torch.distributed`` (NCCL over NVLink/NVSwitch on the box, gloo in the CPU tests) is the
+plumbing.  Sharding is OFF unless ``enable()`` was called (``bench.py`` does under torchrun), so a plain
+single-process script never needs a process group.
+"""
+import os
+
+import torch
+
+_state = {"enabled": False, "rank": 0, "world": 1, "group": None}
+
+
+def enable(rank=None, world=None, group=None):
+    """Turn row sharding on.  rank / world default to the initialised default process group."""
+    import torch.distributed as td
+    if rank is None or world is None:
+        if not td.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        rank, world = td.get_rank(group), td.get_world_size(group)
+    _state.update(enabled=world > 1, rank=int(rank), world=int(world), group=group)
+
+
+def disable():
+    _state.update(enabled=False, rank=0, world=1, group=None)
+
+
+def world_size():
+    return _state["world"] if _state["enabled"] else 1
+
+
+def rank():
+    return _state["rank"] if _state["enabled"] else 0
+
+
+def shard_range(n, rank_=None, world=None):
+    """Contiguous row range [lo, hi) of ``n`` rows owned by a rank: rank r gets [r n / P, (r+1) n / P)."""
+    r = rank() if rank_ is None else rank_
+    p = world_size() if world is None else world
+    return (r * n) // p, ((r + 1) * n) // p
+
+
+def all_reduce_sum(tensor):
+    """In-place SUM all-reduce of a packed accumulator over the active group (no-op when not sharded)."""
+    if world_size() == 1:
+        return tensor
+    import torch.distributed as td
+    td.all_reduce(tensor, op=td.ReduceOp.SUM, group=_state["group"])
+    return tensor
+
+
+def init_from_env(backend=None):
+    """Initialise the default process group from torchrun's environment (RANK / WORLD_SIZE / LOCAL_RANK /
+    MASTER_ADDR / MASTER_PORT) and enable sharding.  Returns (rank, world, local_rank)."""
+    import torch.distributed as td
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank_ = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not td.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        kw = {}
+        if backend == "nccl":
+            kw["device_id"] = torch.device("cuda", local)
+        td.init_process_group(backend=backend, rank=rank_, world_size=world, **kw)
+    if world > 1:
+        enable(rank_, world)
+    return rank_, world, local

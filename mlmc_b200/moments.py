@@ -97,7 +97,7 @@ class Moments:
     def _eval_device(self, value, size):
         """value: CUDA float64 tensor of any shape -> CUDA tensor ``value.shape + (size,)``."""
         flat = value.reshape(-1)
-        out = _native.basis_eval(self.basis_struct(max(size, 1) if size <= self.size else self.size), flat, size)
+        out = _native.basis_eval(self.basis_struct(size), flat, size)
         return out.reshape(tuple(value.shape) + (size,))
 
     def _eval_all(self, value, size):

@@ -1,0 +1,219 @@
+"""Estimation operators -- mirror of ``mlmc/quantity/quantity_estimate.py:6-156`` on the fused CUDA path.
+
+``moments`` / ``covariance`` / ``moment`` build lazy quantities exactly like the reference.  ``estimate_mean``
+recognises them and, instead of materialising the moment (or outer-product) chunks, streams the INPUT quantity's
+device chunks ``[M, n, 2]`` through the fused kernels:
+
+=====================================  ======================================================================
+quantity                               kernels
+=====================================  ======================================================================
+``moments(q, basis)``                  ``mlmcb200_moments_accumulate`` (+ ``sample_mask`` when M > 1)
+``moments(q, TransformedMoments)``     moments sums of the base functions + DMMA Gram of the differences,
+                                       then mean' = L s, sum d'^2 = diag(L G L^T)   (scalar q)
+``covariance(q, basis)`` (scalar q)    ``mlmcb200_gram_accumulate`` (DMMA), sums and sums of squares
+anything else                          generic: chunk evaluated by device ops, reduced by the RAW kernel
+=====================================  ======================================================================
+
+Level sums are reduced across ranks (``mlmc_b200.dist``) when sample sharding is active, then finalised on the
+device (``mlmcb200_finalize_levels``) and copied to the host once.
+"""
+import numpy as np
+import torch
+
+from .. import _native
+from .. import dist as _dist
+from ..moments import TransformedMoments
+from . import quantity as q_mod
+from . import quantity_types as qt
+
+
+def mask_nan_samples(chunk):
+    """Drop samples with a NaN in the fine or the coarse part (quantity_estimate.py:6-14).
+    Accepts a NumPy array or a CUDA tensor ``[M, n, S]``; returns (compacted chunk, number dropped)."""
+    if isinstance(chunk, torch.Tensor):
+        bad = torch.isnan(chunk).any(dim=0).any(dim=1)
+        return chunk[:, ~bad, :], int(bad.sum().item())
+    bad = np.any(np.isnan(chunk), axis=0).any(axis=1)
+    return chunk[..., ~bad, :], np.count_nonzero(bad)
+
+
+def cache_clear():
+    """The reference clears its per-chunk memoisation here (quantity_estimate.py:17-19); this implementation
+    keeps no sample caches besides the storage's resident device copy, which stays valid."""
+    return None
+
+
+# ----------------------------------------------------------------------------------------------------------
+class _MomentsQuantity(q_mod.Quantity):
+    """``moments(quantity, moments_fn)``: lazy quantity that remembers what it is, so that ``estimate_mean`` can fuse."""
+
+    def __init__(self, quantity_type, operation, input_quantity, moments_fn, at_bottom, kind):
+        super().__init__(quantity_type, operation, [input_quantity])
+        self._moments_fn = moments_fn
+        self._at_bottom = at_bottom
+        self._fused_kind = kind          # "moments" | "covariance"
+
+
+def moment(quantity, moments_fn, i=0):
+    """Quantity of a single moment function (quantity_estimate.py:83-93)."""
+    def eval_moment(x):
+        return moments_fn.eval_single_moment(i, value=x)
+    return q_mod.Quantity(quantity_type=quantity.qtype, input_quantities=[quantity], operation=eval_moment)
+
+
+def moments(quantity, moments_fn, mom_at_bottom=True):
+    """Quantity of all moment functions (quantity_estimate.py:96-119).  Chunk ``[M, n, S] -> [M*R, n, S]`` with
+    flat index ``m*R + r`` (``mom_at_bottom``) or ``r*M + m``."""
+    def eval_moments(x):
+        mom = moments_fn.eval_all(x)                                   # [M, n, S, R]
+        mom = mom.permute(0, 3, 1, 2) if mom_at_bottom else mom.permute(3, 0, 1, 2)
+        return mom.reshape((-1,) + tuple(mom.shape[-2:]))
+
+    if mom_at_bottom:
+        moments_array_type = qt.ArrayType(shape=(moments_fn.size,), qtype=qt.ScalarType())
+        moments_qtype = quantity.qtype.replace_scalar(moments_array_type)
+    else:
+        moments_qtype = qt.ArrayType(shape=(moments_fn.size,), qtype=quantity.qtype)
+    return _MomentsQuantity(moments_qtype, eval_moments, quantity, moments_fn, mom_at_bottom, "moments")
+
+
+def covariance(quantity, moments_fn, cov_at_bottom=True):
+    """Quantity of the moment outer products (quantity_estimate.py:122-156): ``[M, n, S] -> [M*R*R, n, S]``."""
+    def eval_cov(x):
+        mom = moments_fn.eval_all(x)                                   # [M, n, S, R]
+        cov = mom.unsqueeze(-1) * mom.unsqueeze(-2)                    # [M, n, S, R, R]
+        cov = cov.permute(0, 3, 4, 1, 2) if cov_at_bottom else cov.permute(3, 4, 0, 1, 2)
+        return cov.reshape((-1,) + tuple(cov.shape[-2:]))
+
+    r = moments_fn.size
+    if cov_at_bottom:
+        moments_qtype = quantity.qtype.replace_scalar(qt.ArrayType(shape=(r, r), qtype=qt.ScalarType()))
+    else:
+        moments_qtype = qt.ArrayType(shape=(r, r), qtype=quantity.qtype)
+    return _MomentsQuantity(moments_qtype, eval_cov, quantity, moments_fn, cov_at_bottom, "covariance")
+
+
+# ----------------------------------------------------------------------------------------------------------
+class _Plan:
+    """How one ``estimate_mean`` call is executed on the device."""
+
+    def __init__(self, quantity):
+        self.quantity = quantity
+        self.kind = "raw"
+        self.inner = quantity
+        self.fn = None
+        self.at_bottom = True
+        if isinstance(quantity, _MomentsQuantity):
+            fn = quantity._moments_fn
+            inner = quantity._input_quantities[0]
+            scalar = inner.size() == 1
+            transformed = isinstance(fn, TransformedMoments)
+            base_ok = fn.base_moments().size <= _native.MAX_MOMENTS
+            if quantity._fused_kind == "moments" and base_ok and not transformed:
+                self.kind = "moments"
+            elif quantity._fused_kind == "moments" and base_ok and transformed and scalar \
+                    and fn.base_moments().size <= 112:
+                self.kind = "transformed"
+            elif quantity._fused_kind == "covariance" and scalar and not transformed and fn.size <= 112:
+                self.kind = "covariance"
+            if self.kind != "raw":
+                self.inner, self.fn, self.at_bottom = inner, fn, quantity._at_bottom
+
+
+def _level_row_ranges(storage, level_ids):
+    """Row range of every level handled by this rank (contiguous shards)."""
+    n_collected = storage.get_n_collected()
+    return {l: _dist.shard_range(int(n_collected[l])) for l in level_ids}
+
+
+def estimate_mean(quantity):
+    """MLMC mean estimator (quantity_estimate.py:22-80) -> ``QuantityMean``."""
+    cache_clear()
+    storage_q = quantity.get_quantity_storage()
+    storage = storage_q._storage
+    level_ids = storage_q.level_ids()
+    n_levels = int(np.max(level_ids)) + 1
+    device = q_mod._device()
+    plan = _Plan(quantity)
+    ranges = _level_row_ranges(storage, level_ids)
+    sharded = _dist.world_size() > 1
+
+    acc = None          # LevelAccumulator of the main statistics
+    gram = None         # transformed moments: Gram of the base differences
+    base_basis = None
+    for level_id in level_ids:
+        lo, hi = ranges[level_id]
+        chunk_id = 0
+        for rows in storage.device_chunks(level_id, device, keep_resident=not sharded,
+                                          row_range=(lo, hi) if sharded else None):
+            if rows.shape[0] == 0:
+                continue
+            x = plan.inner.device_samples(q_mod.DeviceChunk(level_id, rows, chunk_id))
+            chunk_id += 1
+            if plan.kind == "moments":
+                basis = plan.fn.basis_struct()
+                if acc is None:
+                    acc = _native.LevelAccumulator(n_levels, x.shape[0] * basis.size, device)
+                _native.moments_accumulate(basis, x, acc.level(level_id))
+            elif plan.kind == "transformed":
+                base_basis = plan.fn.basis_struct()
+                r0 = base_basis.size
+                if acc is None:
+                    acc = _native.LevelAccumulator(n_levels, r0, device)
+                    gram = _native.LevelAccumulator(n_levels, r0 * r0, device)
+                _native.moments_accumulate(base_basis, x, acc.level(level_id))
+                if x.shape[2] == 2:
+                    _native.gram_accumulate(base_basis, x, gram.level(level_id), mode=1, want_var=False)
+                else:
+                    _native.gram_accumulate(base_basis, x, gram.level(level_id), mode=0, want_var=False)
+            elif plan.kind == "covariance":
+                basis = plan.fn.basis_struct()
+                if acc is None:
+                    acc = _native.LevelAccumulator(n_levels, basis.size * basis.size, device)
+                _native.gram_accumulate(basis, x, acc.level(level_id), mode=0, want_var=True)
+            else:
+                x = x if x.dtype == torch.float64 else x.to(torch.float64)
+                if acc is None:
+                    acc = _native.LevelAccumulator(n_levels, x.shape[0], device)
+                _native.moments_accumulate(_native.RAW_BASIS, x, acc.level(level_id))
+
+    if acc is None:
+        raise Exception("All samples were masked")
+    if sharded:
+        _dist.all_reduce_sum(acc.acc)
+        if gram is not None:
+            _dist.all_reduce_sum(gram.acc)
+
+    if plan.kind == "transformed":
+        acc = _transform_sums(acc, gram, plan.fn, device)
+    out = acc.finalize()
+    packed = torch.cat([out["packed"].reshape(-1), acc.acc[:, :2].reshape(-1)]).cpu().numpy()   # single D2H copy
+    L, K = acc.n_levels, acc.K
+    l_means = packed[:L * K].reshape(L, K)
+    l_vars = packed[L * K:2 * L * K].reshape(L, K)
+    counts = packed[(2 * L + 2) * K:].reshape(L, 2)
+    n_samples = [int(c) for c in counts[:, 0]]
+    n_rm_samples = [int(c) for c in counts[:, 1]]
+    if sum(n_samples) == 0:
+        raise Exception("All samples were masked")
+    if plan.kind in ("moments", "transformed") and not plan.at_bottom:
+        r = plan.fn.size
+        l_means = l_means.reshape(L, -1, r).transpose(0, 2, 1).reshape(L, K)
+        l_vars = l_vars.reshape(L, -1, r).transpose(0, 2, 1).reshape(L, K)
+    elif plan.kind == "covariance" and not plan.at_bottom:
+        pass        # scalar input quantity: both layouts coincide
+    return q_mod.QuantityMean(quantity.qtype, l_means=l_means, l_vars=l_vars, n_samples=n_samples,
+                              n_rm_samples=n_rm_samples)
+
+
+def _transform_sums(acc, gram, fn, device):
+    """Level sums of ``L phi`` from the sums / Gram of the base differences: ``sum d' = L sum d`` and
+    ``sum d'_k^2 = L_k G L_k^T`` (moments.py:256-259 applied under the sums)."""
+    l_mat = fn._matrix_on(device)                         # [R1, R0]
+    r1, r0 = l_mat.shape
+    out = _native.LevelAccumulator(acc.n_levels, r1, device)
+    out.acc[:, :2] = acc.acc[:, :2]
+    out.acc[:, 2:2 + r1] = acc.acc[:, 2:2 + r0] @ l_mat.T
+    g = gram.acc[:, 2:2 + r0 * r0].reshape(-1, r0, r0)
+    out.acc[:, 2 + r1:] = torch.einsum("ki,lij,kj->lk", l_mat, g, l_mat)
+    return out

