@@ -187,6 +187,26 @@ def sample_mask(basis, x):
     return valid
 
 
+_ws_bytes_cache = {}
+
+
+class _on_device:
+    """``torch.cuda.device(dev)`` only when ``dev`` is not already current (the context manager costs ~20 us)."""
+
+    def __init__(self, device):
+        self._ctx = None
+        if device.index is not None and device.index != torch.cuda.current_device():
+            self._ctx = torch.cuda.device(device)
+
+    def __enter__(self):
+        if self._ctx is not None:
+            self._ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+
+
 def moments_accumulate(basis, x, acc_row, valid=None):
     """Add the chunk x [M, n, S] to ``acc_row`` ([2 + 2*M*R] float64, contiguous)."""
     global launch_count
@@ -200,10 +220,14 @@ def moments_accumulate(basis, x, acc_row, valid=None):
     lib = load()
     if M > 1 and valid is None:
         valid = sample_mask(basis, x)
-    with torch.cuda.device(x.device):
-        ws_bytes = lib.mlmcb200_moments_workspace_bytes(basis.size, M)
-        if ws_bytes < 0:
-            raise NativeError("moments workspace: %s" % lib.mlmcb200_last_error().decode())
+    with _on_device(x.device):
+        key = (basis.size, M)
+        ws_bytes = _ws_bytes_cache.get(key)
+        if ws_bytes is None:
+            ws_bytes = lib.mlmcb200_moments_workspace_bytes(basis.size, M)
+            if ws_bytes < 0:
+                raise NativeError("moments workspace: %s" % lib.mlmcb200_last_error().decode())
+            _ws_bytes_cache[key] = ws_bytes
         ws = _workspace(x.device, ws_bytes)
         _check(lib.mlmcb200_moments_accumulate(ctypes.byref(basis), _ptr(x), n, M, sn, ss, sm, has_coarse,
                                                _ptr(valid), _ptr(acc_row), _ptr(ws), ws.numel(), _stream()),

@@ -56,10 +56,31 @@ __device__ __forceinline__ double map_to_ref(const mlmcb200_basis_t& b, double v
     return t;
 }
 
+template <bool LOG>
+__device__ __forceinline__ double map_to_ref_t(const mlmcb200_basis_t& b, double v) {
+    if (LOG) v = log(v);
+    double t = __dadd_rn(__dmul_rn(__dsub_rn(v, b.shift), b.scale), b.ref_lo);
+    if (b.is_clip && !(t >= b.ref_lo && t <= b.ref_hi)) t = __longlong_as_double(0x7ff8000000000000LL);
+    return t;
+}
+
 // numpy legvander step, exactly: (p1 * t * (2i-1) - p0 * (i-1)) / i
 __device__ __forceinline__ double legendre_step_exact(double p1, double p0, double t, int i) {
     return __ddiv_rn(__dsub_rn(__dmul_rn(__dmul_rn(p1, t), (double)(2 * i - 1)), __dmul_rn(p0, (double)(i - 1))),
                      (double)i);
+}
+
+// Unclipped Legendre far outside the domain: numpy's recurrence overflows to inf and then gives inf - inf = NaN two
+// steps later; replay it exactly (rare path, kept out of line so that the hot kernels stay small).
+static __device__ __noinline__ bool legendre_table_finite(double t, int size) {
+    double p0 = 1.0, p1 = t;
+    for (int i = 2; i < size; ++i) {
+        const double p2 = legendre_step_exact(p1, p0, t, i);
+        if (isnan(p2)) return false;
+        p0 = p1;
+        p1 = p2;
+    }
+    return true;
 }
 
 // Does the moment vector of the mapped value t contain no NaN?  (mask_nan_samples,
@@ -69,15 +90,7 @@ __device__ __forceinline__ bool moments_finite(const mlmcb200_basis_t& b, double
     if (b.kind == MLMCB200_FOURIER) return b.size == 1 || isfinite(t);   // column 0 is the literal 1
     if (!isfinite(t)) return false;                   // numpy: v[0] = t*0 + 1 is NaN for NaN and +-inf
     if (b.kind == MLMCB200_MONOMIAL || b.is_clip || fabs(t) <= 4.0) return true;
-    // unclipped Legendre far outside the domain: overflow gives inf - inf = NaN two steps after the first inf
-    double p0 = 1.0, p1 = t;
-    for (int i = 2; i < b.size; ++i) {
-        double p2 = legendre_step_exact(p1, p0, t, i);
-        if (isnan(p2)) return false;
-        p0 = p1;
-        p1 = p2;
-    }
-    return true;
+    return legendre_table_finite(t, b.size);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

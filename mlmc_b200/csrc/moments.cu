@@ -65,7 +65,30 @@ __device__ __forceinline__ void accumulate(double* __restrict__ col_sum, double*
     *col_sq = qa + qb;
 }
 
-template <int KIND, bool COARSE, int S>
+// raw (fine, coarse) values of the S samples of one tile owned by this thread; out-of-range samples read NaN
+template <bool COARSE, int S>
+__device__ __forceinline__ void load_tile(const MomentsArgs& a, const double* base_f, int64_t n0, int TN, bool active,
+                                          double (&xf)[S], double (&xc)[S]) {
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int64_t n = n0 + (int64_t)s * TN;
+        xf[s] = qnan;
+        xc[s] = qnan;
+        if (active && n < a.n) {
+            if (COARSE && a.vec2) {
+                const double2 v = __ldcs(reinterpret_cast<const double2*>(a.pairs) + n);
+                xf[s] = v.x;
+                xc[s] = v.y;
+            } else {
+                xf[s] = __ldcs(base_f + n * a.stride_n);
+                if (COARSE) xc[s] = __ldcs(base_f + n * a.stride_n + a.stride_side);
+            }
+        }
+    }
+}
+
+template <int KIND, bool COARSE, bool LOG, int S>
 __global__ void __launch_bounds__(kThreads)
 moments_acc_kernel(const MomentsArgs a) {
     extern __shared__ double sm[];
@@ -102,6 +125,10 @@ moments_acc_kernel(const MomentsArgs a) {
 
     unsigned cnt_ok = 0, cnt_rm = 0;
 
+    // software pipeline: the raw values of the NEXT tile are in flight while the current tile is reduced
+    double xf[S], xc[S];
+    load_tile<COARSE, S>(a, base_f, (int64_t)blockIdx.y * tile_n + tn, TN, active, xf, xc);
+
     for (int64_t tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
         double tf[S], tc[S];
         bool ok[S];
@@ -110,29 +137,18 @@ moments_acc_kernel(const MomentsArgs a) {
         for (int s = 0; s < S; ++s) {
             const int64_t n = n0 + (int64_t)s * TN;
             const bool in = active && n < a.n;
-            double xf = 0.0, xc = 0.0;
-            if (in) {
-                if (COARSE && a.vec2) {
-                    const double2 v = __ldcs(reinterpret_cast<const double2*>(a.pairs) + n);
-                    xf = v.x;
-                    xc = v.y;
-                } else {
-                    xf = __ldcs(base_f + n * a.stride_n);
-                    if (COARSE) xc = __ldcs(base_f + n * a.stride_n + a.stride_side);
-                }
-            }
-            bool good = in;
             if (KIND == MLMCB200_RAW) {
-                tf[s] = xf;
-                tc[s] = xc;
+                tf[s] = xf[s];
+                tc[s] = xc[s];
             } else {
-                tf[s] = map_to_ref(a.basis, xf);
-                tc[s] = COARSE ? map_to_ref(a.basis, xc) : 0.0;
+                tf[s] = map_to_ref_t<LOG>(a.basis, xf[s]);
+                tc[s] = COARSE ? map_to_ref_t<LOG>(a.basis, xc[s]) : 0.0;
             }
+            bool good;
             if (a.valid != nullptr) {
                 good = in && a.valid[n] != 0;
-            } else if (in) {
-                good = moments_finite(a.basis, tf[s]) && (!COARSE || moments_finite(a.basis, tc[s]));
+            } else {
+                good = in && moments_finite(a.basis, tf[s]) && (!COARSE || moments_finite(a.basis, tc[s]));
             }
             if (count_here && in) {
                 cnt_ok += good ? 1u : 0u;
@@ -144,6 +160,8 @@ moments_acc_kernel(const MomentsArgs a) {
             }
             ok[s] = good;
         }
+        if (tile + gridDim.y < n_tiles)
+            load_tile<COARSE, S>(a, base_f, (tile + gridDim.y) * tile_n + tn, TN, active, xf, xc);
 
         if (KIND == MLMCB200_RAW) {
             accumulate<COARSE, S>(sum_col, sq_col, tf, tc);
@@ -289,14 +307,25 @@ moments_acc_kernel(const MomentsArgs a) {
     }
 }
 
-// acc[j] += sum_b partial[b][j], fixed order
+// acc[j] += sum_b partial[b][j] in a fixed order (bitwise reproducible).  One warp per output when there are many
+// partials (lanes take b = lane, lane + 32, ... then a shuffle tree), one thread per output otherwise.
 __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n_partials, int64_t stride,
-                                       int64_t len, double* __restrict__ acc) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= len) return;
-    double s = 0.0;
-    for (int b = 0; b < n_partials; ++b) s += partial[(int64_t)b * stride + j];
-    acc[j] += s;
+                                       int64_t len, double* __restrict__ acc, int warp_per_output) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (warp_per_output) {
+        const int64_t j = gid >> 5;
+        const int lane = threadIdx.x & 31;
+        if (j >= len) return;
+        double s = 0.0;
+        for (int b = lane; b < n_partials; b += 32) s += partial[(int64_t)b * stride + j];
+        s = warp_sum(s);
+        if (lane == 0) acc[j] += s;
+    } else {
+        if (gid >= len) return;
+        double s = 0.0;
+        for (int b = 0; b < n_partials; ++b) s += partial[(int64_t)b * stride + gid];
+        acc[gid] += s;
+    }
 }
 
 __global__ void sample_mask_kernel(const mlmcb200_basis_t basis, const double* __restrict__ pairs, int64_t n,
@@ -349,8 +378,10 @@ __global__ void finalize_levels_kernel(const double* __restrict__ acc, int64_t a
 int launch_reduce_partials(const double* partial, int n_partials, int64_t stride, int64_t len, double* acc,
                            cudaStream_t st) {
     const int threads = 256;
-    reduce_partials_kernel<<<(unsigned)((len + threads - 1) / threads), threads, 0, st>>>(partial, n_partials,
-                                                                                          stride, len, acc);
+    const int wpo = n_partials >= 32 && len <= (1 << 20) ? 1 : 0;
+    const int64_t total = wpo ? len * 32 : len;
+    reduce_partials_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(partial, n_partials,
+                                                                                            stride, len, acc, wpo);
     MB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -386,13 +417,25 @@ int plan_moments(int kind, int size, int n_comp, int64_t n, Plan* p) {
     return 0;
 }
 
-template <int KIND, bool COARSE, int S>
-int launch_moments(const MomentsArgs& a, const Plan& p, cudaStream_t st) {
-    auto kern = moments_acc_kernel<KIND, COARSE, S>;
-    MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+template <int KIND, bool COARSE, bool LOG, int S>
+int launch_moments(const MomentsArgs& a, Plan p, cudaStream_t st) {
+    auto kern = moments_acc_kernel<KIND, COARSE, LOG, S>;
+    // resident CTAs per SM for this variant and shared-memory size (registers may bind before shared memory);
+    // the sample-partition dimension of the grid is sized to exactly one resident wave
+    static thread_local size_t cached_smem = 0;
+    static thread_local int cached_ctas = 0;
+    if (cached_smem != p.smem || cached_ctas == 0) {
+        MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        int ctas = 0;
+        MB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, kThreads, p.smem));
+        cached_ctas = ctas > 0 ? ctas : 1;
+        cached_smem = p.smem;
+    }
+    const unsigned wave = (unsigned)((sm_count() * cached_ctas + p.grid.x - 1) / p.grid.x);
+    if (p.grid.y > wave) p.grid.y = wave;
     kern<<<p.grid, kThreads, p.smem, st>>>(a);
     MB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return (int)p.grid.y;
 }
 
 }  // namespace
@@ -439,18 +482,25 @@ extern "C" int mlmcb200_moments_accumulate(const mlmcb200_basis_t* basis, const 
     a.partial = static_cast<double*>(workspace);
     a.partial_stride = stride;
 
-    int rc = -1;
-#define MB_DISPATCH(KIND, S)                                                  \
-    rc = has_coarse ? launch_moments<KIND, true, S>(a, p, st) : launch_moments<KIND, false, S>(a, p, st)
+    int rc = -1;     // > 0: number of partial vectors written
+#define MB_DISPATCH(KIND, S)                                                                               \
+    rc = basis->is_log                                                                                      \
+             ? (has_coarse ? launch_moments<KIND, true, true, S>(a, p, st)                                  \
+                           : launch_moments<KIND, false, true, S>(a, p, st))                                \
+             : (has_coarse ? launch_moments<KIND, true, false, S>(a, p, st)                                 \
+                           : launch_moments<KIND, false, false, S>(a, p, st))
     switch (basis->kind) {
-        case MLMCB200_RAW: MB_DISPATCH(MLMCB200_RAW, 8); break;
+        case MLMCB200_RAW:
+            rc = has_coarse ? launch_moments<MLMCB200_RAW, true, false, 8>(a, p, st)
+                            : launch_moments<MLMCB200_RAW, false, false, 8>(a, p, st);
+            break;
         case MLMCB200_LEGENDRE: MB_DISPATCH(MLMCB200_LEGENDRE, 8); break;
         case MLMCB200_MONOMIAL: MB_DISPATCH(MLMCB200_MONOMIAL, 8); break;
         case MLMCB200_FOURIER: MB_DISPATCH(MLMCB200_FOURIER, 4); break;
     }
 #undef MB_DISPATCH
-    if (rc != 0) return rc;
-    return launch_reduce_partials(a.partial, (int)p.grid.y, stride, stride, acc, st);
+    if (rc <= 0) return rc < 0 ? rc : -1;
+    return launch_reduce_partials(a.partial, rc, stride, stride, acc, st);
 }
 
 extern "C" int mlmcb200_sample_mask(const mlmcb200_basis_t* basis, const double* pairs, int64_t n, int32_t n_comp,

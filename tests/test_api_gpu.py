@@ -212,14 +212,14 @@ def test_vector_quantity_and_dag(golden):
     rel_close(qe.estimate_mean(vec / 2 - vec).mean, -0.5 * m1, rtol=1e-12)
     # indexing, ufuncs, selection
     comp = vec[2, 0]
-    rel_close(qe.estimate_mean(comp).mean, m1.reshape(-1)[2], rtol=1e-12)
+    rel_close(np.squeeze(qe.estimate_mean(comp).mean), m1.reshape(-1)[2], rtol=1e-12)
     want = orc.estimate_mean(levels, lambda x: np.sin(x)).mean
     rel_close(qe.estimate_mean(np.sin(vec)).mean.reshape(-1), want, rtol=1e-11)
     sel = vec.select(vec < 1.0)
     want = orc.estimate_mean([lv[(lv[:, :1 if i == 0 else 2, :] < 1.0).all(axis=(1, 2))] for i, lv in enumerate(levels)]).mean
     rel_close(qe.estimate_mean(sel).mean.reshape(-1), want, rtol=1e-11)
     one = qe.moment(comp, fn, 2)
-    rel_close(qe.estimate_mean(one).mean, qe.estimate_mean(qe.moments(comp, fn)).mean[2], rtol=1e-11)
+    rel_close(np.squeeze(qe.estimate_mean(one).mean), qe.estimate_mean(qe.moments(comp, fn)).mean[2], rtol=1e-11)
 
 
 def test_all_samples_masked_raises():
