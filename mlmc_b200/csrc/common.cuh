@@ -34,7 +34,7 @@ int check_basis(const mlmcb200_basis_t* b);
 // Coefficients of the monic Legendre recurrence W_i = t W_{i-1} - kLegCoef[i] W_{i-2}, P_i = kLegAlpha[i] W_i
 // (gen_tables.py).  Statically initialised __constant__ data, one copy per translation unit (no -rdc).
 #include "legendre_tables.inc"
-static __constant__ double kLegCoef[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_COEF_INIT;
+static __constant__ double kLegCoef[MLMCB200_MAX_MOMENTS + 8] = MLMCB200_LEG_COEF_INIT;   // padded: prefetch
 static __constant__ double kLegAlpha[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_ALPHA_INIT;
 // P_i = (kLegA[i] t) P_{i-1} - kLegB[i] P_{i-2}: the un-scaled recurrence with correctly rounded ratios
 static __constant__ double kLegA[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_A_INIT;

@@ -165,66 +165,70 @@ moments_acc_kernel(const MomentsArgs a) {
 
         if (KIND == MLMCB200_RAW) {
             accumulate<COARSE, S>(sum_col, sq_col, tf, tc);
-        } else if (KIND == MLMCB200_LEGENDRE) {
-            // monic recurrence W_0 = 1, W_1 = t, W_i = t W_{i-1} - e_i W_{i-2}  (P_i = g_i W_i, applied in the
-            // epilogue); the e_i product is done in place and is off the critical path.
-            double f0[S], f1[S], c0[S], c1[S];
+        } else if (KIND == MLMCB200_LEGENDRE || KIND == MLMCB200_MONOMIAL) {
+            // Two ping-pong register sets hold moment k of the S samples: even k in (fb, cb), odd k in (fa, ca).
+            //   Legendre (monic): W_k = t W_{k-1} - e_k W_{k-2}, the e_k product in place on the older set
+            //   Monomial        : t^k = t^{k-1} t
+            // Software pipeline: the reduction of moment k is issued AFTER the recurrence of moment k+1, so the
+            // dependent tail of one (add tree, smem update) overlaps the independent FP64 work of the other.
+            double fa[S], fb[S], ca[S], cb[S];
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-                f0[s] = c0[s] = ok[s] ? 1.0 : 0.0;
-                f1[s] = tf[s];
-                c1[s] = tc[s];
+                fb[s] = cb[s] = ok[s] ? 1.0 : 0.0;
+                fa[s] = tf[s];
+                ca[s] = tc[s];
             }
-            accumulate<COARSE, S>(sum_col, sq_col, f0, c0);
-            if (R > 1) accumulate<COARSE, S>(sum_col + T, sq_col + T, f1, c1);
-            int i = 2;
-            for (; i + 1 < R; i += 2) {
-                const double ea = kLegCoef[i], eb = kLegCoef[i + 1];
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    f0[s] *= ea;
-                    if (COARSE) c0[s] *= ea;
+            accumulate<COARSE, S>(sum_col, sq_col, fb, cb);                       // moment 0
+#define MB_REC(DST_F, DST_C, SRC_F, SRC_C, E)                                   \
+    _Pragma("unroll") for (int s = 0; s < S; ++s) {                              \
+        if (KIND == MLMCB200_LEGENDRE) {                                         \
+            DST_F[s] *= (E);                                                     \
+            if (COARSE) DST_C[s] *= (E);                                         \
+        }                                                                        \
+    }                                                                            \
+    _Pragma("unroll") for (int s = 0; s < S; ++s) {                              \
+        if (KIND == MLMCB200_LEGENDRE) {                                         \
+            DST_F[s] = fma(tf[s], SRC_F[s], -DST_F[s]);                          \
+            if (COARSE) DST_C[s] = fma(tc[s], SRC_C[s], -DST_C[s]);              \
+        } else {                                                                 \
+            DST_F[s] = SRC_F[s] * tf[s];                                         \
+            if (COARSE) DST_C[s] = SRC_C[s] * tc[s];                             \
+        }                                                                        \
+    }
+#define MB_ACC(K, VF, VC) accumulate<COARSE, S>(sum_col + (K) * T, sq_col + (K) * T, VF, VC)
+            int i = 2;                                                            // next moment to generate
+            if (R > 5) {
+                double e0 = kLegCoef[2], e1 = kLegCoef[3], e2 = kLegCoef[4], e3 = kLegCoef[5];
+                for (; i + 3 < R; i += 4) {
+                    // coefficients of the NEXT group are fetched now (the table is padded past MAX_MOMENTS)
+                    const double n0 = kLegCoef[i + 4], n1 = kLegCoef[i + 5], n2 = kLegCoef[i + 6], n3 = kLegCoef[i + 7];
+                    MB_REC(fb, cb, fa, ca, e0)
+                    MB_ACC(i - 1, fa, ca);
+                    MB_REC(fa, ca, fb, cb, e1)
+                    MB_ACC(i, fb, cb);
+                    MB_REC(fb, cb, fa, ca, e2)
+                    MB_ACC(i + 1, fa, ca);
+                    MB_REC(fa, ca, fb, cb, e3)
+                    MB_ACC(i + 2, fb, cb);
+                    e0 = n0; e1 = n1; e2 = n2; e3 = n3;
                 }
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    f0[s] = fma(tf[s], f1[s], -f0[s]);
-                    if (COARSE) c0[s] = fma(tc[s], c1[s], -c0[s]);
-                }
-                accumulate<COARSE, S>(sum_col + i * T, sq_col + i * T, f0, c0);
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    f1[s] *= eb;
-                    if (COARSE) c1[s] *= eb;
-                }
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    f1[s] = fma(tf[s], f0[s], -f1[s]);
-                    if (COARSE) c1[s] = fma(tc[s], c0[s], -c1[s]);
-                }
-                accumulate<COARSE, S>(sum_col + (i + 1) * T, sq_col + (i + 1) * T, f1, c1);
             }
-            if (i < R) {
-                const double ea = kLegCoef[i];
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    f0[s] = fma(tf[s], f1[s], -(f0[s] * ea));
-                    if (COARSE) c0[s] = fma(tc[s], c1[s], -(c0[s] * ea));
+            for (; i < R; ++i) {                                                 // remainder, one moment at a time
+                const double e = kLegCoef[i];
+                if ((i & 1) == 0) {
+                    MB_REC(fb, cb, fa, ca, e)
+                    MB_ACC(i - 1, fa, ca);
+                } else {
+                    MB_REC(fa, ca, fb, cb, e)
+                    MB_ACC(i - 1, fb, cb);
                 }
-                accumulate<COARSE, S>(sum_col + i * T, sq_col + i * T, f0, c0);
             }
-        } else if (KIND == MLMCB200_MONOMIAL) {
-            double pf[S], pc[S];
-#pragma unroll
-            for (int s = 0; s < S; ++s) pf[s] = pc[s] = ok[s] ? 1.0 : 0.0;
-            accumulate<COARSE, S>(sum_col, sq_col, pf, pc);
-            for (int i = 1; i < R; ++i) {
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    pf[s] *= tf[s];
-                    if (COARSE) pc[s] *= tc[s];
-                }
-                accumulate<COARSE, S>(sum_col + i * T, sq_col + i * T, pf, pc);
+            if (R > 1) {                                                          // the last moment is still pending
+                if ((R - 1) & 1) MB_ACC(R - 1, fa, ca);
+                else MB_ACC(R - 1, fb, cb);
             }
+#undef MB_REC
+#undef MB_ACC
         } else {  // FOURIER: columns 1, cos t, sin t, cos 2t, sin 2t, ... by exact-angle rotation
             double cf1[S], sf1[S], cc1[S], sc1[S], cfk[S], sfk[S], cck[S], sck[S];
 #pragma unroll

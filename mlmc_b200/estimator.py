@@ -67,8 +67,9 @@ class Estimate:
         reg_vars = raw_vars.copy()
         n_levels, n_moments = raw_vars.shape
         if n_levels >= 3 and n_moments > 1:
-            cols = [m for m in range(1, n_moments) if not np.allclose(raw_vars[:, m], 0)]
-            if cols:
+            cols = np.flatnonzero(~np.isclose(raw_vars, 0).all(axis=0))
+            cols = cols[cols >= 1]
+            if len(cols):
                 log_h = np.log(np.asarray(sim_steps, dtype=float)[1:])
                 design = np.column_stack([np.ones(n_levels - 1), log_h, log_h ** 2])
                 coef = np.linalg.lstsq(design, np.log(raw_vars[1:][:, cols]), rcond=None)[0]

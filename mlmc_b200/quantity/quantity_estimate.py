@@ -141,41 +141,39 @@ def estimate_mean(quantity):
     acc = None          # LevelAccumulator of the main statistics
     gram = None         # transformed moments: Gram of the base differences
     base_basis = None
-    for level_id in level_ids:
-        lo, hi = ranges[level_id]
-        chunk_id = 0
-        for rows in storage.device_chunks(level_id, device, keep_resident=not sharded,
-                                          row_range=(lo, hi) if sharded else None):
-            if rows.shape[0] == 0:
-                continue
-            x = plan.inner.device_samples(q_mod.DeviceChunk(level_id, rows, chunk_id))
-            chunk_id += 1
-            if plan.kind == "moments":
-                basis = plan.fn.basis_struct()
-                if acc is None:
-                    acc = _native.LevelAccumulator(n_levels, x.shape[0] * basis.size, device)
-                _native.moments_accumulate(basis, x, acc.level(level_id))
-            elif plan.kind == "transformed":
-                base_basis = plan.fn.basis_struct()
-                r0 = base_basis.size
-                if acc is None:
-                    acc = _native.LevelAccumulator(n_levels, r0, device)
-                    gram = _native.LevelAccumulator(n_levels, r0 * r0, device)
-                _native.moments_accumulate(base_basis, x, acc.level(level_id))
-                if x.shape[2] == 2:
-                    _native.gram_accumulate(base_basis, x, gram.level(level_id), mode=1, want_var=False)
-                else:
-                    _native.gram_accumulate(base_basis, x, gram.level(level_id), mode=0, want_var=False)
-            elif plan.kind == "covariance":
-                basis = plan.fn.basis_struct()
-                if acc is None:
-                    acc = _native.LevelAccumulator(n_levels, basis.size * basis.size, device)
-                _native.gram_accumulate(basis, x, acc.level(level_id), mode=0, want_var=True)
+    chunk_id = 0
+    for level_id, rows in storage.device_chunks(level_ids, device, keep_resident=not sharded,
+                                                row_ranges=ranges if sharded else None):
+        if rows.shape[0] == 0:
+            continue
+        x = plan.inner.device_samples(q_mod.DeviceChunk(level_id, rows, chunk_id))
+        chunk_id += 1
+        if plan.kind == "moments":
+            basis = plan.fn.basis_struct()
+            if acc is None:
+                acc = _native.LevelAccumulator(n_levels, x.shape[0] * basis.size, device)
+            _native.moments_accumulate(basis, x, acc.level(level_id))
+        elif plan.kind == "transformed":
+            base_basis = plan.fn.basis_struct()
+            r0 = base_basis.size
+            if acc is None:
+                acc = _native.LevelAccumulator(n_levels, r0, device)
+                gram = _native.LevelAccumulator(n_levels, r0 * r0, device)
+            _native.moments_accumulate(base_basis, x, acc.level(level_id))
+            if x.shape[2] == 2:
+                _native.gram_accumulate(base_basis, x, gram.level(level_id), mode=1, want_var=False)
             else:
-                x = x if x.dtype == torch.float64 else x.to(torch.float64)
-                if acc is None:
-                    acc = _native.LevelAccumulator(n_levels, x.shape[0], device)
-                _native.moments_accumulate(_native.RAW_BASIS, x, acc.level(level_id))
+                _native.gram_accumulate(base_basis, x, gram.level(level_id), mode=0, want_var=False)
+        elif plan.kind == "covariance":
+            basis = plan.fn.basis_struct()
+            if acc is None:
+                acc = _native.LevelAccumulator(n_levels, basis.size * basis.size, device)
+            _native.gram_accumulate(basis, x, acc.level(level_id), mode=0, want_var=True)
+        else:
+            x = x if x.dtype == torch.float64 else x.to(torch.float64)
+            if acc is None:
+                acc = _native.LevelAccumulator(n_levels, x.shape[0], device)
+            _native.moments_accumulate(_native.RAW_BASIS, x, acc.level(level_id))
 
     if acc is None:
         raise Exception("All samples were masked")

@@ -38,7 +38,7 @@ class SampleStorage(metaclass=ABCMeta):
     """Abstract storage (``mlmc/sample_storage.py:9-131``)."""
 
     #: rows per streamed device chunk (x 16*M bytes); whole level if it is already resident
-    device_chunk_bytes = 256 << 20
+    device_chunk_bytes = 32 << 20
     #: fraction of free HBM a resident copy of all levels may take
     resident_fraction = 0.6
 
@@ -137,7 +137,7 @@ class SampleStorage(metaclass=ABCMeta):
         """Rows as a (preferably pinned) torch CPU tensor; subclasses with pinned storage override."""
         return torch.from_numpy(np.ascontiguousarray(self.level_rows(level_id)))
 
-    def device_rows(self, level_id, device, keep_resident=True):
+    def device_rows(self, level_id, device, keep_resident=True, free_bytes=None):
         """Whole level as one CUDA tensor ``[N, 2, M]`` (uploaded once, cached) or None if it should be streamed."""
         key = (level_id, str(device))
         cache = self._resident()
@@ -145,10 +145,13 @@ class SampleStorage(metaclass=ABCMeta):
         n_now = len(self.level_rows(level_id))
         if rows is not None and rows.shape[0] == n_now:
             return rows
+        if self.resident_fraction <= 0:
+            return None
         host = self._host_tensor(level_id)
         n_bytes = host.numel() * 8
-        free, _total = torch.cuda.mem_get_info(device)
-        if n_bytes > self.resident_fraction * free:
+        if free_bytes is None:
+            free_bytes, _total = torch.cuda.mem_get_info(device)
+        if n_bytes > self.resident_fraction * free_bytes:
             return None
         rows = torch.empty(host.shape, dtype=torch.float64, device=device)
         rows.copy_(host, non_blocking=True)
@@ -156,55 +159,100 @@ class SampleStorage(metaclass=ABCMeta):
             cache[key] = rows
         return rows
 
-    def device_chunks(self, level_id, device, keep_resident=True, row_range=None):
-        """Yield CUDA tensors ``[n, 2, M]`` covering the level (or ``row_range = (start, stop)`` of it).
+    def device_chunks(self, level_ids, device, keep_resident=True, row_ranges=None):
+        """Yield ``(level_id, rows)`` with ``rows`` a CUDA tensor ``[n, 2, M]``, covering the given levels (or
+        ``row_ranges[level_id] = (start, stop)`` of them) in level order.
 
-        Resident / small levels: a single tensor.  Otherwise chunks of ``device_chunk_bytes`` are copied from
-        pinned host memory on a side stream into two alternating device buffers; the consumer's kernels on the
-        current stream overlap the next copy."""
-        rows = self.device_rows(level_id, device, keep_resident) if row_range is None or keep_resident else None
-        if rows is not None:
-            yield rows if row_range is None else rows[row_range[0]:row_range[1]]
-            return
-        host = self._host_tensor(level_id)
-        start, stop = (0, host.shape[0]) if row_range is None else row_range
-        yield from stream_rows(host[start:stop], device, self.device_chunk_bytes)
+        Levels that are (or may become) resident in HBM are yielded whole.  Everything else is copied from
+        pinned host memory in ``device_chunk_bytes`` pieces on a side stream into two alternating device buffers,
+        ONE pipeline across all levels, so the copy engine never idles between levels and the consumer's kernels
+        on the current stream overlap the next copy."""
+        free_bytes = None
+        if self.resident_fraction > 0 and keep_resident:
+            free_bytes, _total = torch.cuda.mem_get_info(device)
+        pending = []          # (level_id, host rows) still to be streamed, in order
+        for level_id in level_ids:
+            rng = None if row_ranges is None else row_ranges[level_id]
+            rows = None
+            if keep_resident:
+                was_cached = (level_id, str(device)) in self._resident()
+                rows = self.device_rows(level_id, device, True, free_bytes)
+                if rows is not None and not was_cached and free_bytes is not None:
+                    free_bytes -= rows.numel() * 8
+            if rows is not None:
+                if pending:
+                    yield from stream_levels(pending, device, self.device_chunk_bytes)
+                    pending = []
+                yield level_id, (rows if rng is None else rows[rng[0]:rng[1]])
+            else:
+                host = self._host_tensor(level_id)
+                pending.append((level_id, host if rng is None else host[rng[0]:rng[1]]))
+        if pending:
+            yield from stream_levels(pending, device, self.device_chunk_bytes)
 
 
-def stream_rows(host, device, chunk_bytes=256 << 20):
-    """Double-buffered H2D streaming of host rows ``[N, 2, M]`` (pinned => truly asynchronous)."""
-    n = host.shape[0]
-    if n == 0:
+def stream_levels(segments, device, chunk_bytes=32 << 20):
+    """Double-buffered H2D streaming of ``[(level_id, host rows [N, 2, M]), ...]`` (pinned => truly asynchronous).
+    Yields ``(level_id, device rows)``; a yielded tensor stays valid until the second next ``next()``."""
+    pieces = []
+    max_elems = 0
+    for level_id, host in segments:
+        n = host.shape[0]
+        if n == 0:
+            continue
+        row_elems = host[0].numel()
+        chunk_rows = max(1, min(n, chunk_bytes // (8 * row_elems)))
+        for lo in range(0, n, chunk_rows):
+            hi = min(lo + chunk_rows, n)
+            pieces.append((level_id, host, lo, hi))
+            max_elems = max(max_elems, (hi - lo) * row_elems)
+    if not pieces:
         return
-    row_bytes = host[0].numel() * 8
-    chunk_rows = max(1, min(n, chunk_bytes // row_bytes))
     compute = torch.cuda.current_stream(device)
-    copy_stream = torch.cuda.Stream(device)
-    bufs = [torch.empty((chunk_rows,) + tuple(host.shape[1:]), dtype=torch.float64, device=device) for _ in range(2)]
+    copy_stream = _copy_stream(device)
+    bufs = [torch.empty(max_elems, dtype=torch.float64, device=device) for _ in range(2)]
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
-    starts = list(range(0, n, chunk_rows))
+    copy_stream.wait_stream(compute)          # the buffers may be recycled memory still in use on the compute stream
 
     def issue(k):
         b = k % 2
-        lo = starts[k]
-        hi = min(lo + chunk_rows, n)
+        level_id, host, lo, hi = pieces[k]
+        view = bufs[b][: (hi - lo) * host[0].numel()].view((hi - lo,) + tuple(host.shape[1:]))
         with torch.cuda.stream(copy_stream):
             if k >= 2:
                 copy_stream.wait_event(consumed[b])
-            bufs[b][: hi - lo].copy_(host[lo:hi], non_blocking=True)
+            view.copy_(host[lo:hi], non_blocking=True)
             copied[b].record(copy_stream)
-        return hi - lo
+        return level_id, view
 
-    sizes = {0: issue(0)}
-    for k in range(len(starts)):
-        if k + 1 < len(starts):
-            sizes[k + 1] = issue(k + 1)
+    nxt = issue(0)
+    for k in range(len(pieces)):
+        cur = nxt
+        if k + 1 < len(pieces):
+            nxt = issue(k + 1)
         b = k % 2
         compute.wait_event(copied[b])
-        yield bufs[b][: sizes[k]]
+        yield cur
         consumed[b].record(compute)
-    compute.synchronize()      # buffers are freed on return: make sure the last consumer is done
+    for buf in bufs:                           # allocated on the compute stream, written on the copy stream
+        buf.record_stream(copy_stream)
+
+
+_copy_streams = {}
+
+
+def _copy_stream(device):
+    key = str(device)
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device)
+    return _copy_streams[key]
+
+
+def stream_rows(host, device, chunk_bytes=32 << 20):
+    """Single-level convenience wrapper of ``stream_levels`` yielding the device rows only."""
+    for _level, rows in stream_levels([(0, host)], device, chunk_bytes):
+        yield rows
 
 
 class Memory(SampleStorage):
