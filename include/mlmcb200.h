@@ -125,8 +125,10 @@ int mlmcb200_maxent_fgh(const double* phi, int64_t ld, const double* w, const do
                         int64_t n_nodes, int32_t size, int32_t what, double* out,
                         void* workspace, int64_t workspace_bytes, void* stream);
 
-/* FP64 pipe micro-benchmarks used by bench.py for the roofline denominators (not on the data path):
- * sustained DFMA (kind 0) or DMMA m8n8k4 (kind 1) throughput in FLOP/s (FMA = 2) measured with CUDA events. */
+/* FP64 pipe micro-benchmarks used by bench.py for the roofline denominators (not on the data path).
+ * kind & 15: 0 = DFMA with two loop-invariant operands, 1 = DMMA m8n8k4, 2 = DFMA with three distinct register
+ * operands: sustained throughput in FLOP/s (FMA = 2), CUDA events; 3 = latency of a dependent DFMA in SM cycles.
+ * kind >> 4: resident warps per SM to run with (0 = full occupancy). */
 int mlmcb200_fp64_peak(int32_t kind, double* flops_per_s, void* stream);
 
 #ifdef __cplusplus

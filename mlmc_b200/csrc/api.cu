@@ -55,6 +55,48 @@ __global__ void dfma_peak_kernel(double* sink, int iters, double seed) {
     if (r == 123.456) sink[0] = r;
 }
 
+// 8 independent chains, three DISTINCT register operands per DFMA (what a recurrence looks like)
+__global__ void dfma3_peak_kernel(double* sink, int iters, double seed) {
+    double a[8], b[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = seed + i;
+        b[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+        c[i] = 1e-9 * (i + 1);
+    }
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fma(a[i], b[i], c[i]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) c[i] = fma(c[i], b[i], a[i]);
+        }
+    }
+    double r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r += a[i] + c[i];
+    if (r == 123.456) sink[0] = r;
+}
+
+// one dependent DFMA chain per thread: cycles per dependent instruction
+__global__ void dfma_latency_kernel(double* sink, int iters, double seed) {
+    double a = seed;
+    const double m = 1.0000001, c = 1e-9;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 64; ++u) a = fma(a, m, c);
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        sink[0] = (double)(t1 - t0) / ((double)iters * 64.0);
+        sink[1] = a;
+    }
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
@@ -93,31 +135,49 @@ extern "C" const char* mlmcb200_last_error(void) { return g_error; }
 extern "C" int mlmcb200_sm_count(void) { return sm_count(); }
 
 extern "C" int mlmcb200_fp64_peak(int32_t kind, double* flops_per_s, void* stream) {
-    MB_REQUIRE(flops_per_s != nullptr && (kind == 0 || kind == 1), "fp64_peak: bad arguments");
+    // kind & 15: 0 DFMA (2 loop-invariant operands), 1 DMMA m8n8k4, 2 DFMA with 3 distinct register operands,
+    //            3 dependent-DFMA latency in SM cycles (returned in *flops_per_s);  kind >> 4: warps per SM (0 = 64)
+    const int base = kind & 15, warps_per_sm = kind >> 4;
+    MB_REQUIRE(flops_per_s != nullptr && base >= 0 && base <= 3, "fp64_peak: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     double* sink = nullptr;
-    MB_CUDA_OK(cudaMalloc(&sink, 8));
+    MB_CUDA_OK(cudaMalloc(&sink, 16));
+    if (base == 3) {
+        dfma_latency_kernel<<<1, 32, 0, st>>>(sink, 256, 0.5);
+        MB_CUDA_OK(cudaGetLastError());
+        MB_CUDA_OK(cudaStreamSynchronize(st));
+        MB_CUDA_OK(cudaMemcpy(flops_per_s, sink, 8, cudaMemcpyDeviceToHost));
+        cudaFree(sink);
+        return 0;
+    }
     cudaEvent_t e0, e1;
     MB_CUDA_OK(cudaEventCreate(&e0));
     MB_CUDA_OK(cudaEventCreate(&e1));
-    const int blocks = sm_count() * 8, threads = 256, iters = 4096;
+    int threads = 256, blocks = sm_count() * 8;
+    if (warps_per_sm > 0) {
+        threads = 128;
+        blocks = sm_count() * ((warps_per_sm + 3) / 4);
+    }
+    const int iters = 4096;
     double best = 0.0;
     for (int rep = 0; rep < 4; ++rep) {
         MB_CUDA_OK(cudaEventRecord(e0, st));
-        if (kind == 0)
+        if (base == 0)
             dfma_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, 0.5);
-        else
+        else if (base == 1)
             dmma_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, 0.5);
+        else
+            dfma3_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, 0.5);
         MB_CUDA_OK(cudaGetLastError());
         MB_CUDA_OK(cudaEventRecord(e1, st));
         MB_CUDA_OK(cudaEventSynchronize(e1));
         float ms = 0.f;
         MB_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
         double flops;
-        if (kind == 0)
-            flops = (double)blocks * threads * iters * 64.0 * 2.0;                   // 64 DFMA per thread-iteration
-        else
+        if (base == 1)
             flops = (double)blocks * (threads / 32) * iters * 32.0 * (8 * 8 * 4) * 2.0;  // 32 DMMA per warp-iteration
+        else
+            flops = (double)blocks * threads * iters * 64.0 * 2.0;                   // 64 DFMA per thread-iteration
         const double rate = flops / (ms * 1e-3);
         if (rep > 0 && rate > best) best = rate;                                        // rep 0 = warm-up
     }

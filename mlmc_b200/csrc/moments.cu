@@ -19,6 +19,7 @@
 //   * FP64 instruction count per level-sample-moment: Legendre 2*(DMUL+DFMA) + DADD + DADD + DFMA = 7
 //     (level 0: 4); Monomial 5 (3); Fourier 7 (4).  The kernel is bound by the FP64 pipe, not by HBM, for
 //     R >= ~8 (DESIGN.md "Rooflines").
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mlmcb200 {
@@ -39,18 +40,21 @@ struct MomentsArgs {
     int64_t partial_stride;
 };
 
-// ---- per-moment accumulate: a1 += sum_s d_s, a2 += sum_s d_s^2 over the S samples held by this thread.
-// Pairwise tree for the sum and two interleaved FMA chains for the squares keep the dependency depth at
-// log2(S) / S/2 instead of S (the FP64 pipe issues in order; a serial chain would stall it).
-template <bool COARSE, int S>
-__device__ __forceinline__ void accumulate(double* __restrict__ col_sum, double* __restrict__ col_sq,
+// ---- per-moment reduction of the S samples held by this thread into its shared-memory column(s) ----
+// sum   : pairwise add tree (depth log2 S)
+// square: two interleaved FMA chains (depth S/2)
+// PAIR (scalar quantity): lanes 2j and 2j+1 share ONE pair of columns -- the even lane keeps the sum of both, the odd
+// lane the sum of squares of both (one 64-bit shuffle) -- which halves the shared memory per thread and so doubles
+// the number of resident warps for a given number of moments.
+template <bool COARSE, int S, bool PAIR>
+__device__ __forceinline__ void accumulate(double* __restrict__ sm, int k, int R, int tid,
                                            const double (&vf)[S], const double (&vc)[S]) {
     static_assert(S % 2 == 0, "S must be even");
+    constexpr int T = 128;
     double d[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) d[s] = COARSE ? vf[s] - vc[s] : vf[s];
-    double qa = *col_sq, qb = d[1] * d[1];
-    qa = fma(d[0], d[0], qa);
+    double qa = d[0] * d[0], qb = d[1] * d[1];
 #pragma unroll
     for (int s = 2; s < S; s += 2) {
         qa = fma(d[s], d[s], qa);
@@ -61,8 +65,15 @@ __device__ __forceinline__ void accumulate(double* __restrict__ col_sum, double*
 #pragma unroll
         for (int s = 0; s + w < S; s += 2 * w) d[s] += d[s + w];
     }
-    *col_sum += d[0];
-    *col_sq = qa + qb;
+    const double p1 = d[0], p2 = qa + qb;
+    if (PAIR) {
+        const bool odd = tid & 1;
+        const double recv = __shfl_xor_sync(0xffffffffu, odd ? p1 : p2, 1);
+        sm[k * T + tid] += (odd ? p2 : p1) + recv;
+    } else {
+        sm[k * T + tid] += p1;
+        sm[(R + k) * T + tid] += p2;
+    }
 }
 
 // raw (fine, coarse) values of the S samples of one tile owned by this thread; out-of-range samples read NaN
@@ -88,21 +99,18 @@ __device__ __forceinline__ void load_tile(const MomentsArgs& a, const double* ba
     }
 }
 
-template <int KIND, bool COARSE, bool LOG, int S>
+// FAST: scalar quantity in storage order (pairs contiguous, no external mask): 32-bit tile arithmetic, immediate
+// load offsets, no per-sample bounds tests on full tiles.
+template <int KIND, bool COARSE, bool LOG, int S, bool PAIR, bool FAST>
 __global__ void __launch_bounds__(kThreads)
 moments_acc_kernel(const MomentsArgs a) {
     extern __shared__ double sm[];
-    const int T = kThreads;
+    constexpr int T = kThreads;
     const int tid = threadIdx.x;
     const int R = a.basis.size;
     const int M = a.n_comp;
-    double* const sum_col = sm + tid;                       // element r at sum_col[r * T]
-    double* const sq_col = sm + (size_t)R * T + tid;
-
-    for (int r = 0; r < R; ++r) {
-        sum_col[r * T] = 0.0;
-        sq_col[r * T] = 0.0;
-    }
+    const int n_cols = PAIR ? R : 2 * R;
+    for (int r = 0; r < n_cols; ++r) sm[r * T + tid] = 0.0;         // own column(s) only: no barrier needed
 
     // thread -> (component, sample lane)
     int m, tn, TN;
@@ -122,93 +130,140 @@ moments_acc_kernel(const MomentsArgs a) {
     const int64_t n_tiles = (a.n + tile_n - 1) / tile_n;
     const double* const base_f = a.pairs + (int64_t)m * a.stride_m;
     const bool count_here = (blockIdx.x == 0) && (M >= T ? tid == 0 : m == 0);
-
     unsigned cnt_ok = 0, cnt_rm = 0;
+
+#define MB_ACC(K, VF, VC) accumulate<COARSE, S, PAIR>(sm, (K), R, tid, VF, VC)
 
     // software pipeline: the raw values of the NEXT tile are in flight while the current tile is reduced
     double xf[S], xc[S];
-    load_tile<COARSE, S>(a, base_f, (int64_t)blockIdx.y * tile_n + tn, TN, active, xf, xc);
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    // FAST addressing: sample (tile, s, tid) = pairs[(tile * S * T + s * T + tid) * stride_n (+ 1 for the coarse half)]
+    auto load_fast = [&](int64_t tile) {
+        const int64_t first = tile * tile_n + tid;
+        const bool full = (tile + 1) * tile_n <= a.n;
+        if (COARSE) {
+            const double2* p = reinterpret_cast<const double2*>(a.pairs) + first;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                double2 v = make_double2(qnan, qnan);
+                if (full || first + s * T < a.n) v = __ldcs(p + s * T);
+                xf[s] = v.x;
+                xc[s] = v.y;
+            }
+        } else {
+            const double* p = a.pairs + first * a.stride_n;
+            const int64_t step = (int64_t)T * a.stride_n;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                xf[s] = qnan;
+                if (full || first + s * T < a.n) xf[s] = __ldcs(p + s * step);
+            }
+        }
+    };
+    if (FAST) load_fast(blockIdx.y);
+    else load_tile<COARSE, S>(a, base_f, (int64_t)blockIdx.y * tile_n + tn, TN, active, xf, xc);
 
     for (int64_t tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
         double tf[S], tc[S];
         bool ok[S];
-        const int64_t n0 = tile * tile_n + tn;
+        if (FAST) {
+            // an out-of-range slot holds NaN: it fails every validity test below, it only must not be counted
+            const int64_t first = tile * tile_n + tid;
+            const bool full = (tile + 1) * tile_n <= a.n;
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const int64_t n = n0 + (int64_t)s * TN;
-            const bool in = active && n < a.n;
-            if (KIND == MLMCB200_RAW) {
-                tf[s] = xf[s];
-                tc[s] = xc[s];
-            } else {
+            for (int s = 0; s < S; ++s) {
                 tf[s] = map_to_ref_t<LOG>(a.basis, xf[s]);
                 tc[s] = COARSE ? map_to_ref_t<LOG>(a.basis, xc[s]) : 0.0;
-            }
-            bool good;
-            if (a.valid != nullptr) {
-                good = in && a.valid[n] != 0;
-            } else {
-                good = in && moments_finite(a.basis, tf[s]) && (!COARSE || moments_finite(a.basis, tc[s]));
-            }
-            if (count_here && in) {
+                bool good;
+                if (a.basis.is_clip) {            // map_to_ref_t returns NaN outside [ref_lo, ref_hi]
+                    good = (tf[s] == tf[s]) && (!COARSE || tc[s] == tc[s]);
+                    if (KIND == MLMCB200_FOURIER && R == 1) good = true;
+                } else {
+                    good = moments_finite(a.basis, tf[s]) && (!COARSE || moments_finite(a.basis, tc[s]));
+                }
+                const bool in = full || first + s * T < a.n;
+                good = good && in;
                 cnt_ok += good ? 1u : 0u;
-                cnt_rm += good ? 0u : 1u;
+                cnt_rm += (in && !good) ? 1u : 0u;
+                tf[s] = good ? tf[s] : 0.0;
+                tc[s] = good ? tc[s] : 0.0;
+                ok[s] = good;
             }
-            if (!good) {          // a dropped sample contributes exact zeros to every sum
-                tf[s] = 0.0;
-                tc[s] = 0.0;
+            if (tile + gridDim.y < n_tiles) load_fast(tile + gridDim.y);
+        } else {
+            const int64_t n0 = tile * tile_n + tn;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const int64_t n = n0 + (int64_t)s * TN;
+                const bool in = active && n < a.n;
+                if (KIND == MLMCB200_RAW) {
+                    tf[s] = xf[s];
+                    tc[s] = xc[s];
+                } else {
+                    tf[s] = map_to_ref_t<LOG>(a.basis, xf[s]);
+                    tc[s] = COARSE ? map_to_ref_t<LOG>(a.basis, xc[s]) : 0.0;
+                }
+                bool good;
+                if (a.valid != nullptr) {
+                    good = in && a.valid[n] != 0;
+                } else {
+                    good = in && moments_finite(a.basis, tf[s]) && (!COARSE || moments_finite(a.basis, tc[s]));
+                }
+                if (count_here && in) {
+                    cnt_ok += good ? 1u : 0u;
+                    cnt_rm += good ? 0u : 1u;
+                }
+                if (!good) {          // a dropped sample contributes exact zeros to every sum
+                    tf[s] = 0.0;
+                    tc[s] = 0.0;
+                }
+                ok[s] = good;
             }
-            ok[s] = good;
+            if (tile + gridDim.y < n_tiles)
+                load_tile<COARSE, S>(a, base_f, (tile + gridDim.y) * tile_n + tn, TN, active, xf, xc);
         }
-        if (tile + gridDim.y < n_tiles)
-            load_tile<COARSE, S>(a, base_f, (tile + gridDim.y) * tile_n + tn, TN, active, xf, xc);
 
         if (KIND == MLMCB200_RAW) {
-            accumulate<COARSE, S>(sum_col, sq_col, tf, tc);
-        } else if (KIND == MLMCB200_LEGENDRE || KIND == MLMCB200_MONOMIAL) {
-            // Two ping-pong register sets hold moment k of the S samples: even k in (fb, cb), odd k in (fa, ca).
-            //   Legendre (monic): W_k = t W_{k-1} - e_k W_{k-2}, the e_k product in place on the older set
-            //   Monomial        : t^k = t^{k-1} t
-            // Software pipeline: the reduction of moment k is issued AFTER the recurrence of moment k+1, so the
-            // dependent tail of one (add tree, smem update) overlaps the independent FP64 work of the other.
-            double fa[S], fb[S], ca[S], cb[S];
+            MB_ACC(0, tf, tc);
+        } else if (KIND == MLMCB200_LEGENDRE) {
+            // Monic recurrence W_k = t W_{k-1} - e_k W_{k-2} (P_k = g_k W_k is applied in the epilogue), kept as
+            //     W_k = fma(-e_k, W_{k-2}, Z),  Z = t * W_{k-1}          (Z carried in a register)
+            // because a DFMA with three distinct register operands issues at 2/3 rate on sm_100 (24.7 vs 36.5 TFLOP/s,
+            // tools/fp64_probe.py): here both instructions read two registers (e_k sits in a uniform register).
+            // Even k live in (fb, cb), odd k in (fa, ca).  The reduction of moment k is issued AFTER the recurrence of
+            // moment k+1 so that its dependent tail overlaps independent FP64 work.
+            double fa[S], fb[S], ca[S], cb[S], zf[S], zc[S];
 #pragma unroll
             for (int s = 0; s < S; ++s) {
                 fb[s] = cb[s] = ok[s] ? 1.0 : 0.0;
                 fa[s] = tf[s];
                 ca[s] = tc[s];
+                zf[s] = tf[s] * tf[s];
+                zc[s] = tc[s] * tc[s];
             }
-            accumulate<COARSE, S>(sum_col, sq_col, fb, cb);                       // moment 0
-#define MB_REC(DST_F, DST_C, SRC_F, SRC_C, E)                                   \
+            MB_ACC(0, fb, cb);
+#define MB_REC(DST_F, DST_C, E)                                                  \
     _Pragma("unroll") for (int s = 0; s < S; ++s) {                              \
-        if (KIND == MLMCB200_LEGENDRE) {                                         \
-            DST_F[s] *= (E);                                                     \
-            if (COARSE) DST_C[s] *= (E);                                         \
-        }                                                                        \
+        DST_F[s] = fma(-(E), DST_F[s], zf[s]);                                   \
+        if (COARSE) DST_C[s] = fma(-(E), DST_C[s], zc[s]);                       \
     }                                                                            \
     _Pragma("unroll") for (int s = 0; s < S; ++s) {                              \
-        if (KIND == MLMCB200_LEGENDRE) {                                         \
-            DST_F[s] = fma(tf[s], SRC_F[s], -DST_F[s]);                          \
-            if (COARSE) DST_C[s] = fma(tc[s], SRC_C[s], -DST_C[s]);              \
-        } else {                                                                 \
-            DST_F[s] = SRC_F[s] * tf[s];                                         \
-            if (COARSE) DST_C[s] = SRC_C[s] * tc[s];                             \
-        }                                                                        \
+        zf[s] = tf[s] * DST_F[s];                                                \
+        if (COARSE) zc[s] = tc[s] * DST_C[s];                                    \
     }
-#define MB_ACC(K, VF, VC) accumulate<COARSE, S>(sum_col + (K) * T, sq_col + (K) * T, VF, VC)
             int i = 2;                                                            // next moment to generate
             if (R > 5) {
                 double e0 = kLegCoef[2], e1 = kLegCoef[3], e2 = kLegCoef[4], e3 = kLegCoef[5];
                 for (; i + 3 < R; i += 4) {
                     // coefficients of the NEXT group are fetched now (the table is padded past MAX_MOMENTS)
                     const double n0 = kLegCoef[i + 4], n1 = kLegCoef[i + 5], n2 = kLegCoef[i + 6], n3 = kLegCoef[i + 7];
-                    MB_REC(fb, cb, fa, ca, e0)
+                    MB_REC(fb, cb, e0)
                     MB_ACC(i - 1, fa, ca);
-                    MB_REC(fa, ca, fb, cb, e1)
+                    MB_REC(fa, ca, e1)
                     MB_ACC(i, fb, cb);
-                    MB_REC(fb, cb, fa, ca, e2)
+                    MB_REC(fb, cb, e2)
                     MB_ACC(i + 1, fa, ca);
-                    MB_REC(fa, ca, fb, cb, e3)
+                    MB_REC(fa, ca, e3)
                     MB_ACC(i + 2, fb, cb);
                     e0 = n0; e1 = n1; e2 = n2; e3 = n3;
                 }
@@ -216,10 +271,10 @@ moments_acc_kernel(const MomentsArgs a) {
             for (; i < R; ++i) {                                                 // remainder, one moment at a time
                 const double e = kLegCoef[i];
                 if ((i & 1) == 0) {
-                    MB_REC(fb, cb, fa, ca, e)
+                    MB_REC(fb, cb, e)
                     MB_ACC(i - 1, fa, ca);
                 } else {
-                    MB_REC(fa, ca, fb, cb, e)
+                    MB_REC(fa, ca, e)
                     MB_ACC(i - 1, fb, cb);
                 }
             }
@@ -228,7 +283,37 @@ moments_acc_kernel(const MomentsArgs a) {
                 else MB_ACC(R - 1, fb, cb);
             }
 #undef MB_REC
-#undef MB_ACC
+        } else if (KIND == MLMCB200_MONOMIAL) {
+            // t^k = t^{k-1} t on two ping-pong sets, reduction of moment k issued after the product for k+1
+            double fa[S], fb[S], ca[S], cb[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                fb[s] = cb[s] = ok[s] ? 1.0 : 0.0;
+                fa[s] = tf[s];
+                ca[s] = tc[s];
+            }
+            MB_ACC(0, fb, cb);
+            for (int i = 2; i < R; ++i) {
+                if ((i & 1) == 0) {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        fb[s] = fa[s] * tf[s];
+                        if (COARSE) cb[s] = ca[s] * tc[s];
+                    }
+                    MB_ACC(i - 1, fa, ca);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        fa[s] = fb[s] * tf[s];
+                        if (COARSE) ca[s] = cb[s] * tc[s];
+                    }
+                    MB_ACC(i - 1, fb, cb);
+                }
+            }
+            if (R > 1) {
+                if ((R - 1) & 1) MB_ACC(R - 1, fa, ca);
+                else MB_ACC(R - 1, fb, cb);
+            }
         } else {  // FOURIER: columns 1, cos t, sin t, cos 2t, sin 2t, ... by exact-angle rotation
             double cf1[S], sf1[S], cc1[S], sc1[S], cfk[S], sfk[S], cck[S], sck[S];
 #pragma unroll
@@ -240,7 +325,7 @@ moments_acc_kernel(const MomentsArgs a) {
                     if (COARSE) sincos(tc[s], &sc1[s], &cc1[s]);
                 }
             }
-            accumulate<COARSE, S>(sum_col, sq_col, cfk, cck);
+            MB_ACC(0, cfk, cck);
 #pragma unroll
             for (int s = 0; s < S; ++s) {
                 cfk[s] = cf1[s];
@@ -249,8 +334,8 @@ moments_acc_kernel(const MomentsArgs a) {
                 sck[s] = sc1[s];
             }
             for (int i = 1; i < R; i += 2) {
-                accumulate<COARSE, S>(sum_col + i * T, sq_col + i * T, cfk, cck);
-                if (i + 1 < R) accumulate<COARSE, S>(sum_col + (i + 1) * T, sq_col + (i + 1) * T, sfk, sck);
+                MB_ACC(i, cfk, cck);
+                if (i + 1 < R) MB_ACC(i + 1, sfk, sck);
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     const double nc = fma(cfk[s], cf1[s], -(sfk[s] * sf1[s]));
@@ -265,6 +350,7 @@ moments_acc_kernel(const MomentsArgs a) {
             }
         }
     }
+#undef MB_ACC
 
     // ---------------- block epilogue ----------------
     __syncthreads();
@@ -274,8 +360,8 @@ moments_acc_kernel(const MomentsArgs a) {
         if (active) {
             for (int r = 0; r < R; ++r) {
                 const double al = (KIND == MLMCB200_LEGENDRE) ? kLegAlpha[r] : 1.0;
-                out[2 + (int64_t)m * R + r] = sum_col[r * T] * al;
-                out[2 + K + (int64_t)m * R + r] = sq_col[r * T] * (al * al);
+                out[2 + (int64_t)m * R + r] = sm[r * T + tid] * al;
+                out[2 + K + (int64_t)m * R + r] = sm[(R + r) * T + tid] * (al * al);
             }
         }
     } else {
@@ -283,9 +369,16 @@ moments_acc_kernel(const MomentsArgs a) {
         for (int k = warp; k < (int)K; k += n_warps) {
             const int mm = k / R, r = k - mm * R;
             double s1 = 0.0, s2 = 0.0;
-            for (int j = lane; j < TN; j += 32) {
-                s1 += sm[r * T + j * M + mm];
-                s2 += sm[(size_t)R * T + r * T + j * M + mm];
+            if (PAIR) {                         // M == 1: even columns hold sums, odd columns sums of squares
+                for (int j = 2 * lane; j < T; j += 64) {
+                    s1 += sm[r * T + j];
+                    s2 += sm[r * T + j + 1];
+                }
+            } else {
+                for (int j = lane; j < TN; j += 32) {
+                    s1 += sm[r * T + j * M + mm];
+                    s2 += sm[(R + r) * T + j * M + mm];
+                }
             }
             s1 = warp_sum(s1);
             s2 = warp_sum(s2);
@@ -395,35 +488,42 @@ namespace {
 struct Plan {
     dim3 grid;
     size_t smem;
-    int samples_per_thread;
+    int S;        // samples per thread and tile
+    bool pair;    // lane pairs share accumulator columns (scalar quantity)
+    bool fast;    // scalar quantity in storage order: specialised addressing
 };
 
+// Samples per thread and tile: 8 keeps the accumulator traffic per sample-moment low (Fourier carries twice the
+// state per sample and uses 4).
+int choose_S(int kind) { return kind == MLMCB200_FOURIER ? 4 : 8; }
+
 int plan_moments(int kind, int size, int n_comp, int64_t n, Plan* p) {
-    const int S = (kind == MLMCB200_FOURIER) ? 4 : 8;
-    const size_t smem = (size_t)2 * size * kThreads * sizeof(double);
+    p->S = choose_S(kind);
+    p->pair = n_comp == 1;
+    p->fast = false;
+    const size_t smem = (size_t)(p->pair ? 1 : 2) * size * kThreads * sizeof(double);
     if (smem > 227u * 1024u) {
         set_error("moments: size %d needs %zu B of shared memory per CTA (max %u)", size, smem, 227u * 1024u);
         return -1;
     }
     int ctas_per_sm = (int)((227u * 1024u) / (smem + 1024));
-    if (ctas_per_sm > 4) ctas_per_sm = 4;
+    if (ctas_per_sm > 8) ctas_per_sm = 8;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const int gx = n_comp >= kThreads ? (n_comp + kThreads - 1) / kThreads : 1;
     int gy = (sm_count() * ctas_per_sm + gx - 1) / gx;
     if (n >= 0) {
         const int TN = n_comp >= kThreads ? 1 : kThreads / n_comp;
-        const int64_t tiles = (n + (int64_t)S * TN - 1) / ((int64_t)S * TN);
+        const int64_t tiles = (n + (int64_t)p->S * TN - 1) / ((int64_t)p->S * TN);
         if (tiles < gy) gy = (int)(tiles > 0 ? tiles : 1);
     }
     p->grid = dim3(gx, gy, 1);
     p->smem = smem;
-    p->samples_per_thread = S;
     return 0;
 }
 
-template <int KIND, bool COARSE, bool LOG, int S>
+template <int KIND, bool COARSE, bool LOG, int S, bool PAIR, bool FAST>
 int launch_moments(const MomentsArgs& a, Plan p, cudaStream_t st) {
-    auto kern = moments_acc_kernel<KIND, COARSE, LOG, S>;
+    auto kern = moments_acc_kernel<KIND, COARSE, LOG, S, PAIR, FAST>;
     // resident CTAs per SM for this variant and shared-memory size (registers may bind before shared memory);
     // the sample-partition dimension of the grid is sized to exactly one resident wave
     static thread_local size_t cached_smem = 0;
@@ -440,6 +540,26 @@ int launch_moments(const MomentsArgs& a, Plan p, cudaStream_t st) {
     kern<<<p.grid, kThreads, p.smem, st>>>(a);
     MB_CUDA_OK(cudaGetLastError());
     return (int)p.grid.y;
+}
+
+template <int KIND, bool COARSE, bool LOG, int S>
+int launch_moments_pair(const MomentsArgs& a, const Plan& p, cudaStream_t st) {
+    if (!p.pair) return launch_moments<KIND, COARSE, LOG, S, false, false>(a, p, st);
+    if (KIND != MLMCB200_RAW && p.fast) return launch_moments<KIND, COARSE, LOG, S, true, true>(a, p, st);
+    return launch_moments<KIND, COARSE, LOG, S, true, false>(a, p, st);
+}
+
+template <int KIND, bool COARSE, bool LOG>
+int launch_moments_s(const MomentsArgs& a, const Plan& p, cudaStream_t st) {
+    return launch_moments_pair<KIND, COARSE, LOG, KIND == MLMCB200_FOURIER ? 4 : 8>(a, p, st);
+}
+
+template <int KIND>
+int launch_moments_kind(const MomentsArgs& a, const Plan& p, bool coarse, bool is_log, cudaStream_t st) {
+    if (KIND == MLMCB200_RAW) is_log = false;
+    if (is_log)
+        return coarse ? launch_moments_s<KIND, true, true>(a, p, st) : launch_moments_s<KIND, false, true>(a, p, st);
+    return coarse ? launch_moments_s<KIND, true, false>(a, p, st) : launch_moments_s<KIND, false, false>(a, p, st);
 }
 
 }  // namespace
@@ -485,24 +605,16 @@ extern "C" int mlmcb200_moments_accumulate(const mlmcb200_basis_t* basis, const 
               (reinterpret_cast<uintptr_t>(pairs) & 15) == 0) ? 1 : 0;
     a.partial = static_cast<double*>(workspace);
     a.partial_stride = stride;
+    p.fast = n_comp == 1 && valid == nullptr && (has_coarse ? a.vec2 != 0 : stride_n >= 1);
 
     int rc = -1;     // > 0: number of partial vectors written
-#define MB_DISPATCH(KIND, S)                                                                               \
-    rc = basis->is_log                                                                                      \
-             ? (has_coarse ? launch_moments<KIND, true, true, S>(a, p, st)                                  \
-                           : launch_moments<KIND, false, true, S>(a, p, st))                                \
-             : (has_coarse ? launch_moments<KIND, true, false, S>(a, p, st)                                 \
-                           : launch_moments<KIND, false, false, S>(a, p, st))
+    const bool coarse = has_coarse != 0, is_log = basis->is_log != 0;
     switch (basis->kind) {
-        case MLMCB200_RAW:
-            rc = has_coarse ? launch_moments<MLMCB200_RAW, true, false, 8>(a, p, st)
-                            : launch_moments<MLMCB200_RAW, false, false, 8>(a, p, st);
-            break;
-        case MLMCB200_LEGENDRE: MB_DISPATCH(MLMCB200_LEGENDRE, 8); break;
-        case MLMCB200_MONOMIAL: MB_DISPATCH(MLMCB200_MONOMIAL, 8); break;
-        case MLMCB200_FOURIER: MB_DISPATCH(MLMCB200_FOURIER, 4); break;
+        case MLMCB200_RAW: rc = launch_moments_kind<MLMCB200_RAW>(a, p, coarse, is_log, st); break;
+        case MLMCB200_LEGENDRE: rc = launch_moments_kind<MLMCB200_LEGENDRE>(a, p, coarse, is_log, st); break;
+        case MLMCB200_MONOMIAL: rc = launch_moments_kind<MLMCB200_MONOMIAL>(a, p, coarse, is_log, st); break;
+        case MLMCB200_FOURIER: rc = launch_moments_kind<MLMCB200_FOURIER>(a, p, coarse, is_log, st); break;
     }
-#undef MB_DISPATCH
     if (rc <= 0) return rc < 0 ? rc : -1;
     return launch_reduce_partials(a.partial, rc, stride, stride, acc, st);
 }

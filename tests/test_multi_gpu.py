@@ -1,0 +1,63 @@
+"""GPU, world size 2 (NCCL): sharded ``estimate_mean`` through the public API equals the single-GPU estimate.
+Skipped on boxes with one GPU (the CPU/gloo test ``test_dist_gloo.py`` covers the host logic everywhere)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch
+    from mlmc_b200 import dist
+    from mlmc_b200.moments import Legendre
+    from mlmc_b200.sample_storage import Memory
+    from mlmc_b200.quantity.quantity import make_root_quantity
+    from mlmc_b200.quantity.quantity_spec import QuantitySpec
+    from mlmc_b200.quantity import quantity_estimate as qe
+    dist.init_from_env(backend="nccl")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "estimates.npz"))
+    levels = [g["A_rows%d" % l] for l in range(3)]
+    spec = [QuantitySpec(name="v", unit="", shape=(1, 1), times=[0.0], locations=["0"])]
+    storage = Memory.from_arrays(levels, level_parameters=[[h] for h in g["A_steps"]], result_format=spec)
+    value = make_root_quantity(storage, spec)["v"][0.0]["0"][0, 0]
+    qm = qe.estimate_mean(qe.moments(value, Legendre(12, tuple(g["A_domain"]))))
+    cm = qe.estimate_mean(qe.covariance(value, Legendre(8, tuple(g["A_domain"]))))
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), l_means=qm.l_means, l_vars=qm.l_vars, n=qm.n_samples,
+             n_rm=qm.n_rm_samples, cov=cm.mean, cov_var=cm.var)
+    import torch.distributed as td
+    td.barrier()
+    td.destroy_process_group()
+
+
+def test_two_gpu_sharded_estimate(tmp_path, golden):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    mp.start_processes(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True,
+                       start_method="spawn")
+    g = golden("estimates")
+    for r in range(world):
+        out = np.load(os.path.join(str(tmp_path), "r%d.npz" % r))
+        assert np.array_equal(out["n"], g["A_leg_n"]) and np.array_equal(out["n_rm"], g["A_leg_n_rm"])
+        assert np.allclose(out["l_means"], g["A_leg_l_means"], rtol=1e-10, atol=1e-15)
+        assert np.allclose(out["l_vars"], g["A_leg_l_vars"], rtol=1e-10, atol=1e-15)
+        assert np.allclose(out["cov"], g["A_cov_mean"], rtol=1e-8, atol=1e-14)
+        assert np.allclose(out["cov_var"], g["A_cov_var"], rtol=1e-8, atol=1e-16)
