@@ -191,6 +191,7 @@ def run_gpu_arm(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")   # NCCL prints its banner on stdout
     rank, world, local = mdist.init_from_env()
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
@@ -289,6 +290,7 @@ def run_gpu_arm(args):
     host_levels = [lv.cpu() for lv in levels]
     spec = [QuantitySpec(name="v", unit="", shape=(1, 1), times=[0.0], locations=["0"])]
     storage = Memory.from_arrays(host_levels, level_parameters=[[h] for h in steps], n_ops=n_ops, result_format=spec)
+    storage.rows_are_local_shard = True      # weak scaling: every rank owns n_rows samples per level
     storage.resident_fraction = 0.0          # never keep a device copy: every step streams host -> HBM
     storage.device_chunk_bytes = 32 << 20    # 32 MB chunks, copy stream overlapped with the kernels
     del host_levels

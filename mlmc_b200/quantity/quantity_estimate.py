@@ -135,8 +135,9 @@ def estimate_mean(quantity):
     n_levels = int(np.max(level_ids)) + 1
     device = q_mod._device()
     plan = _Plan(quantity)
-    ranges = _level_row_ranges(storage, level_ids)
-    sharded = _dist.world_size() > 1
+    multi = _dist.world_size() > 1
+    sharded = multi and not getattr(storage, "rows_are_local_shard", False)
+    ranges = _level_row_ranges(storage, level_ids) if sharded else None
 
     acc = None          # LevelAccumulator of the main statistics
     gram = None         # transformed moments: Gram of the base differences
@@ -177,7 +178,7 @@ def estimate_mean(quantity):
 
     if acc is None:
         raise Exception("All samples were masked")
-    if sharded:
+    if multi:
         _dist.all_reduce_sum(acc.acc)
         if gram is not None:
             _dist.all_reduce_sum(gram.acc)

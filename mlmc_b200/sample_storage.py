@@ -41,6 +41,9 @@ class SampleStorage(metaclass=ABCMeta):
     device_chunk_bytes = 32 << 20
     #: fraction of free HBM a resident copy of all levels may take
     resident_fraction = 0.6
+    #: multi-GPU: True if this process's storage already holds only ITS shard of every level (then every local row
+    #: is reduced and only the level sums are combined); False = every rank sees all rows and takes a row range
+    rows_are_local_shard = False
 
     # ------------------------------------------------------------------ write side (reference API)
     @abstractmethod
