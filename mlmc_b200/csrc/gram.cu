@@ -49,6 +49,18 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
+// Warp-uniformly predicated DMMA (no branch, no re-convergence barrier around the mma.sync)
+__device__ __forceinline__ void dmma_if(unsigned on, double& c0, double& c1, double a, double b) {
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " setp.ne.u32 p, %4, 0;\n"
+        " @p mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        "}\n"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b), "r"(on));
+}
+
 // One basis row (R values, zero-padded to 8*nb) into shared memory.  Zero row for a dropped sample.
 __device__ __forceinline__ void write_row(const mlmcb200_basis_t& b, double t, bool good, double* row, int r_pad) {
     const int R = b.size;
@@ -86,6 +98,69 @@ __device__ __forceinline__ void write_row(const mlmcb200_basis_t& b, double t, b
     for (int i = R; i < r_pad; ++i) row[i] = 0.0;
 }
 
+// All DMMAs of one task (GS x GS blocks of shape SHAPE) for one 4-sample step.  Products into the same accumulator
+// are issued in separate passes so that consecutive DMMAs are independent.
+template <int GS, int SHAPE>
+__device__ __forceinline__ constexpr bool block_on(int u, int v) {
+    return SHAPE == 0 ? true : SHAPE == 1 ? v == 0 : SHAPE == 2 ? v >= u : (u == 0 && v == 0);
+}
+
+template <bool COARSE, int MODE, int GS, int SHAPE>
+__device__ __forceinline__ void slot_mma(double (&am)[GS][GS][2], double (&av)[GS][GS][2], const double* pf,
+                                         const double* pc, const int (&off_r)[GS], const int (&off_c)[GS]) {
+    constexpr int NR = (SHAPE == 3) ? 1 : GS;                 // row / column fragments actually needed
+    constexpr int NC = (SHAPE == 1 || SHAPE == 3) ? 1 : GS;
+    double fr[GS], cr[GS], fcol[GS], ccol[GS];
+#pragma unroll
+    for (int u = 0; u < GS; ++u) {
+        fr[u] = cr[u] = fcol[u] = ccol[u] = 0.0;
+        if (u < NR) {
+            fr[u] = pf[off_r[u]];
+            if (COARSE) cr[u] = pc[off_r[u]];
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < GS; ++v) {
+        if (v < NC) {
+            if (SHAPE == 2 || SHAPE == 3) {                    // diagonal task: column fragments = row fragments
+                fcol[v] = fr[v];
+                ccol[v] = cr[v];
+            } else {
+                fcol[v] = pf[off_c[v]];
+                if (COARSE) ccol[v] = pc[off_c[v]];
+            }
+        }
+    }
+#define MB_FOR_BLOCKS(BODY)                                                     \
+    _Pragma("unroll") for (int u = 0; u < GS; ++u) {                            \
+        _Pragma("unroll") for (int v = 0; v < GS; ++v) {                        \
+            if (block_on<GS, SHAPE>(u, v)) { BODY }                             \
+        }                                                                       \
+    }
+    if (MODE == 2) {
+        MB_FOR_BLOCKS(dmma(am[u][v][0], am[u][v][1], fr[u] - cr[u], fcol[v] - ccol[v]);)
+    } else {
+        MB_FOR_BLOCKS(dmma(am[u][v][0], am[u][v][1], fr[u], fcol[v]);)
+        if (COARSE) { MB_FOR_BLOCKS(dmma(am[u][v][0], am[u][v][1], -cr[u], ccol[v]);) }
+        if (MODE == 1) {
+            if (COARSE) {
+                double di[GS], dj[GS];
+#pragma unroll
+                for (int u = 0; u < GS; ++u) {
+                    di[u] = fr[u] - cr[u];
+                    dj[u] = fcol[u] - ccol[u];
+                }
+                MB_FOR_BLOCKS(dmma(av[u][v][0], av[u][v][1], di[u] * di[u], fcol[v] * fcol[v]);)
+                MB_FOR_BLOCKS(dmma(av[u][v][0], av[u][v][1], cr[u] * cr[u], dj[v] * dj[v]);)
+                MB_FOR_BLOCKS(dmma(av[u][v][0], av[u][v][1], 2.0 * (di[u] * cr[u]), fcol[v] * dj[v]);)
+            } else {
+                MB_FOR_BLOCKS(dmma(av[u][v][0], av[u][v][1], fr[u] * fr[u], fcol[v] * fcol[v]);)
+            }
+        }
+    }
+#undef MB_FOR_BLOCKS
+}
+
 // MODE 0: covariance sums only; 1: covariance sums + sums of squares; 2: Gram of the differences
 template <bool COARSE, int MODE, int GS>
 __global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a) {
@@ -117,6 +192,25 @@ __global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a)
     const int frag_off = (lane & 3) * LD + (lane >> 2);
     unsigned cnt_ok = 0, cnt_rm = 0;
 
+    // decode this warp's task list ONCE: shared-memory column offsets of its row / column fragments and the SHAPE of
+    // each task = which of its GS x GS 8x8 blocks exist and lie on or above the diagonal:
+    //   0 = all, 1 = first column only (last, half-filled column group), 2 = upper triangle (diagonal task),
+    //   3 = block (0,0) only, 4 = empty slot.
+    int off_r[kMaxSlots][GS], off_c[kMaxSlots][GS], shape[kMaxSlots];
+#pragma unroll
+    for (int slot = 0; slot < kMaxSlots; ++slot) {
+        const bool used = slot < my_tasks;
+        const int gi = used ? pl.gi[warp][slot] : 0, gj = used ? pl.gj[warp][slot] : 0;
+        const int bi0 = gi * GS, bj0 = gj * GS;
+#pragma unroll
+        for (int u = 0; u < GS; ++u) {
+            off_r[slot][u] = 8 * min(bi0 + u, nb - 1);
+            off_c[slot][u] = 8 * min(bj0 + u, nb - 1);
+        }
+        const bool col_full = bj0 + GS <= nb;                   // the row group of a task is full unless gi == gj
+        shape[slot] = !used ? 4 : (gi == gj ? ((GS > 1 && col_full) ? 2 : 3) : ((GS > 1 && col_full) ? 0 : 1));
+    }
+
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t n0 = tile * NS;
         // ---- phase A: basis rows of the tile into shared memory ----
@@ -124,7 +218,7 @@ __global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a)
         __syncthreads();
         // pass 1: map values, AND the validity of both sides
         for (int w = tid; w < NS * n_sides; w += kThreadsGram) {
-            const int s = w % NS, side = w / NS;
+            const int side = w >= NS ? 1 : 0, s = w - side * NS;
             const int64_t n = n0 + s;
             if (n < a.n) {
                 const double x = __ldcs(a.pairs + n * a.stride_n + side * a.stride_side);
@@ -137,7 +231,7 @@ __global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a)
         }
         __syncthreads();
         for (int w = tid; w < NS * n_sides; w += kThreadsGram) {
-            const int s = w % NS, side = w / NS;
+            const int side = w >= NS ? 1 : 0, s = w - side * NS;
             double* row = (side == 0 ? phi_f : phi_c) + (size_t)s * LD;
             const bool good = flags[s] != 0;
             if (side == 0 && n0 + s < a.n) {
@@ -154,50 +248,14 @@ __global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a)
             const double* pc = phi_c + (size_t)k0 * LD + frag_off;
 #pragma unroll
             for (int slot = 0; slot < kMaxSlots; ++slot) {
-                if (slot < my_tasks) {
-                    const int bi0 = pl.gi[warp][slot] * GS, bj0 = pl.gj[warp][slot] * GS;
-                    double fr[GS], cr[GS], fcol[GS], ccol[GS];
-#pragma unroll
-                    for (int u = 0; u < GS; ++u) {
-                        const bool in_r = bi0 + u < nb, in_c = bj0 + u < nb;
-                        fr[u] = in_r ? pf[8 * (bi0 + u)] : 0.0;
-                        fcol[u] = in_c ? pf[8 * (bj0 + u)] : 0.0;
-                        if (COARSE) {
-                            cr[u] = in_r ? pc[8 * (bi0 + u)] : 0.0;
-                            ccol[u] = in_c ? pc[8 * (bj0 + u)] : 0.0;
-                        } else {
-                            cr[u] = ccol[u] = 0.0;
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < GS; ++u) {
-#pragma unroll
-                        for (int v = 0; v < GS; ++v) {
-                            const int I = bi0 + u, J = bj0 + v;
-                            if (I < nb && J < nb && J >= I) {
-                                double& m0 = acc_m[slot][u][v][0];
-                                double& m1 = acc_m[slot][u][v][1];
-                                if (MODE == 2) {
-                                    dmma(m0, m1, fr[u] - cr[u], fcol[v] - ccol[v]);
-                                } else {
-                                    dmma(m0, m1, fr[u], fcol[v]);
-                                    if (COARSE) dmma(m0, m1, -cr[u], ccol[v]);
-                                    if (MODE == 1) {
-                                        double& v0 = acc_v[slot][u][v][0];
-                                        double& v1 = acc_v[slot][u][v][1];
-                                        if (COARSE) {
-                                            const double di = fr[u] - cr[u], dj = fcol[v] - ccol[v];
-                                            dmma(v0, v1, di * di, fcol[v] * fcol[v]);
-                                            dmma(v0, v1, cr[u] * cr[u], dj * dj);
-                                            dmma(v0, v1, 2.0 * (di * cr[u]), fcol[v] * dj);
-                                        } else {
-                                            dmma(v0, v1, fr[u] * fr[u], fcol[v] * fcol[v]);
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                    }
+                const double* rf = pf;
+                const double* rc = pc;
+                switch (shape[slot]) {                         // warp-uniform; straight-line DMMA runs inside
+                    case 0: slot_mma<COARSE, MODE, GS, 0>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], rf, rc, off_r[slot], off_c[slot]); break;
+                    case 1: slot_mma<COARSE, MODE, GS, 1>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], rf, rc, off_r[slot], off_c[slot]); break;
+                    case 2: slot_mma<COARSE, MODE, GS, 2>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], rf, rc, off_r[slot], off_c[slot]); break;
+                    case 3: slot_mma<COARSE, MODE, GS, 3>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], rf, rc, off_r[slot], off_c[slot]); break;
+                    default: break;
                 }
             }
         }
