@@ -19,9 +19,10 @@
 namespace mlmcb200 {
 namespace {
 
-constexpr int kWarps = 8;
+constexpr int kWarps = 16;
 constexpr int kThreadsGram = kWarps * 32;
-constexpr int kMaxSlots = 4;     // tasks per warp
+constexpr int kMaxSlots = 3;     // tasks per warp (array bound; the plan uses 2 or 3)
+constexpr int kGenWarps = 4;     // pipelined variant: dedicated generator warps (one per SM sub-partition)
 constexpr int kMaxGroup = 2;     // blocks per task side
 
 struct GramPlan {
@@ -32,6 +33,7 @@ struct GramPlan {
     int n_tasks[kWarps];
     unsigned char gi[kWarps][kMaxSlots];
     unsigned char gj[kWarps][kMaxSlots];
+    unsigned char mk[kWarps][kMaxSlots];   // which of the task's gs x gs blocks this slot owns (bit u*gs+v)
 };
 
 struct GramArgs {
@@ -98,43 +100,35 @@ __device__ __forceinline__ void write_row(const mlmcb200_basis_t& b, double t, b
     for (int i = R; i < r_pad; ++i) row[i] = 0.0;
 }
 
-// All DMMAs of one task (GS x GS blocks of shape SHAPE) for one 4-sample step.  Products into the same accumulator
-// are issued in separate passes so that consecutive DMMAs are independent.
-template <int GS, int SHAPE>
-__device__ __forceinline__ constexpr bool block_on(int u, int v) {
-    return SHAPE == 0 ? true : SHAPE == 1 ? v == 0 : SHAPE == 2 ? v >= u : (u == 0 && v == 0);
-}
-
-template <bool COARSE, int MODE, int GS, int SHAPE>
+// All DMMAs of one task for one 4-sample step.  MASK = the 8x8 blocks of the GS x GS group this slot owns
+// (bit u*GS+v).  Products into the same accumulator are issued in separate passes so that consecutive DMMAs are
+// independent; only the fragments the mask needs are loaded.
+template <bool COARSE, int MODE, int GS, int MASK>
 __device__ __forceinline__ void slot_mma(double (&am)[GS][GS][2], double (&av)[GS][GS][2], const double* pf,
                                          const double* pc, const int (&off_r)[GS], const int (&off_c)[GS]) {
-    constexpr int NR = (SHAPE == 3) ? 1 : GS;                 // row / column fragments actually needed
-    constexpr int NC = (SHAPE == 1 || SHAPE == 3) ? 1 : GS;
     double fr[GS], cr[GS], fcol[GS], ccol[GS];
 #pragma unroll
     for (int u = 0; u < GS; ++u) {
         fr[u] = cr[u] = fcol[u] = ccol[u] = 0.0;
-        if (u < NR) {
+        bool row_used = false, col_used = false;
+#pragma unroll
+        for (int v = 0; v < GS; ++v) {
+            row_used = row_used || ((MASK >> (u * GS + v)) & 1);
+            col_used = col_used || ((MASK >> (v * GS + u)) & 1);
+        }
+        if (row_used) {
             fr[u] = pf[off_r[u]];
             if (COARSE) cr[u] = pc[off_r[u]];
         }
-    }
-#pragma unroll
-    for (int v = 0; v < GS; ++v) {
-        if (v < NC) {
-            if (SHAPE == 2 || SHAPE == 3) {                    // diagonal task: column fragments = row fragments
-                fcol[v] = fr[v];
-                ccol[v] = cr[v];
-            } else {
-                fcol[v] = pf[off_c[v]];
-                if (COARSE) ccol[v] = pc[off_c[v]];
-            }
+        if (col_used) {
+            fcol[u] = pf[off_c[u]];
+            if (COARSE) ccol[u] = pc[off_c[u]];
         }
     }
 #define MB_FOR_BLOCKS(BODY)                                                     \
     _Pragma("unroll") for (int u = 0; u < GS; ++u) {                            \
         _Pragma("unroll") for (int v = 0; v < GS; ++v) {                        \
-            if (block_on<GS, SHAPE>(u, v)) { BODY }                             \
+            if ((MASK >> (u * GS + v)) & 1) { BODY }                            \
         }                                                                       \
     }
     if (MODE == 2) {
@@ -161,24 +155,42 @@ __device__ __forceinline__ void slot_mma(double (&am)[GS][GS][2], double (&av)[G
 #undef MB_FOR_BLOCKS
 }
 
+// the block masks the planner can emit (make_plan): whole group, one column, one row, upper triangle, single blocks
+#define MB_SLOT_SWITCH(MASKVAR, CALL)                                           \
+    switch (MASKVAR) {                                                          \
+        case 0xF: CALL(0xF); break;                                             \
+        case 0x5: CALL(0x5); break;                                             \
+        case 0xA: CALL(0xA); break;                                             \
+        case 0xB: CALL(0xB); break;                                             \
+        case 0x3: CALL(0x3); break;                                             \
+        case 0x1: CALL(0x1); break;                                             \
+        case 0x8: CALL(0x8); break;                                             \
+        default: break;                                                         \
+    }
+
 // MODE 0: covariance sums only; 1: covariance sums + sums of squares; 2: Gram of the differences
-template <bool COARSE, int MODE, int GS>
+//
+// PIPE = true (MODE 0 / 2): warp-specialised.  The last kGenWarps warps (one per SM sub-partition) only PRODUCE basis
+//   rows -- one (sample, side) recurrence per thread, FP64 pipe -- into one of two shared-memory tiles while the other
+//   12 warps CONSUME the previous tile with DMMA (tensor pipe); one __syncthreads per tile.
+// PIPE = false (MODE 1, whose 4 accumulators per block leave no registers for a third task slot): all 16 warps
+//   produce a single, larger tile, then all consume it.
+template <bool COARSE, int MODE, int GS, bool PIPE>
 __global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a) {
     extern __shared__ double sm[];
     const GramPlan& pl = a.plan;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int LD = pl.ld, NS = pl.ns, nb = pl.nb, r_pad = 8 * nb;
-    double* const phi_f = sm;
-    double* const phi_c = sm + (size_t)NS * LD;
-    int* const flags = reinterpret_cast<int*>(sm + (size_t)2 * NS * LD);   // [NS] sample validity
+    const int LD = pl.ld, NS = pl.ns, nb = pl.nb, r_pad = 8 * nb, R = a.basis.size;
+    constexpr int SLOTS = PIPE ? 3 : 2;
+    const size_t tile_elems = (size_t)2 * NS * LD;             // Phi_f rows then Phi_c rows
     __shared__ unsigned cnt_sm[2];
     if (tid == 0) cnt_sm[0] = cnt_sm[1] = 0;
 
     const int my_tasks = pl.n_tasks[warp];
-    double acc_m[kMaxSlots][GS][GS][2];
-    double acc_v[MODE == 1 ? kMaxSlots : 1][GS][GS][2];
+    double acc_m[SLOTS][GS][GS][2];
+    double acc_v[MODE == 1 ? SLOTS : 1][GS][GS][2];
 #pragma unroll
-    for (int s = 0; s < kMaxSlots; ++s)
+    for (int s = 0; s < SLOTS; ++s)
 #pragma unroll
         for (int u = 0; u < GS; ++u)
 #pragma unroll
@@ -192,83 +204,97 @@ __global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a)
     const int frag_off = (lane & 3) * LD + (lane >> 2);
     unsigned cnt_ok = 0, cnt_rm = 0;
 
-    // decode this warp's task list ONCE: shared-memory column offsets of its row / column fragments and the SHAPE of
-    // each task = which of its GS x GS 8x8 blocks exist and lie on or above the diagonal:
-    //   0 = all, 1 = first column only (last, half-filled column group), 2 = upper triangle (diagonal task),
-    //   3 = block (0,0) only, 4 = empty slot.
-    int off_r[kMaxSlots][GS], off_c[kMaxSlots][GS], shape[kMaxSlots];
+    // decode this warp's task list ONCE: shared-memory column offsets of its row / column fragments and the mask of
+    // 8x8 blocks each slot owns (0 = empty slot)
+    int off_r[SLOTS][GS], off_c[SLOTS][GS], mask[SLOTS];
 #pragma unroll
-    for (int slot = 0; slot < kMaxSlots; ++slot) {
+    for (int slot = 0; slot < SLOTS; ++slot) {
         const bool used = slot < my_tasks;
-        const int gi = used ? pl.gi[warp][slot] : 0, gj = used ? pl.gj[warp][slot] : 0;
-        const int bi0 = gi * GS, bj0 = gj * GS;
+        const int bi0 = used ? pl.gi[warp][slot] * GS : 0, bj0 = used ? pl.gj[warp][slot] * GS : 0;
 #pragma unroll
         for (int u = 0; u < GS; ++u) {
             off_r[slot][u] = 8 * min(bi0 + u, nb - 1);
             off_c[slot][u] = 8 * min(bj0 + u, nb - 1);
         }
-        const bool col_full = bj0 + GS <= nb;                   // the row group of a task is full unless gi == gj
-        shape[slot] = !used ? 4 : (gi == gj ? ((GS > 1 && col_full) ? 2 : 3) : ((GS > 1 && col_full) ? 0 : 1));
+        mask[slot] = used ? pl.mk[warp][slot] : 0;
     }
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t n0 = tile * NS;
-        // ---- phase A: basis rows of the tile into shared memory ----
-        for (int s = tid; s < NS; s += kThreadsGram) flags[s] = 1;
-        __syncthreads();
-        // pass 1: map values, AND the validity of both sides
-        for (int w = tid; w < NS * n_sides; w += kThreadsGram) {
+    // basis rows of one tile: item w = (sample s, side); every item tests both sides of its sample for validity
+    auto produce = [&](int64_t tile, double* tile_base, int first, int n_threads) {
+        for (int w = first; w < NS * n_sides; w += n_threads) {
             const int side = w >= NS ? 1 : 0, s = w - side * NS;
-            const int64_t n = n0 + s;
-            if (n < a.n) {
-                const double x = __ldcs(a.pairs + n * a.stride_n + side * a.stride_side);
-                const double t = a.basis.kind == MLMCB200_RAW ? x : map_to_ref(a.basis, x);
-                if (!moments_finite(a.basis, t)) flags[s] = 0;
-                (side == 0 ? phi_f : phi_c)[(size_t)s * LD] = t;           // park t in column 0
-            } else {
-                flags[s] = 0;
+            const int64_t n = tile * NS + s;
+            double* row = tile_base + ((size_t)side * NS + s) * LD;
+            bool good = n < a.n;
+            double t = 0.0;
+            if (good) {
+                const double xf = __ldcs(a.pairs + n * a.stride_n);
+                const double tf = a.basis.kind == MLMCB200_RAW ? xf : map_to_ref(a.basis, xf);
+                good = moments_finite(a.basis, tf);
+                t = tf;
+                if (COARSE) {
+                    const double xc = __ldcs(a.pairs + n * a.stride_n + a.stride_side);
+                    const double tc = a.basis.kind == MLMCB200_RAW ? xc : map_to_ref(a.basis, xc);
+                    good = good && moments_finite(a.basis, tc);
+                    if (side == 1) t = tc;
+                }
+                if (side == 0) {
+                    cnt_ok += good ? 1u : 0u;
+                    cnt_rm += good ? 0u : 1u;
+                }
             }
+            write_row(a.basis, t, good, row, r_pad);
         }
-        __syncthreads();
-        for (int w = tid; w < NS * n_sides; w += kThreadsGram) {
-            const int side = w >= NS ? 1 : 0, s = w - side * NS;
-            double* row = (side == 0 ? phi_f : phi_c) + (size_t)s * LD;
-            const bool good = flags[s] != 0;
-            if (side == 0 && n0 + s < a.n) {
-                cnt_ok += good ? 1u : 0u;
-                cnt_rm += good ? 0u : 1u;
-            }
-            write_row(a.basis, row[0], good, row, r_pad);
-        }
-        __syncthreads();
-
-        // ---- phase B: DMMA over the tile, 4 samples per step ----
+    };
+    auto consume = [&](const double* tile_base) {
+        const double* phi_f = tile_base;
+        const double* phi_c = tile_base + (size_t)NS * LD;
         for (int k0 = 0; k0 < NS; k0 += 4) {
             const double* pf = phi_f + (size_t)k0 * LD + frag_off;
             const double* pc = phi_c + (size_t)k0 * LD + frag_off;
 #pragma unroll
-            for (int slot = 0; slot < kMaxSlots; ++slot) {
-                const double* rf = pf;
-                const double* rc = pc;
-                switch (shape[slot]) {                         // warp-uniform; straight-line DMMA runs inside
-                    case 0: slot_mma<COARSE, MODE, GS, 0>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], rf, rc, off_r[slot], off_c[slot]); break;
-                    case 1: slot_mma<COARSE, MODE, GS, 1>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], rf, rc, off_r[slot], off_c[slot]); break;
-                    case 2: slot_mma<COARSE, MODE, GS, 2>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], rf, rc, off_r[slot], off_c[slot]); break;
-                    case 3: slot_mma<COARSE, MODE, GS, 3>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], rf, rc, off_r[slot], off_c[slot]); break;
-                    default: break;
+            for (int slot = 0; slot < SLOTS; ++slot) {
+                if (GS == 1) {
+                    if (mask[slot]) slot_mma<COARSE, MODE, GS, 0x1>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], pf, pc, off_r[slot], off_c[slot]);
+                } else {
+#define MB_CALL(M) slot_mma<COARSE, MODE, GS, M>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], pf, pc, off_r[slot], off_c[slot])
+                    MB_SLOT_SWITCH(mask[slot], MB_CALL)           // warp-uniform; straight-line DMMA runs inside
+#undef MB_CALL
                 }
             }
         }
+    };
+
+    if (PIPE) {
+        constexpr int kGenThreads = kGenWarps * 32, kMmaThreads = kThreadsGram - kGenThreads;
+        const bool is_gen = tid >= kMmaThreads;
+        if (is_gen) produce(blockIdx.x, sm, tid - kMmaThreads, kGenThreads);
         __syncthreads();
+        int buf = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+            if (is_gen) {
+                if (tile + gridDim.x < n_tiles)
+                    produce(tile + gridDim.x, sm + (buf ^ 1) * tile_elems, tid - kMmaThreads, kGenThreads);
+            } else {
+                consume(sm + buf * tile_elems);
+            }
+            __syncthreads();
+        }
+    } else {
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            produce(tile, sm, tid, kThreadsGram);
+            __syncthreads();
+            consume(sm);
+            __syncthreads();
+        }
     }
 
     // ---- epilogue: one partial [2 + 2 R R] per CTA, upper blocks mirrored ----
-    const int R = a.basis.size;
     double* const out = a.partial + (int64_t)blockIdx.x * a.partial_stride;
     double* const out_m = out + 2;
     double* const out_v = out + 2 + (int64_t)R * R;
 #pragma unroll
-    for (int slot = 0; slot < kMaxSlots; ++slot) {
+    for (int slot = 0; slot < SLOTS; ++slot) {
         if (slot < my_tasks) {
             const int bi0 = pl.gi[warp][slot] * GS, bj0 = pl.gj[warp][slot] * GS;
 #pragma unroll
@@ -276,7 +302,7 @@ __global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a)
 #pragma unroll
                 for (int v = 0; v < GS; ++v) {
                     const int I = bi0 + u, J = bj0 + v;
-                    if (I < nb && J < nb && J >= I) {
+                    if ((pl.mk[warp][slot] >> (u * GS + v)) & 1) {
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int i = 8 * I + (lane >> 2), j = 8 * J + 2 * (lane & 3) + e;
@@ -303,62 +329,92 @@ __global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a)
     }
 }
 
-int make_plan(int R, GramPlan* pl, size_t* smem) {
+int popcount4(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1); }
+
+// n_warps / n_slots: warps that contract and task slots per warp; two_tiles: double-buffered (pipelined) layout
+int make_plan(int R, int n_warps, int n_slots, bool two_tiles, GramPlan* pl, size_t* smem) {
     const int nb = (R + 7) / 8;
     pl->nb = nb;
     pl->gs = nb <= 5 ? 1 : 2;
-    const int ng = (nb + pl->gs - 1) / pl->gs;
-    const int n_tasks = ng * (ng + 1) / 2;
-    if (n_tasks > kWarps * kMaxSlots) {
-        set_error("gram: %d moments need %d block tasks (max %d)", R, n_tasks, kWarps * kMaxSlots);
-        return -1;
-    }
-    // task weights = number of 8x8 blocks on/above the diagonal, assigned greedily (largest first)
-    struct T { int gi, gj, w; } tasks[kWarps * kMaxSlots];
-    int nt = 0;
+    const int gs = pl->gs;
+    const int ng = (nb + gs - 1) / gs;
+    const int kMaxTasks = n_warps * n_slots;
+    // natural tasks: one per pair of block groups on/above the diagonal; mask = blocks that exist and have J >= I
+    struct T { int gi, gj, mask, w; } tasks[kWarps * kMaxSlots + 2];
+    int nt = 0, total = 0;
     for (int gi = 0; gi < ng; ++gi)
         for (int gj = gi; gj < ng; ++gj) {
-            int w = 0;
-            for (int u = 0; u < pl->gs; ++u)
-                for (int v = 0; v < pl->gs; ++v) {
-                    const int I = gi * pl->gs + u, J = gj * pl->gs + v;
-                    if (I < nb && J < nb && J >= I) ++w;
+            int mask = 0;
+            for (int u = 0; u < gs; ++u)
+                for (int v = 0; v < gs; ++v) {
+                    const int I = gi * gs + u, J = gj * gs + v;
+                    if (I < nb && J < nb && J >= I) mask |= 1 << (u * gs + v);
                 }
-            tasks[nt++] = {gi, gj, w};
+            if (nt >= kMaxTasks) {
+                set_error("gram: %d moments need more than %d block tasks", R, kMaxTasks);
+                return -1;
+            }
+            tasks[nt++] = {gi, gj, mask, popcount4(mask)};
+            total += popcount4(mask);
         }
-    for (int i = 0; i < nt; ++i)
-        for (int j = i + 1; j < nt; ++j)
-            if (tasks[j].w > tasks[i].w) { T t = tasks[i]; tasks[i] = tasks[j]; tasks[j] = t; }
-    int load[kWarps] = {0};
-    for (int w = 0; w < kWarps; ++w) pl->n_tasks[w] = 0;
-    for (int i = 0; i < nt; ++i) {
-        int best = -1;
-        for (int w = 0; w < kWarps; ++w)
-            if (pl->n_tasks[w] < kMaxSlots && (best < 0 || load[w] < load[best])) best = w;
-        pl->gi[best][pl->n_tasks[best]] = (unsigned char)tasks[i].gi;
-        pl->gj[best][pl->n_tasks[best]] = (unsigned char)tasks[i].gj;
-        pl->n_tasks[best]++;
-        load[best] += tasks[i].w;
+    // longest-processing-time assignment; while the heaviest warp exceeds the ideal load, split the biggest splittable
+    // task (whole group -> two columns, triangle -> first row + last block) and redo the assignment
+    const int target = (total + n_warps - 1) / n_warps;
+    int load[kWarps];
+    for (int round = 0; round < kMaxTasks; ++round) {
+        for (int i = 0; i < nt; ++i)
+            for (int j = i + 1; j < nt; ++j)
+                if (tasks[j].w > tasks[i].w) { T t = tasks[i]; tasks[i] = tasks[j]; tasks[j] = t; }
+        for (int w = 0; w < kWarps; ++w) { pl->n_tasks[w] = 0; load[w] = 0; }
+        for (int i = 0; i < nt; ++i) {
+            int best = -1;
+            for (int w = 0; w < n_warps; ++w)
+                if (pl->n_tasks[w] < n_slots && (best < 0 || load[w] < load[best])) best = w;
+            const int k = pl->n_tasks[best]++;
+            pl->gi[best][k] = (unsigned char)tasks[i].gi;
+            pl->gj[best][k] = (unsigned char)tasks[i].gj;
+            pl->mk[best][k] = (unsigned char)tasks[i].mask;
+            load[best] += tasks[i].w;
+        }
+        int worst = 0;
+        for (int w = 0; w < n_warps; ++w) worst = load[w] > worst ? load[w] : worst;
+        if (worst <= target || gs == 1 || nt + 1 > kMaxTasks) break;
+        int pick = -1;
+        for (int i = 0; i < nt; ++i)
+            if ((tasks[i].mask == 0xF || tasks[i].mask == 0xB) && (pick < 0 || tasks[i].w > tasks[pick].w)) pick = i;
+        if (pick < 0) break;
+        const T t = tasks[pick];
+        if (t.mask == 0xF) {
+            tasks[pick] = {t.gi, t.gj, 0x5, 2};
+            tasks[nt++] = {t.gi, t.gj, 0xA, 2};
+        } else {
+            tasks[pick] = {t.gi, t.gj, 0x3, 2};
+            tasks[nt++] = {t.gi, t.gj, 0x8, 1};
+        }
     }
     int ld = 8 * nb;
     while (ld % 8 != 4) ++ld;
     pl->ld = ld;
-    const size_t budget = 200u * 1024u;
-    int ns = (int)(budget / ((size_t)2 * ld * sizeof(double)));
-    ns = (ns / 32) * 32;
-    if (ns > 128) ns = 128;
-    if (ns < 32) {
+    // tile(s) of Phi_f + Phi_c rows; NS a multiple of 4
+    const size_t budget = 216u * 1024u;
+    const int n_tiles = two_tiles ? 2 : 1;
+    int ns = (int)(budget / ((size_t)2 * n_tiles * ld * sizeof(double)));
+    ns = (ns / 4) * 4;
+    const int cap = two_tiles ? 64 : 128;
+    if (ns > cap) ns = cap;
+    if (ns < 8) {
         set_error("gram: %d moments do not fit the shared-memory tile", R);
         return -1;
     }
     pl->ns = ns;
-    *smem = (size_t)2 * ns * ld * sizeof(double) + (size_t)ns * sizeof(int);
+    *smem = (size_t)2 * n_tiles * ns * ld * sizeof(double);
     return 0;
 }
 
 template <bool COARSE, int MODE, int GS>
 int launch_gram(const GramArgs& a, int grid, size_t smem, cudaStream_t st) {
-    auto kern = gram_kernel<COARSE, MODE, GS>;
+    constexpr bool kPipe = MODE != 1;
+    auto kern = gram_kernel<COARSE, MODE, GS, kPipe>;
     MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreadsGram, smem, st>>>(a);
     MB_CUDA_OK(cudaGetLastError());
@@ -370,7 +426,6 @@ int launch_gram_gs(const GramArgs& a, int grid, size_t smem, cudaStream_t st) {
     return a.plan.gs == 1 ? launch_gram<COARSE, MODE, 1>(a, grid, smem, st)
                           : launch_gram<COARSE, MODE, 2>(a, grid, smem, st);
 }
-
 
 // ------------------------------------------------------------------------------------------------------------
 // Max-entropy functional pieces on a fixed node set (mlmc/tool/simple_distribution.py:254-327):
@@ -459,7 +514,8 @@ __global__ void __launch_bounds__(kThreadsGram, 1) maxent_kernel(const MaxentArg
 #pragma unroll
                             for (int v = 0; v < GS; ++v) {
                                 const int I = bi0 + u, J = bj0 + v;
-                                if (I < nb && J < nb && J >= I) dmma(acc[slot][u][v][0], acc[slot][u][v][1], fr[u], fcol[v]);
+                                (void)I; (void)J;
+                                if ((pl.mk[warp][slot] >> (u * GS + v)) & 1) dmma(acc[slot][u][v][0], acc[slot][u][v][1], fr[u], fcol[v]);
                             }
                     }
                 }
@@ -481,7 +537,7 @@ __global__ void __launch_bounds__(kThreadsGram, 1) maxent_kernel(const MaxentArg
 #pragma unroll
                     for (int v = 0; v < GS; ++v) {
                         const int I = bi0 + u, J = bj0 + v;
-                        if (I < nb && J < nb && J >= I) {
+                        if ((pl.mk[warp][slot] >> (u * GS + v)) & 1) {
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 const int i = 8 * I + (lane >> 2), j = 8 * J + 2 * (lane & 3) + e;
@@ -540,7 +596,8 @@ extern "C" int mlmcb200_gram_accumulate(const mlmcb200_basis_t* basis, const dou
     a.stride_n = stride_n;
     a.stride_side = stride_side;
     size_t smem = 0;
-    if (make_plan(basis->size, &a.plan, &smem) != 0) return -1;
+    const bool pipe = !(mode == 0 && want_var);                 // MODE 1 (sums + squares) is the non-pipelined variant
+    if (make_plan(basis->size, pipe ? kWarps - kGenWarps : kWarps, pipe ? 3 : 2, pipe, &a.plan, &smem) != 0) return -1;
     const int64_t R2 = (int64_t)basis->size * basis->size;
     const int64_t stride = 2 + 2 * R2;
     const int64_t tiles = (n + a.plan.ns - 1) / a.plan.ns;
@@ -583,7 +640,7 @@ extern "C" int mlmcb200_maxent_fgh(const double* phi, int64_t ld, const double* 
     a.R = size;
     a.want_h = (what & 4) ? 1 : 0;
     size_t smem = 0;
-    if (make_plan(size, &a.plan, &smem) != 0) return -1;
+    if (make_plan(size, kWarps, 2, false, &a.plan, &smem) != 0) return -1;
     // single table + weights + multipliers instead of two tables + flags
     const int ns = a.plan.ns;
     smem = ((size_t)ns * a.plan.ld + ns + 8 * a.plan.nb) * sizeof(double);

@@ -213,8 +213,9 @@ def test_covariance_sizes_vs_oracle(kind, R):
     assert np.array_equal(res["n"], want.n_samples) and np.array_equal(res["n_rm"], want.n_rm_samples)
     rel_close(res["l_means"], want.l_means, rtol=1e-8, atol_scale=1e-13)
     rel_close(res["l_vars"], want.l_vars, rtol=1e-8, atol_scale=1e-13)
-    mean_only = run_gram(to_struct(b), levels, False, 1000)
-    assert np.array_equal(mean_only["l_means"], res["l_means"])
+    mean_only = run_gram(to_struct(b), levels, False, 1000)       # pipelined variant: another summation order
+    rel_close(mean_only["l_means"], res["l_means"], rtol=1e-11, atol_scale=1e-14)
+    rel_close(mean_only["l_means"], want.l_means, rtol=1e-8, atol_scale=1e-13)
 
 
 def test_difference_gram_vs_oracle():
