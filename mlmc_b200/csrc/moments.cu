@@ -499,7 +499,16 @@ int choose_S(int kind) { return kind == MLMCB200_FOURIER ? 4 : 8; }
 
 int plan_moments(int kind, int size, int n_comp, int64_t n, Plan* p) {
     p->S = choose_S(kind);
-    p->pair = n_comp == 1;
+    // Lane-pair columns halve the shared memory per thread at the price of a shuffle in every moment's reduction tail:
+    // worth it only where private columns would cap the CTAs per SM below what the registers allow (2 for the
+    // fine+coarse kernels), i.e. above ~56 moments.  MLMCB200_PAIR=0|1 overrides (experiments).
+    static int forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("MLMCB200_PAIR");
+        forced = e ? atoi(e) : -1;
+    }
+    p->pair = n_comp == 1 && (size_t)2 * size * kThreads * sizeof(double) > 113u * 1024u;
+    if (forced >= 0 && n_comp == 1) p->pair = forced != 0;
     p->fast = false;
     const size_t smem = (size_t)(p->pair ? 1 : 2) * size * kThreads * sizeof(double);
     if (smem > 227u * 1024u) {
@@ -544,9 +553,11 @@ int launch_moments(const MomentsArgs& a, Plan p, cudaStream_t st) {
 
 template <int KIND, bool COARSE, bool LOG, int S>
 int launch_moments_pair(const MomentsArgs& a, const Plan& p, cudaStream_t st) {
-    if (!p.pair) return launch_moments<KIND, COARSE, LOG, S, false, false>(a, p, st);
-    if (KIND != MLMCB200_RAW && p.fast) return launch_moments<KIND, COARSE, LOG, S, true, true>(a, p, st);
-    return launch_moments<KIND, COARSE, LOG, S, true, false>(a, p, st);
+    if (KIND != MLMCB200_RAW && p.fast)
+        return p.pair ? launch_moments<KIND, COARSE, LOG, S, true, true>(a, p, st)
+                      : launch_moments<KIND, COARSE, LOG, S, false, true>(a, p, st);
+    return p.pair ? launch_moments<KIND, COARSE, LOG, S, true, false>(a, p, st)
+                  : launch_moments<KIND, COARSE, LOG, S, false, false>(a, p, st);
 }
 
 template <int KIND, bool COARSE, bool LOG>
