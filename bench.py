@@ -257,16 +257,18 @@ def run_gpu_arm(args):
     if rank == 0:
         sampler.start()
     torch.cuda.synchronize()
-    # per-kernel timing of the dominant kernel (level 1: fine + coarse) on the launching stream
+    # per-launch time of the dominant kernel (level 1: fine + coarse) with CUDA events on the launching stream:
+    # 10 back-to-back launches per measurement (each = moments kernel + its 5 us partial reduction), best of 3
     k_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     cur = torch.cuda.current_stream()
     kernel_ms = []
     for _ in range(3):
         k_ev[0].record(cur)
-        nat.moments_accumulate(basis, views[1], acc.level(1))
+        for _rep in range(10):
+            nat.moments_accumulate(basis, views[1], acc.level(1))
         k_ev[1].record(cur)
         torch.cuda.synchronize()
-        kernel_ms.append(k_ev[0].elapsed_time(k_ev[1]))
+        kernel_ms.append(k_ev[0].elapsed_time(k_ev[1]) / 10)
     kernel_ms = float(np.min(kernel_ms))
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -334,8 +336,9 @@ def run_gpu_arm(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     dfma_peak = nat.fp64_peak(0) / 1e12
-    # algorithmic work of one launch over a level with a coarse part: 16 B and 7 FP64 instr (=14 flop with FMA = 2,
-    # DESIGN.md "Rooflines") per sample-moment
+    # algorithmic work of one launch over a level with a coarse part: 16 B per sample and 7 FP64 instructions per
+    # sample-moment (2 x (DMUL + DFMA) recurrence, f - c, sum, FMA square), counted as 14 flop -- one FMA-equivalent
+    # per instruction slot, the way the DFMA peak is counted
     alg_bytes = n_rows * 16.0
     alg_flop = n_rows * N_MOMENTS * 14.0
     achieved_tflops = alg_flop / (kernel_ms * 1e-3) / 1e12
