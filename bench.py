@@ -191,7 +191,9 @@ def run_gpu_arm(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
-    os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")   # NCCL prints its banner on stdout
+    # NCCL writes its debug stream (incl. the "NCCL version" banner at VERSION/WARN level) to stdout by default, which
+    # would put a non-JSON line before ours: send it to stderr instead
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, world, local = mdist.init_from_env()
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)

@@ -55,6 +55,30 @@ def all_reduce_sum(tensor):
     return tensor
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (pinned staging buffers are then allocated
+    next to the PCIe root of the GPU they feed).  Best effort: silently does nothing where sysfs does not tell."""
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        pass
+    return None
+
+
 def init_from_env(backend=None):
     """Initialise the default process group from torchrun's environment (RANK / WORLD_SIZE / LOCAL_RANK /
     MASTER_ADDR / MASTER_PORT) and enable sharding.  Returns (rank, world, local_rank)."""
@@ -67,6 +91,7 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if torch.cuda.is_available():
             torch.cuda.set_device(local)
+            bind_to_gpu_numa_node(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         kw = {}
         if backend == "nccl":
