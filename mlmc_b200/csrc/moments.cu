@@ -511,7 +511,7 @@ int plan_moments(int kind, int size, int n_comp, int64_t n, Plan* p) {
     if (forced >= 0 && n_comp == 1) p->pair = forced != 0;
     p->fast = false;
     const size_t smem = (size_t)(p->pair ? 1 : 2) * size * kThreads * sizeof(double);
-    if (smem > 227u * 1024u) {
+    if (smem + 64 > 227u * 1024u) {        // 64 B: static shared memory of the kernel (sample counters)
         set_error("moments: size %d needs %zu B of shared memory per CTA (max %u)", size, smem, 227u * 1024u);
         return -1;
     }

@@ -303,3 +303,97 @@ def test_large_run_properties():
     out = acc.finalize()
     rel_close(out["l_means"][1].cpu().numpy(), want.l_means[1], rtol=1e-10)
     rel_close(out["l_vars"][1].cpu().numpy(), want.l_vars[1], rtol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------------------
+# edge cases: ragged / tiny / empty inputs, degenerate levels, size limits
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sizes", [[1, 3], [7, 1], [1025, 2, 1], [129, 128, 127]])
+def test_ragged_and_tiny_levels_match_oracle(sizes):
+    rng = np.random.default_rng(sum(sizes))
+    steps = orc.level_steps(len(sizes), (0.4, 0.01)) if len(sizes) > 1 else [0.4]
+    levels = [orc.synth_level_rows(rng.normal(size=n), steps[l], steps[l - 1] if l else None)
+              for l, n in enumerate(sizes)]
+    b = orc.Basis("legendre", 9, (-5.0, 5.0))
+    with np.errstate(all="ignore"):
+        want = orc.estimate_moments(levels, b)
+    res = run_moments(to_struct(b), levels, 100)
+    assert np.array_equal(res["n"], want.n_samples)
+    rel_close(res["l_means"], want.l_means, rtol=1e-10)
+    finite = np.isfinite(want.l_vars)
+    assert np.array_equal(np.isinf(res["l_vars"]), np.isinf(want.l_vars))          # n == 1 -> +inf (quantity_estimate.py:77)
+    rel_close(res["l_vars"][finite], want.l_vars[finite], rtol=1e-9, atol_scale=1e-13)
+
+
+def test_fully_masked_level_behaves_like_reference():
+    """One level loses every sample: the reference divides by n = 0 (NaN mean, inf variance) and goes on."""
+    rng = np.random.default_rng(3)
+    levels = [orc.synth_level_rows(rng.normal(size=50), 0.1, None), np.full((20, 2, 1), 99.0)]
+    b = orc.Basis("monomial", 4, (-5.0, 5.0))
+    with np.errstate(all="ignore"):
+        want = orc.estimate_moments(levels, b)
+    res = run_moments(to_struct(b), levels)
+    assert np.array_equal(res["n"], [50, 0]) and np.array_equal(res["n_rm"], [0, 20])
+    assert np.isnan(res["l_means"][1]).all() and np.isinf(res["l_vars"][1]).all()
+    rel_close(res["l_means"][0], want.l_means[0], rtol=1e-10)
+
+
+def test_empty_chunk_is_a_no_op():
+    nat = native()
+    b = to_struct(orc.Basis("legendre", 5, (-1.0, 1.0)))
+    acc = nat.LevelAccumulator(1, 5, dev())
+    nat.moments_accumulate(b, torch.empty(1, 0, 2, dtype=torch.float64, device=dev()), acc.level(0))
+    acc2 = nat.LevelAccumulator(1, 25, dev())
+    nat.gram_accumulate(b, torch.empty(1, 0, 2, dtype=torch.float64, device=dev()), acc2.level(0))
+    assert float(acc.acc.abs().sum()) == 0.0 and float(acc2.acc.abs().sum()) == 0.0
+
+
+def test_size_limits_and_error_text():
+    nat = native()
+    x = torch.zeros(1, 64, 2, dtype=torch.float64, device=dev())
+    for size in (113, 226):                       # largest sizes with private / lane-pair accumulator columns
+        b = to_struct(orc.Basis("legendre", size, (-1.0, 1.0)))
+        acc = nat.LevelAccumulator(1, size, dev())
+        nat.moments_accumulate(b, x, acc.level(0))
+        a = acc.acc.cpu().numpy()[0]
+        assert a[0] == 64 and a[2] == 0.0          # P_k(0) - P_k(0) = 0 for every k
+    with pytest.raises(nat.NativeError, match="shared memory"):
+        b = to_struct(orc.Basis("legendre", 240, (-1.0, 1.0)))
+        nat.moments_accumulate(b, x, nat.LevelAccumulator(1, 240, dev()).level(0))
+    with pytest.raises(nat.NativeError, match="block tasks|do not fit"):
+        b = to_struct(orc.Basis("legendre", 130, (-1.0, 1.0)))
+        nat.gram_accumulate(b, x, nat.LevelAccumulator(1, 130 * 130, dev()).level(0))
+    with pytest.raises(nat.NativeError, match="basis size"):
+        nat.basis_eval(nat.BasisStruct(1, 300, 0, 1, 0.0, 1.0, -1.0, 1.0), torch.zeros(4, dtype=torch.float64, device=dev()), 3)
+
+
+def test_large_moment_count_values_match_oracle():
+    """R = 200 (lane-pair columns, one CTA per SM): monic recurrence stays accurate over the whole range."""
+    rng = np.random.default_rng(200)
+    rows = orc.synth_level_rows(rng.uniform(-1.0, 1.0, size=3000), 0.02, 0.2)
+    b = orc.Basis("legendre", 200, (-1.3, 1.3))
+    want = orc.estimate_moments([np.zeros((1, 2, 1)), rows], b)
+    nat = native()
+    acc = nat.LevelAccumulator(2, 200, dev())
+    nat.moments_accumulate(to_struct(b), torch.zeros(1, 1, 1, dtype=torch.float64, device=dev()), acc.level(0))
+    nat.moments_accumulate(to_struct(b), torch.from_numpy(rows).to(dev()).permute(2, 0, 1), acc.level(1))
+    out = acc.finalize()
+    rel_close(out["l_means"][1].cpu().numpy(), want.l_means[1], rtol=1e-9, atol_scale=1e-13)
+    rel_close(out["l_vars"][1].cpu().numpy(), want.l_vars[1], rtol=1e-9, atol_scale=1e-13)
+
+
+def test_strided_scalar_column_of_wide_storage():
+    """A scalar quantity that is one column of a 24-component storage row (strides 48 / 24 / 1): generic path."""
+    rng = np.random.default_rng(11)
+    wide = rng.normal(size=(700, 2, 24))
+    b = orc.Basis("legendre", 7, (-3.0, 3.0))
+    nat = native()
+    for col in (0, 5, 23):
+        want = orc.estimate_moments([np.zeros((1, 2, 1)), wide[:, :, col:col + 1]], b)
+        acc = nat.LevelAccumulator(1, 7, dev())
+        x = torch.from_numpy(wide).to(dev()).permute(2, 0, 1)[col:col + 1]
+        nat.moments_accumulate(to_struct(b), x, acc.level(0))
+        a = acc.acc.cpu().numpy()[0]
+        n = a[0]
+        assert n == want.n_samples[1]
+        rel_close(a[2:9] / n, want.l_means[1], rtol=1e-10, atol_scale=1e-14)
