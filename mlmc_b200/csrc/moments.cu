@@ -47,10 +47,11 @@ struct MomentsArgs {
 // lane the sum of squares of both (one 64-bit shuffle) -- which halves the shared memory per thread and so doubles
 // the number of resident warps for a given number of moments.
 template <bool COARSE, int S, bool PAIR>
-__device__ __forceinline__ void accumulate(double* __restrict__ sm, int k, int R, int tid,
+__device__ __forceinline__ void accumulate(double* __restrict__ col, int sq_off, bool odd,
                                            const double (&vf)[S], const double (&vc)[S]) {
+    // col = this thread's column entry of the moment (sm + k*T + tid); the squares live sq_off doubles further (private
+    // columns) or in the odd lane's entry (lane pairs)
     static_assert(S % 2 == 0, "S must be even");
-    constexpr int T = 128;
     double d[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) d[s] = COARSE ? vf[s] - vc[s] : vf[s];
@@ -67,12 +68,11 @@ __device__ __forceinline__ void accumulate(double* __restrict__ sm, int k, int R
     }
     const double p1 = d[0], p2 = qa + qb;
     if (PAIR) {
-        const bool odd = tid & 1;
         const double recv = __shfl_xor_sync(0xffffffffu, odd ? p1 : p2, 1);
-        sm[k * T + tid] += (odd ? p2 : p1) + recv;
+        *col += (odd ? p2 : p1) + recv;
     } else {
-        sm[k * T + tid] += p1;
-        sm[(R + k) * T + tid] += p2;
+        *col += p1;
+        col[sq_off] += p2;
     }
 }
 
@@ -132,7 +132,17 @@ moments_acc_kernel(const MomentsArgs a) {
     const bool count_here = (blockIdx.x == 0) && (M >= T ? tid == 0 : m == 0);
     unsigned cnt_ok = 0, cnt_rm = 0;
 
-#define MB_ACC(K, VF, VC) accumulate<COARSE, S, PAIR>(sm, (K), R, tid, VF, VC)
+    // the moment index is kept out of the vector address arithmetic (column pointer + constant steps) so that the loop
+    // counter -- and with it the recurrence coefficients fetched by it -- stays in uniform registers
+    double* const col0 = sm + tid;
+    const int sq_off = R * T;
+    const bool odd_lane = tid & 1;
+    // moments are reduced strictly in increasing order: a running column pointer replaces the index arithmetic
+#define MB_ACC(K, VF, VC)                                                       \
+    {                                                                            \
+        accumulate<COARSE, S, PAIR>(col, sq_off, odd_lane, VF, VC);              \
+        col += T;                                                                \
+    }
 
     // software pipeline: the raw values of the NEXT tile are in flight while the current tile is reduced
     double xf[S], xc[S];
@@ -223,6 +233,7 @@ moments_acc_kernel(const MomentsArgs a) {
                 load_tile<COARSE, S>(a, base_f, (tile + gridDim.y) * tile_n + tn, TN, active, xf, xc);
         }
 
+        double* col = col0;                                      // column entry of the next moment to reduce
         if (KIND == MLMCB200_RAW) {
             MB_ACC(0, tf, tc);
         } else if (KIND == MLMCB200_LEGENDRE) {
@@ -252,21 +263,18 @@ moments_acc_kernel(const MomentsArgs a) {
         if (COARSE) zc[s] = tc[s] * DST_C[s];                                    \
     }
             int i = 2;                                                            // next moment to generate
-            if (R > 5) {
-                double e0 = kLegCoef[2], e1 = kLegCoef[3], e2 = kLegCoef[4], e3 = kLegCoef[5];
-                for (; i + 3 < R; i += 4) {
-                    // coefficients of the NEXT group are fetched now (the table is padded past MAX_MOMENTS)
-                    const double n0 = kLegCoef[i + 4], n1 = kLegCoef[i + 5], n2 = kLegCoef[i + 6], n3 = kLegCoef[i + 7];
-                    MB_REC(fb, cb, e0)
-                    MB_ACC(i - 1, fa, ca);
-                    MB_REC(fa, ca, e1)
-                    MB_ACC(i, fb, cb);
-                    MB_REC(fb, cb, e2)
-                    MB_ACC(i + 1, fa, ca);
-                    MB_REC(fa, ca, e3)
-                    MB_ACC(i + 2, fb, cb);
-                    e0 = n0; e1 = n1; e2 = n2; e3 = n3;
-                }
+            for (; i + 3 < R; i += 4) {
+                // e_k are read straight from constant memory with the (uniform) loop index so that they stay in
+                // UNIFORM registers: as a vector-register operand they would be the third register read of the DFMA
+                const double e0 = kLegCoef[i], e1 = kLegCoef[i + 1], e2 = kLegCoef[i + 2], e3 = kLegCoef[i + 3];
+                MB_REC(fb, cb, e0)
+                MB_ACC(i - 1, fa, ca);
+                MB_REC(fa, ca, e1)
+                MB_ACC(i, fb, cb);
+                MB_REC(fb, cb, e2)
+                MB_ACC(i + 1, fa, ca);
+                MB_REC(fa, ca, e3)
+                MB_ACC(i + 2, fb, cb);
             }
             for (; i < R; ++i) {                                                 // remainder, one moment at a time
                 const double e = kLegCoef[i];
@@ -279,8 +287,8 @@ moments_acc_kernel(const MomentsArgs a) {
                 }
             }
             if (R > 1) {                                                          // the last moment is still pending
-                if ((R - 1) & 1) MB_ACC(R - 1, fa, ca);
-                else MB_ACC(R - 1, fb, cb);
+                if ((R - 1) & 1) MB_ACC(R - 1, fa, ca)
+                else MB_ACC(R - 1, fb, cb)
             }
 #undef MB_REC
         } else if (KIND == MLMCB200_MONOMIAL) {
@@ -311,8 +319,8 @@ moments_acc_kernel(const MomentsArgs a) {
                 }
             }
             if (R > 1) {
-                if ((R - 1) & 1) MB_ACC(R - 1, fa, ca);
-                else MB_ACC(R - 1, fb, cb);
+                if ((R - 1) & 1) MB_ACC(R - 1, fa, ca)
+                else MB_ACC(R - 1, fb, cb)
             }
         } else {  // FOURIER: columns 1, cos t, sin t, cos 2t, sin 2t, ... by exact-angle rotation
             double cf1[S], sf1[S], cc1[S], sc1[S], cfk[S], sfk[S], cck[S], sck[S];
@@ -335,7 +343,7 @@ moments_acc_kernel(const MomentsArgs a) {
             }
             for (int i = 1; i < R; i += 2) {
                 MB_ACC(i, cfk, cck);
-                if (i + 1 < R) MB_ACC(i + 1, sfk, sck);
+                if (i + 1 < R) MB_ACC(i + 1, sfk, sck)
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     const double nc = fma(cfk[s], cf1[s], -(sfk[s] * sf1[s]));
