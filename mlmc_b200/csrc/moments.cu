@@ -501,12 +501,15 @@ struct Plan {
     bool fast;    // scalar quantity in storage order: specialised addressing
 };
 
-// Samples per thread and tile: 8 keeps the accumulator traffic per sample-moment low (Fourier carries twice the
-// state per sample and uses 4).
-int choose_S(int kind) { return kind == MLMCB200_FOURIER ? 4 : 8; }
+// Samples per thread and tile: 8 fine+coarse pairs = 16 independent recurrence chains per thread (Fourier carries twice
+// the state per sample and uses 4); a scalar level without coarse part takes 16 samples to keep the same 16 chains.
+int choose_S(int kind, bool coarse, bool scalar) {
+    if (kind == MLMCB200_FOURIER) return 4;
+    return (!coarse && scalar && kind != MLMCB200_RAW) ? 16 : 8;
+}
 
-int plan_moments(int kind, int size, int n_comp, int64_t n, Plan* p) {
-    p->S = choose_S(kind);
+int plan_moments(int kind, int size, int n_comp, int64_t n, bool coarse, Plan* p) {
+    p->S = choose_S(kind, coarse, n_comp == 1);
     // Lane-pair columns halve the shared memory per thread at the price of a shuffle in every moment's reduction tail:
     // worth it only where private columns would cap the CTAs per SM below what the registers allow (2 for the
     // fine+coarse kernels), i.e. above ~56 moments.  MLMCB200_PAIR=0|1 overrides (experiments).
@@ -570,7 +573,9 @@ int launch_moments_pair(const MomentsArgs& a, const Plan& p, cudaStream_t st) {
 
 template <int KIND, bool COARSE, bool LOG>
 int launch_moments_s(const MomentsArgs& a, const Plan& p, cudaStream_t st) {
-    return launch_moments_pair<KIND, COARSE, LOG, KIND == MLMCB200_FOURIER ? 4 : 8>(a, p, st);
+    if (KIND == MLMCB200_FOURIER) return launch_moments_pair<KIND, COARSE, LOG, 4>(a, p, st);
+    if (!COARSE && KIND != MLMCB200_RAW && p.S == 16) return launch_moments_pair<KIND, false, LOG, 16>(a, p, st);
+    return launch_moments_pair<KIND, COARSE, LOG, 8>(a, p, st);
 }
 
 template <int KIND>
@@ -590,7 +595,7 @@ using namespace mlmcb200;
 extern "C" int64_t mlmcb200_moments_workspace_bytes(int32_t size, int32_t n_comp) {
     Plan p;
     if (size < 1 || n_comp < 1) return -1;
-    if (plan_moments(MLMCB200_LEGENDRE, size, n_comp, -1, &p) != 0) return -1;
+    if (plan_moments(MLMCB200_LEGENDRE, size, n_comp, -1, true, &p) != 0) return -1;
     return (int64_t)p.grid.y * (2 + 2 * (int64_t)size * n_comp) * (int64_t)sizeof(double);
 }
 
@@ -606,7 +611,7 @@ extern "C" int mlmcb200_moments_accumulate(const mlmcb200_basis_t* basis, const 
     MB_REQUIRE(pairs != nullptr, "moments_accumulate: null pairs");
     cudaStream_t st = (cudaStream_t)stream;
     Plan p;
-    if (plan_moments(basis->kind, basis->size, n_comp, n, &p) != 0) return -1;
+    if (plan_moments(basis->kind, basis->size, n_comp, n, has_coarse != 0, &p) != 0) return -1;
     const int64_t K = (int64_t)basis->size * n_comp;
     const int64_t stride = 2 + 2 * K;
     MB_REQUIRE(workspace_bytes >= (int64_t)p.grid.y * stride * 8, "moments_accumulate: workspace too small");
