@@ -173,9 +173,11 @@ def make_levels_on_device(torch, device, n_rows, seed_base):
         x = torch.randn(n_rows, generator=gen, device=device, dtype=torch.float64)
         root = torch.sqrt(1e-4 + x.abs())
         fine = x + steps[l] * root
-        coarse = x + steps[l - 1] * root if l > 0 else torch.zeros_like(x)
-        levels.append(torch.stack([fine, coarse], dim=1).unsqueeze(2).contiguous())
-        del x, root, fine, coarse
+        if l > 0:
+            levels.append(torch.stack([fine, x + steps[l - 1] * root], dim=1).unsqueeze(2).contiguous())
+        else:                       # level 0 has no coarse simulation: rows [n, 1, 1] (the zero row is not stored)
+            levels.append(fine.reshape(-1, 1, 1).contiguous())
+        del x, root, fine
     return levels
 
 
@@ -205,14 +207,13 @@ def run_gpu_arm(args):
     basis = moments_fn.basis_struct()
     levels = make_levels_on_device(torch, device, n_rows, 1234 + rank)
     units_per_rank = N_LEVELS * n_rows * N_MOMENTS
-    bytes_per_rank = sum(n_rows * (16 if l else 16) for l in range(N_LEVELS))     # rows are stored as (fine, coarse)
+    bytes_per_rank = sum(lv.numel() * 8 for lv in levels)          # 8 B per level-0 sample, 16 B per (fine, coarse) pair
 
     # ---------------- device-resident step: one CUDA graph = zero, 3 x (moments + reduce), finalize ----------
     acc = nat.LevelAccumulator(N_LEVELS, N_MOMENTS, device)
     views = []
     for l, rows in enumerate(levels):
-        x = rows.permute(2, 0, 1)
-        views.append(x[:, :, :1] if l == 0 else x)
+        views.append(rows.permute(2, 0, 1))
     result = {}
 
     def enqueue_step():
@@ -344,10 +345,18 @@ def run_gpu_arm(args):
     alg_bytes = n_rows * 16.0
     alg_flop = n_rows * N_MOMENTS * 14.0
     achieved_tflops = alg_flop / (kernel_ms * 1e-3) / 1e12
+    traffic = None
+    try:                                   # dram__bytes_read + dram__bytes_write of this kernel, one ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")) as f:
+            cap = json.load(f)["moments_acc_kernel_coarse_R50"]
+        if cap["samples"] == n_rows:
+            traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"kernel": "moments_acc_kernel<LEGENDRE, coarse> (level with fine+coarse, R=50)",
                 "bound": "fp64", "achieved": achieved_tflops, "peak": dfma_peak, "unit": "TFLOP/s",
                 "frac": achieved_tflops / dfma_peak, "peak_source": "DFMA micro-benchmark measured in this run",
-                "traffic": None, "kernel_ms": kernel_ms,
+                "traffic": traffic, "algorithmic_bytes": alg_bytes, "kernel_ms": kernel_ms,
                 "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
                 "note": "R=50 in fp64 is FP64-pipe bound (0.75*R flop/B >> ridge 5.6 flop/B); both terms reported"}

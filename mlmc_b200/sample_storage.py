@@ -77,7 +77,8 @@ class SampleStorage(metaclass=ABCMeta):
     # ------------------------------------------------------------------ read side
     @abstractmethod
     def level_rows(self, level_id):
-        """Host rows ``float64[N, 2, M]`` of one level (NumPy array or memmap)."""
+        """Host rows ``float64[N, 2, M]`` of one level (NumPy array or memmap); level 0 may come as ``[N, 1, M]``
+        (fine row only)."""
 
     @abstractmethod
     def get_level_ids(self):
@@ -294,6 +295,10 @@ class Memory(SampleStorage):
             new = torch.from_numpy(np.ascontiguousarray(np.asarray(rows, dtype=np.float64)))
         if new.dim() == 2:
             new = new.unsqueeze(2)
+        if int(level_id) == 0 and new.shape[1] == 2:
+            # level 0 has no coarse simulation: the reference stores an auxiliary zero row and drops it on every read
+            # (sample_storage.py:282-284); here it is dropped once, so it is neither kept nor copied to the GPU
+            new = new[:, :1, :]
         n_old = self._n.get(level_id, 0)
         buf = self._rows.get(level_id)
         if buf is None or n_old + len(new) > buf.shape[0]:

@@ -53,6 +53,7 @@ def test_memory_storage_contract(golden):
     st2.save_samples({1: [("L01_S0000002", (4 * np.ones(3), 5 * np.ones(3)))]}, {})
     assert st2.get_n_collected() == [2, 2]
     assert np.array_equal(st2.level_rows(1)[:, 1, 0], [3.0, 5.0])
+    assert st2.level_rows(0).shape == (2, 1, 3)           # level 0: the auxiliary zero coarse row is not kept
     assert st2.n_finished().tolist() == [2.0, 3.0]
     st2.save_n_ops([(0, (10.0, 2)), (1, (30.0, 2))])
     assert st2.get_n_ops() == [5.0, 15.0]
