@@ -306,3 +306,25 @@ def test_construct_density_end_to_end():
     oc = orc.estimate_covariance(levels, orc.Basis("legendre", 12, domain))
     l_mat, _, _ = orc.orthogonalize_moments(oc.mean.reshape(12, 12), 1e-4)
     rel_close(info[2], l_mat, rtol=1e-6, atol_scale=1e-9)
+
+
+def test_bootstrap_and_subsample(golden):
+    """est_bootstrap (estimator.py:171-205): statistics of sub-sampled estimates have the reference's shapes and the
+    bootstrap mean of the moment means is close to the full-sample estimate (statistical check, like the reference's
+    atol=1e-2 tests in test_quantity_concept.py)."""
+    from mlmc_b200.moments import Legendre
+    from mlmc_b200.estimator import Estimate
+    from mlmc_b200.quantity import quantity_estimate as qe
+    g = golden("estimates")
+    levels = [g["A_rows%d" % l] for l in range(3)]
+    storage, value = scalar_setup(levels, [[h] for h in g["A_steps"]], g["A_n_ops"])
+    fn = Legendre(6, tuple(g["A_domain"]))
+    est = Estimate(value, storage, fn)
+    est.est_bootstrap(n_subsamples=12, sample_vector=[2000, 1000, 500])
+    assert est.mean_bs_mean.shape == (6,) and est.mean_bs_l_vars.shape == (3, 6) and est.var_bs_l_means.shape == (3, 6)
+    full, _ = est.estimate_moments()
+    assert np.allclose(est.mean_bs_mean, full, atol=2e-2)
+    assert est.mean_bs_mean[0] == 1.0
+    sub = value.subsample(sample_vec=[100, 50, 25])
+    qm = qe.estimate_mean(qe.moments(sub, fn))
+    assert list(qm.n_samples + qm.n_rm_samples) == [100, 50, 25]
