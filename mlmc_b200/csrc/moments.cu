@@ -101,10 +101,13 @@ __device__ __forceinline__ void load_tile(const MomentsArgs& a, const double* ba
 
 // FAST: scalar quantity in storage order (pairs contiguous, no external mask): 32-bit tile arithmetic, immediate
 // load offsets, no per-sample bounds tests on full tiles.
-template <int KIND, bool COARSE, bool LOG, int S, bool PAIR, bool FAST>
+// STAGES > 0 (FAST only): the tiles of this CTA stream through a ring of STAGES shared-memory buffers filled by TMA bulk
+// copies (cp.async.bulk + mbarrier, one elected thread), STAGES - 1 tiles ahead of the compute -- the variant for few
+// moments, where the kernel is HBM-bound and the two register-prefetched tiles per warp do not cover the DRAM latency.
+template <int KIND, bool COARSE, bool LOG, int S, bool PAIR, bool FAST, int STAGES>
 __global__ void __launch_bounds__(kThreads)
 moments_acc_kernel(const MomentsArgs a) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(128) double sm[];
     constexpr int T = kThreads;
     const int tid = threadIdx.x;
     const int R = a.basis.size;
@@ -170,20 +173,68 @@ moments_acc_kernel(const MomentsArgs a) {
             }
         }
     };
-    if (FAST) load_fast(blockIdx.y);
-    else load_tile<COARSE, S>(a, base_f, (int64_t)blockIdx.y * tile_n + tn, TN, active, xf, xc);
+    // ---- TMA ring (STAGES > 0): stage buffers behind the accumulator columns, one mbarrier per stage ----
+    constexpr uint32_t kStageCap = (uint32_t)S * T * 16;                           // bytes reserved per stage
+    char* const ring = reinterpret_cast<char*>(sm + (size_t)n_cols * T);
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(ring + (size_t)(STAGES > 0 ? STAGES : 1) * kStageCap);
+    const uint32_t tile_bytes = (uint32_t)tile_n * 8u * (uint32_t)a.stride_n;      // 8 or 16 bytes per sample
+    const int64_t my_tiles = n_tiles > (int64_t)blockIdx.y ? (n_tiles - blockIdx.y + gridDim.y - 1) / gridDim.y : 0;
+    auto issue_stage = [&](int64_t k) {                                           // elected thread only
+        const int64_t tile = (int64_t)blockIdx.y + k * gridDim.y;
+        if ((tile + 1) * tile_n > a.n) return;                                    // ragged last tile: plain loads
+        const int st = (int)(k % (STAGES > 0 ? STAGES : 1));
+        mbar_expect_tx(&bars[st], tile_bytes);
+        bulk_copy_g2s(ring + (size_t)st * kStageCap, reinterpret_cast<const char*>(a.pairs) + tile * (int64_t)tile_bytes,
+                      tile_bytes, &bars[st]);
+    };
+    if (FAST && STAGES > 0) {
+        if (tid == 0) {
+            for (int st = 0; st < STAGES; ++st) mbar_init(&bars[st], 1);
+            mbar_init_fence();
+        }
+        __syncthreads();
+        if (tid == 0)
+            for (int64_t k = 0; k < STAGES && k < my_tiles; ++k) issue_stage(k);
+    } else if (FAST) {
+        load_fast(blockIdx.y);
+    } else {
+        load_tile<COARSE, S>(a, base_f, (int64_t)blockIdx.y * tile_n + tn, TN, active, xf, xc);
+    }
 
-    for (int64_t tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
+    int64_t k_tile = 0;
+    for (int64_t tile = blockIdx.y; tile < n_tiles; tile += gridDim.y, ++k_tile) {
         double tf[S], tc[S];
         bool ok[S];
         if (FAST) {
             // an out-of-range slot holds NaN: it fails every validity test below, it only must not be counted
             const int64_t first = tile * tile_n + tid;
             const bool full = (tile + 1) * tile_n <= a.n;
+            if (STAGES > 0) {
+                if (full) {
+                    const int st = (int)(k_tile % STAGES);
+                    mbar_wait(&bars[st], (uint32_t)((k_tile / STAGES) & 1));
+                    const char* stage = ring + (size_t)st * kStageCap;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        if (COARSE || a.stride_n == 2) {
+                            const double2 v = reinterpret_cast<const double2*>(stage)[s * T + tid];
+                            xf[s] = v.x;
+                            xc[s] = v.y;
+                        } else {
+                            xf[s] = reinterpret_cast<const double*>(stage)[s * T + tid];
+                            xc[s] = 0.0;
+                        }
+                    }
+                } else {
+                    load_fast(tile);
+                }
+                __syncthreads();                                   // every thread has read the stage: refill it
+                if (tid == 0 && k_tile + STAGES < my_tiles) issue_stage(k_tile + STAGES);
+            }
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-                tf[s] = map_to_ref_t<LOG>(a.basis, xf[s]);
-                tc[s] = COARSE ? map_to_ref_t<LOG>(a.basis, xc[s]) : 0.0;
+                tf[s] = KIND == MLMCB200_RAW ? xf[s] : map_to_ref_t<LOG>(a.basis, xf[s]);
+                tc[s] = !COARSE ? 0.0 : (KIND == MLMCB200_RAW ? xc[s] : map_to_ref_t<LOG>(a.basis, xc[s]));
                 bool good;
                 if (a.basis.is_clip) {            // map_to_ref_t returns NaN outside [ref_lo, ref_hi]
                     good = (tf[s] == tf[s]) && (!COARSE || tc[s] == tc[s]);
@@ -199,7 +250,7 @@ moments_acc_kernel(const MomentsArgs a) {
                 tc[s] = good ? tc[s] : 0.0;
                 ok[s] = good;
             }
-            if (tile + gridDim.y < n_tiles) load_fast(tile + gridDim.y);
+            if (STAGES == 0 && tile + gridDim.y < n_tiles) load_fast(tile + gridDim.y);
         } else {
             const int64_t n0 = tile * tile_n + tn;
 #pragma unroll
@@ -499,17 +550,21 @@ struct Plan {
     int S;        // samples per thread and tile
     bool pair;    // lane pairs share accumulator columns (scalar quantity)
     bool fast;    // scalar quantity in storage order: specialised addressing
+    bool stream;  // few moments (HBM-bound): tiles staged through a TMA-fed shared-memory ring
 };
+
+constexpr int kStages = 4;
+constexpr int kStreamMaxMoments = 12;
 
 // Samples per thread and tile: 8 fine+coarse pairs = 16 independent recurrence chains per thread (Fourier carries twice
 // the state per sample and uses 4); a scalar level without coarse part takes 16 samples to keep the same 16 chains.
-int choose_S(int kind, bool coarse, bool scalar) {
+int choose_S(int kind, bool coarse, bool scalar, bool stream) {
     if (kind == MLMCB200_FOURIER) return 4;
-    return (!coarse && scalar && kind != MLMCB200_RAW) ? 16 : 8;
+    return (!coarse && scalar && kind != MLMCB200_RAW && !stream) ? 16 : 8;
 }
 
-int plan_moments(int kind, int size, int n_comp, int64_t n, bool coarse, Plan* p) {
-    p->S = choose_S(kind, coarse, n_comp == 1);
+int plan_moments(int kind, int size, int n_comp, int64_t n, bool coarse, bool stream, Plan* p) {
+    p->S = choose_S(kind, coarse, n_comp == 1, stream);
     // Lane-pair columns halve the shared memory per thread at the price of a shuffle in every moment's reduction tail:
     // worth it only where private columns would cap the CTAs per SM below what the registers allow (2 for the
     // fine+coarse kernels), i.e. above ~56 moments.  MLMCB200_PAIR=0|1 overrides (experiments).
@@ -521,6 +576,7 @@ int plan_moments(int kind, int size, int n_comp, int64_t n, bool coarse, Plan* p
     p->pair = n_comp == 1 && (size_t)2 * size * kThreads * sizeof(double) > 113u * 1024u;
     if (forced >= 0 && n_comp == 1) p->pair = forced != 0;
     p->fast = false;
+    p->stream = stream;
     const size_t smem = (size_t)(p->pair ? 1 : 2) * size * kThreads * sizeof(double);
     if (smem + 64 > 227u * 1024u) {        // 64 B: static shared memory of the kernel (sample counters)
         set_error("moments: size %d needs %zu B of shared memory per CTA (max %u)", size, smem, 227u * 1024u);
@@ -541,9 +597,10 @@ int plan_moments(int kind, int size, int n_comp, int64_t n, bool coarse, Plan* p
     return 0;
 }
 
-template <int KIND, bool COARSE, bool LOG, int S, bool PAIR, bool FAST>
+template <int KIND, bool COARSE, bool LOG, int S, bool PAIR, bool FAST, int STAGES = 0>
 int launch_moments(const MomentsArgs& a, Plan p, cudaStream_t st) {
-    auto kern = moments_acc_kernel<KIND, COARSE, LOG, S, PAIR, FAST>;
+    auto kern = moments_acc_kernel<KIND, COARSE, LOG, S, PAIR, FAST, STAGES>;
+    if (STAGES > 0) p.smem += (size_t)STAGES * ((size_t)S * kThreads * 16 + 8);
     // resident CTAs per SM for this variant and shared-memory size (registers may bind before shared memory);
     // the sample-partition dimension of the grid is sized to exactly one resident wave
     static thread_local size_t cached_smem = 0;
@@ -564,6 +621,7 @@ int launch_moments(const MomentsArgs& a, Plan p, cudaStream_t st) {
 
 template <int KIND, bool COARSE, bool LOG, int S>
 int launch_moments_pair(const MomentsArgs& a, const Plan& p, cudaStream_t st) {
+    if (p.fast && p.stream && !p.pair) return launch_moments<KIND, COARSE, LOG, S, false, true, kStages>(a, p, st);
     if (KIND != MLMCB200_RAW && p.fast)
         return p.pair ? launch_moments<KIND, COARSE, LOG, S, true, true>(a, p, st)
                       : launch_moments<KIND, COARSE, LOG, S, false, true>(a, p, st);
@@ -595,7 +653,7 @@ using namespace mlmcb200;
 extern "C" int64_t mlmcb200_moments_workspace_bytes(int32_t size, int32_t n_comp) {
     Plan p;
     if (size < 1 || n_comp < 1) return -1;
-    if (plan_moments(MLMCB200_LEGENDRE, size, n_comp, -1, true, &p) != 0) return -1;
+    if (plan_moments(MLMCB200_LEGENDRE, size, n_comp, -1, true, false, &p) != 0) return -1;
     return (int64_t)p.grid.y * (2 + 2 * (int64_t)size * n_comp) * (int64_t)sizeof(double);
 }
 
@@ -611,7 +669,14 @@ extern "C" int mlmcb200_moments_accumulate(const mlmcb200_basis_t* basis, const 
     MB_REQUIRE(pairs != nullptr, "moments_accumulate: null pairs");
     cudaStream_t st = (cudaStream_t)stream;
     Plan p;
-    if (plan_moments(basis->kind, basis->size, n_comp, n, has_coarse != 0, &p) != 0) return -1;
+    // few moments + contiguous 16-byte aligned scalar rows + enough samples: HBM-bound -> TMA-ring variant
+    const bool fast = n_comp == 1 && valid == nullptr &&
+                      (has_coarse ? (stride_n == 2 && stride_side == 1 && (reinterpret_cast<uintptr_t>(pairs) & 15) == 0)
+                                  : stride_n >= 1);
+    const bool use_ring = fast && basis->size <= kStreamMaxMoments && basis->kind != MLMCB200_FOURIER &&
+                        (stride_n == 2 || (!has_coarse && stride_n == 1)) &&
+                        (reinterpret_cast<uintptr_t>(pairs) & 15) == 0 && n >= (int64_t)8 * kThreads * 8;
+    if (plan_moments(basis->kind, basis->size, n_comp, n, has_coarse != 0, use_ring, &p) != 0) return -1;
     const int64_t K = (int64_t)basis->size * n_comp;
     const int64_t stride = 2 + 2 * K;
     MB_REQUIRE(workspace_bytes >= (int64_t)p.grid.y * stride * 8, "moments_accumulate: workspace too small");
@@ -629,7 +694,7 @@ extern "C" int mlmcb200_moments_accumulate(const mlmcb200_basis_t* basis, const 
               (reinterpret_cast<uintptr_t>(pairs) & 15) == 0) ? 1 : 0;
     a.partial = static_cast<double*>(workspace);
     a.partial_stride = stride;
-    p.fast = n_comp == 1 && valid == nullptr && (has_coarse ? a.vec2 != 0 : stride_n >= 1);
+    p.fast = fast;
 
     int rc = -1;     // > 0: number of partial vectors written
     const bool coarse = has_coarse != 0, is_log = basis->is_log != 0;

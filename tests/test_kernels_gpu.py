@@ -397,3 +397,32 @@ def test_strided_scalar_column_of_wide_storage():
         n = a[0]
         assert n == want.n_samples[1]
         rel_close(a[2:9] / n, want.l_means[1], rtol=1e-10, atol_scale=1e-14)
+
+
+@pytest.mark.parametrize("kind,R", [("legendre", 5), ("monomial", 6), ("legendre", 12), ("raw", 1)])
+def test_streaming_variant_few_moments(kind, R):
+    """Few moments + many samples take the TMA-ring (HBM-bound) variant: same results as the oracle, ragged tail
+    tile included, level 0 in both layouts ([n, 1, 1] compact and [n, 2, 1] with the zero row)."""
+    rng = np.random.default_rng(R)
+    n1, n0 = 70_000 + 123, 50_000 + 7
+    lvl1 = orc.synth_level_rows(rng.normal(size=n1), 0.05, 0.3)
+    lvl0 = orc.synth_level_rows(rng.normal(size=n0), 0.3, None)
+    lvl1[11, 0, 0] = np.nan
+    lvl1[-1, 1, 0] = 99.0
+    nat = native()
+    if kind == "raw":
+        basis, want = nat.RAW_BASIS, orc.estimate_mean([lvl0, lvl1], None)
+    else:
+        b = orc.Basis(kind, R, (-3.0, 3.1))
+        basis, want = to_struct(b), orc.estimate_moments([lvl0, lvl1], b)
+    for compact in (True, False):
+        acc = nat.LevelAccumulator(2, R, dev())
+        d0 = torch.from_numpy(np.ascontiguousarray(lvl0[:, :1, :] if compact else lvl0)).to(dev())
+        x0 = d0.permute(2, 0, 1)[:, :, :1]
+        nat.moments_accumulate(basis, x0, acc.level(0))
+        nat.moments_accumulate(basis, torch.from_numpy(lvl1).to(dev()).permute(2, 0, 1), acc.level(1))
+        out = acc.finalize()
+        a = acc.acc.cpu().numpy()
+        assert np.array_equal(a[:, 0], want.n_samples) and np.array_equal(a[:, 1], want.n_rm_samples)
+        rel_close(out["l_means"].cpu().numpy(), want.l_means, rtol=1e-10, atol_scale=1e-14)
+        rel_close(out["l_vars"].cpu().numpy(), want.l_vars, rtol=1e-10, atol_scale=1e-14)
