@@ -408,12 +408,12 @@ class QuantityConst(Quantity):
 class QuantityMean:
     """Result of ``estimate_mean`` (quantity.py:568-651): per-level means / variances and their MLMC totals."""
 
-    def __init__(self, quantity_type, l_means, l_vars, n_samples, n_rm_samples):
+    def __init__(self, quantity_type, l_means, l_vars, n_samples, n_rm_samples, mean=None, var=None):
         self.qtype = quantity_type
-        self._mean = None
-        self._var = None
-        self._l_means = np.array(l_means)
-        self._l_vars = np.array(l_vars)
+        self._mean = mean           # optional: totals already formed on the device (same level order / arithmetic)
+        self._var = var
+        self._l_means = np.asarray(l_means)
+        self._l_vars = np.asarray(l_vars)
         self._n_samples = np.array(n_samples)
         self._n_rm_samples = np.array(n_rm_samples)
 
@@ -423,13 +423,13 @@ class QuantityMean:
 
     @property
     def mean(self):
-        if self._mean is None:
+        if self._mean is None or self._var is None:
             self._calculate_mean_var()
         return self._reshape(self._mean)
 
     @property
     def var(self):
-        if self._var is None:
+        if self._mean is None or self._var is None:
             self._calculate_mean_var()
         return self._reshape(self._var)
 

@@ -191,6 +191,7 @@ def estimate_mean(quantity):
     L, K = acc.n_levels, acc.K
     l_means = packed[:L * K].reshape(L, K)
     l_vars = packed[L * K:2 * L * K].reshape(L, K)
+    mean, var = packed[2 * L * K:(2 * L + 1) * K], packed[(2 * L + 1) * K:(2 * L + 2) * K]
     counts = packed[(2 * L + 2) * K:].reshape(L, 2)
     n_samples = [int(c) for c in counts[:, 0]]
     n_rm_samples = [int(c) for c in counts[:, 1]]
@@ -200,21 +201,28 @@ def estimate_mean(quantity):
         r = plan.fn.size
         l_means = l_means.reshape(L, -1, r).transpose(0, 2, 1).reshape(L, K)
         l_vars = l_vars.reshape(L, -1, r).transpose(0, 2, 1).reshape(L, K)
+        mean = mean.reshape(-1, r).T.reshape(K)
+        var = var.reshape(-1, r).T.reshape(K)
     elif plan.kind == "covariance" and not plan.at_bottom:
         pass        # scalar input quantity: both layouts coincide
     return q_mod.QuantityMean(quantity.qtype, l_means=l_means, l_vars=l_vars, n_samples=n_samples,
-                              n_rm_samples=n_rm_samples)
+                              n_rm_samples=n_rm_samples, mean=mean, var=var)
 
 
 _host_buffers = {}
 
 
 def _to_host(tensor):
-    """Device -> host through a cached pinned buffer (a pageable ``.cpu()`` runs at a fraction of the link rate)."""
+    """Device -> host.  Small results go through a cached pinned buffer (one extra small copy); large ones (vector
+    quantities) are copied once, straight into a fresh array."""
     n = tensor.numel()
+    if n * 8 > (1 << 20):
+        out = torch.empty(n, dtype=torch.float64)
+        out.copy_(tensor)
+        return out.numpy()
     buf = _host_buffers.get("f64")
     if buf is None or buf.numel() < n:
-        buf = torch.empty(max(n, 1 << 16), dtype=torch.float64).pin_memory()
+        buf = torch.empty(1 << 17, dtype=torch.float64).pin_memory()
         _host_buffers["f64"] = buf
     view = buf[:n]
     view.copy_(tensor, non_blocking=True)

@@ -31,8 +31,9 @@ class QType:
         return self._qtype.base_qtype()
 
     def replace_scalar(self, substitute_qtype):
-        """Copy of this type with the innermost ScalarType replaced (quantity_types.py:21-32)."""
-        new_qtype = copy.deepcopy(self)
+        """Copy of this type with the innermost ScalarType replaced (quantity_types.py:21-32).  The copy is shallow:
+        only the chain of ``_qtype`` links is rebuilt, the (never mutated) shape / time / key lists are shared."""
+        new_qtype = copy.copy(self)
         new_qtype._qtype = self._qtype.replace_scalar(substitute_qtype)
         return new_qtype
 
@@ -137,6 +138,15 @@ class FieldType(QType):
 
     def size(self) -> int:
         return len(self._dict) * self._qtype.size()
+
+    def replace_scalar(self, substitute_qtype):
+        """All locations share one inner type: replace it once and share the result (a deep copy of a field with
+        1e4 locations would cost more than the estimate itself)."""
+        inner = self._qtype.replace_scalar(substitute_qtype)
+        new = FieldType.__new__(FieldType)
+        new._dict = {key: inner for key in self._dict}
+        new._qtype = inner
+        return new
 
     def get_key(self, key):
         position = list(self._dict.keys()).index(key)
