@@ -213,13 +213,24 @@ _host_buffers = {}
 
 
 def _to_host(tensor):
-    """Device -> host.  Small results go through a cached pinned buffer (one extra small copy); large ones (vector
-    quantities) are copied once, straight into a fresh array."""
+    """Device -> host into pinned memory.  Small results are copied out of one cached staging buffer.  Large ones
+    (vector quantities: tens of MB) are returned as views of pooled pinned buffers, so that no call pays for fresh
+    pages; a pooled buffer is handed out again only when nothing references the arrays of the call that used it."""
+    import sys
     n = tensor.numel()
     if n * 8 > (1 << 20):
-        out = torch.empty(n, dtype=torch.float64)
-        out.copy_(tensor)
-        return out.numpy()
+        pool = _host_buffers.setdefault(("pool", n), [])
+        for host, arr in pool:
+            if sys.getrefcount(arr) <= 3:            # the pool tuple, the loop variable and getrefcount's argument
+                break
+        else:
+            host = torch.empty(n, dtype=torch.float64).pin_memory()
+            arr = host.numpy()
+            if len(pool) < 4:
+                pool.append((host, arr))
+        host.copy_(tensor, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return arr
     buf = _host_buffers.get("f64")
     if buf is None or buf.numel() < n:
         buf = torch.empty(1 << 17, dtype=torch.float64).pin_memory()

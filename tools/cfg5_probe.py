@@ -31,3 +31,13 @@ pr = cProfile.Profile(); pr.enable()
 qm = qe.estimate_mean(qe.moments(field, fn)); torch.cuda.synchronize()
 pr.disable()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
+ts = []
+for _ in range(8):
+    t0 = time.perf_counter(); qm = qe.estimate_mean(qe.moments(field, fn)); torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
+print("8 consecutive calls (ms):", [round(t, 2) for t in ts])
+import gc
+gc.disable()
+ts = []
+for _ in range(8):
+    t0 = time.perf_counter(); qm = qe.estimate_mean(qe.moments(field, fn)); torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
+print("gc disabled           :", [round(t, 2) for t in ts])
