@@ -465,36 +465,44 @@ __global__ void __launch_bounds__(kThreadsGram, 1) maxent_kernel(const MaxentArg
         for (int u = 0; u < GS; ++u)
 #pragma unroll
             for (int v = 0; v < GS; ++v) acc[s][u][v][0] = acc[s][u][v][1] = 0.0;
-    double g_acc = 0.0, f_acc = 0.0;                            // thread tid < R owns g_tid; thread 0 owns F
+    // F and g: the warp that forms the exponent of a node also adds the node into its partial sums
+    // (lane l owns moments l, l + 32, ...); the per-warp partials meet in shared memory at the end
+    constexpr int GJ = MLMCB200_MAX_MOMENTS / 32;
+    double g_loc[GJ], f_loc = 0.0;
+#pragma unroll
+    for (int j = 0; j < GJ; ++j) g_loc[j] = 0.0;
     const int frag_off = (lane & 3) * LD + (lane >> 2);
     const int64_t n_tiles = (a.n_nodes + NS - 1) / NS;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t q0 = tile * NS;
         __syncthreads();
-        // stage NS rows (zero-padded columns / rows)
-        for (int idx = tid; idx < NS * r_pad; idx += kThreadsGram) {
-            const int s = idx / r_pad, i = idx - s * r_pad;
-            const int64_t q = q0 + s;
-            phi_s[(size_t)s * LD + i] = (q < a.n_nodes && i < R) ? __ldg(a.phi + q * a.ld_g + i) : 0.0;
-        }
-        __syncthreads();
+        // one warp per node: stage the row (coalesced, zero padded), exponent, weight, F / g partials
         for (int s = warp; s < NS; s += kWarps) {
+            const int64_t q = q0 + s;
+            const bool in = q < a.n_nodes;
+            double* row = phi_s + (size_t)s * LD;
             double dot = 0.0;
-            for (int i = lane; i < R; i += 32) dot = fma(phi_s[(size_t)s * LD + i], lam_s[i], dot);
-            dot = warp_sum(dot);
-            if (lane == 0) {
-                const double power = fmin(fmax(-dot, -200.0), 200.0);
-                wr[s] = (q0 + s < a.n_nodes) ? a.w[q0 + s] * exp(power) : 0.0;
+            double mine[GJ];
+#pragma unroll
+            for (int j = 0; j < GJ; ++j) {
+                const int i = lane + 32 * j;
+                mine[j] = 0.0;
+                if (i < r_pad) {
+                    mine[j] = (in && i < R) ? __ldg(a.phi + q * a.ld_g + i) : 0.0;
+                    row[i] = mine[j];
+                    dot = fma(mine[j], lam_s[i], dot);
+                }
             }
+            dot = warp_sum(dot);
+            const double power = fmin(fmax(-dot, -200.0), 200.0);
+            const double wq = in ? __ldg(a.w + q) * exp(power) : 0.0;
+            if (lane == 0) wr[s] = wq;
+            f_loc += wq;
+#pragma unroll
+            for (int j = 0; j < GJ; ++j) g_loc[j] = fma(wq, mine[j], g_loc[j]);
         }
         __syncthreads();
-        if (tid < R) {
-            for (int s = 0; s < NS; ++s) g_acc = fma(wr[s], phi_s[(size_t)s * LD + tid], g_acc);
-        }
-        if (tid == kThreadsGram - 1) {
-            for (int s = 0; s < NS; ++s) f_acc += wr[s];
-        }
         if (a.want_h) {
             for (int k0 = 0; k0 < NS; k0 += 4) {
                 const double* pf = phi_s + (size_t)k0 * LD + frag_off;
@@ -524,8 +532,20 @@ __global__ void __launch_bounds__(kThreadsGram, 1) maxent_kernel(const MaxentArg
     }
 
     double* const out = a.partial + (int64_t)blockIdx.x * a.partial_stride;
-    if (tid == kThreadsGram - 1) out[0] = f_acc;
-    if (tid < R) out[1 + tid] = g_acc;
+    // per-warp F / g partials -> shared memory (the tile buffer is free now) -> one value per moment
+    __syncthreads();
+    double* const red = sm;                                     // [kWarps][1 + 32 * GJ]
+    constexpr int kRedLd = 1 + 32 * GJ;
+#pragma unroll
+    for (int j = 0; j < GJ; ++j) red[warp * kRedLd + 1 + lane + 32 * j] = g_loc[j];
+    if (lane == 0) red[warp * kRedLd] = f_loc;
+    __syncthreads();
+    for (int i = tid; i < 1 + R; i += kThreadsGram) {
+        double v = 0.0;
+        for (int w = 0; w < kWarps; ++w) v += red[w * kRedLd + i];
+        out[i] = v;
+    }
+    __syncthreads();
     if (a.want_h) {
         double* const out_h = out + 1 + R;
 #pragma unroll
@@ -644,6 +664,8 @@ extern "C" int mlmcb200_maxent_fgh(const double* phi, int64_t ld, const double* 
     // single table + weights + multipliers instead of two tables + flags
     const int ns = a.plan.ns;
     smem = ((size_t)ns * a.plan.ld + ns + 8 * a.plan.nb) * sizeof(double);
+    const size_t red_bytes = (size_t)kWarps * (1 + MLMCB200_MAX_MOMENTS) * sizeof(double);   // F / g partials per warp
+    if (smem < red_bytes) smem = red_bytes;
     const int grid = maxent_grid(n_nodes, ns);
     const int64_t stride = 1 + (int64_t)size + (int64_t)size * size;
     MB_REQUIRE(workspace_bytes >= (int64_t)grid * stride * 8, "maxent_fgh: workspace too small");
