@@ -160,7 +160,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_procs, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -193,9 +193,6 @@ def run_gpu_arm(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
-    # NCCL writes its debug stream (incl. the "NCCL version" banner at VERSION/WARN level) to stdout by default, which
-    # would put a non-JSON line before ours: send it to stderr instead
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, world, local = mdist.init_from_env()
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
@@ -385,12 +382,28 @@ def run_gpu_arm(args):
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "n_estimated": [int(v) for v in n_estimated], "n_estimated_e2e": [int(v) for v in n_est_e2e],
             "launch_count_native": nat.launch_count - launches_before}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         td.barrier()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """Print the ONE JSON line on the real stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # Libraries (NCCL prints "NCCL version ..." when a communicator is created) may write to fd 1: keep a private
+    # handle on the real stdout for the JSON line and point fd 1 at stderr for everything else.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
