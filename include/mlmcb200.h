@@ -88,6 +88,33 @@ int mlmcb200_moments_accumulate(const mlmcb200_basis_t* basis, const double* pai
                                 void* stream);
 
 /*
+ * Bootstrap re-sampling of one level on the device.  Replaces the replicate loop of Estimate.est_bootstrap
+ * (mlmc/estimator.py:171-218) over Quantity.subsample / pick_samples (mlmc/quantity/quantity.py:307-364: `size`
+ * rows drawn WITH replacement from the chunk) followed by estimate_mean of the moments: replicate b, b < n_rep,
+ * accumulates the rows  pairs[idx[b * n_draws + i]], i < n_draws  (idx: device, row numbers < n_rows, drawn by
+ * the caller) exactly as mlmcb200_moments_accumulate would accumulate that gathered chunk, into
+ * acc + b * acc_rep_stride (same layout; ADDS).  `valid` is indexed by storage row.  All replicates of the level
+ * run in ONE launch (grid.z = replicate); rows are re-read through L2, never materialised per replicate.
+ */
+/*
+ * Row numbers for mlmcb200_moments_accumulate_resampled, drawn on the device: idx[b * n_draws + j], b < n_rep, is
+ * uniform on [0, n_rows) WITH replacement (RNG.choice of Quantity.pick_samples, mlmc/quantity/quantity.py:318-319).
+ * Counter-based Philox4x32-10 keyed by (seed, stream_id, replicate, draw): the same arguments give the same numbers.
+ * n_blocks > 1 orders each replicate's draws by row block (block p = rows [p n_rows / P, (p+1) n_rows / P)) so that
+ * concurrent CTAs gather from an L2-sized window: block_cum (device, [n_rep][n_blocks + 1], block_cum[b][0] = 0,
+ * block_cum[b][P] = n_draws) are the caller's cumulative MULTINOMIAL block counts -- the draws are then exactly
+ * i.i.d. uniform rows, listed in block order (the level sums do not depend on the order).
+ */
+int mlmcb200_resample_indices(uint64_t seed, uint64_t stream_id, int64_t n_rows, int64_t n_draws, int32_t n_rep,
+                              int32_t n_blocks, const int64_t* block_cum, int32_t* idx, void* stream);
+int64_t mlmcb200_moments_resampled_workspace_bytes(int32_t size, int32_t n_comp, int32_t n_rep);
+int mlmcb200_moments_accumulate_resampled(const mlmcb200_basis_t* basis, const double* pairs, int64_t n_rows,
+                                          int32_t n_comp, int64_t stride_n, int64_t stride_side, int64_t stride_m,
+                                          int32_t has_coarse, const uint8_t* valid, const int32_t* idx,
+                                          int64_t n_draws, int32_t n_rep, double* acc, int64_t acc_rep_stride,
+                                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * Level accumulator of the moment-covariance estimate (scalar quantity).  Replaces estimate_mean over a
  * `covariance` quantity: mlmc/quantity/quantity_estimate.py:131-147 + :43-65.  With R = basis->size:
  *     acc[0] = n_samples, acc[1] = n_rm_samples,
@@ -111,6 +138,13 @@ int mlmcb200_gram_accumulate(const mlmcb200_basis_t* basis, const double* pairs,
  */
 int mlmcb200_finalize_levels(const double* acc, int64_t acc_stride, int32_t n_levels, int64_t K,
                              double* l_means, double* l_vars, double* mean, double* var, void* stream);
+
+/*
+ * The same for n_batch accumulator sets acc_batch_stride doubles apart (the replicates of est_bootstrap,
+ * mlmc/estimator.py:185-193): out[b] = [l_means (L*K) | l_vars (L*K) | mean (K) | var (K)], packed per entry.
+ */
+int mlmcb200_finalize_levels_batched(const double* acc, int64_t acc_stride, int32_t n_levels, int64_t K,
+                                     int32_t n_batch, int64_t acc_batch_stride, double* out, void* stream);
 
 /*
  * Max-entropy functional pieces on a fixed node set (mlmc/tool/simple_distribution.py:254-327):

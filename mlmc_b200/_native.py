@@ -37,11 +37,19 @@ _SIGNATURES = {
     "mlmcb200_moments_workspace_bytes": (_c_i64, [_c_i32, _c_i32]),
     "mlmcb200_moments_accumulate": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_i32, _c_i64,
                                                    _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
+    "mlmcb200_resample_indices": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, _c_i64, _c_i64, _c_i32, _c_i32,
+                                                 _c_vp, _c_vp, _c_vp]),
+    "mlmcb200_moments_resampled_workspace_bytes": (_c_i64, [_c_i32, _c_i32, _c_i32]),
+    "mlmcb200_moments_accumulate_resampled": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_i32,
+                                                             _c_i64, _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_i64,
+                                                             _c_i32, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp]),
     "mlmcb200_gram_workspace_bytes": (_c_i64, [_c_i32]),
     "mlmcb200_gram_accumulate": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_i64, _c_i64,
                                                 _c_i32, _c_i32, _c_i32, _c_vp, _c_vp, _c_i64, _c_vp]),
     "mlmcb200_finalize_levels": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp,
                                                 _c_vp]),
+    "mlmcb200_finalize_levels_batched": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i64, _c_i32, _c_i64, _c_vp,
+                                                        _c_vp]),
     "mlmcb200_maxent_workspace_bytes": (_c_i64, [_c_i64, _c_i32]),
     "mlmcb200_maxent_fgh": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp, _c_vp,
                                            _c_i64, _c_vp]),
@@ -233,6 +241,79 @@ def moments_accumulate(basis, x, acc_row, valid=None):
                                                _ptr(valid), _ptr(acc_row), _ptr(ws), ws.numel(), _stream()),
                "moments_accumulate")
     launch_count += 2
+
+
+def resample_indices(seed, stream_id, n_rows, n_draws, n_rep, device, block_cum=None):
+    """int32 CUDA tensor [n_rep, n_draws] of row numbers drawn uniformly with replacement from ``range(n_rows)``.
+    ``block_cum`` ([n_rep, P + 1] int64 CUDA, cumulative multinomial block counts) lists each replicate's draws in
+    row-block order (L2-friendly gather); reproducible for equal arguments."""
+    global launch_count
+    idx = torch.empty((n_rep, n_draws), dtype=torch.int32, device=device)
+    n_blocks = 1
+    if block_cum is not None:
+        _require_cuda(block_cum, "block_cum", torch.int64)
+        if block_cum.dim() != 2 or block_cum.shape[0] != n_rep or not block_cum.is_contiguous():
+            raise NativeError("block_cum must be a contiguous [n_rep, n_blocks + 1] tensor")
+        n_blocks = block_cum.shape[1] - 1
+    with _on_device(idx.device):
+        _check(load().mlmcb200_resample_indices(int(seed) & (2 ** 64 - 1), int(stream_id) & (2 ** 64 - 1), n_rows,
+                                                n_draws, n_rep, n_blocks, _ptr(block_cum), _ptr(idx), _stream()),
+               "resample_indices")
+    launch_count += 1
+    return idx
+
+
+def moments_accumulate_resampled(basis, x, idx, acc_level, valid=None):
+    """Bootstrap replicates of one level in one launch.
+
+    x [M, n_rows, S]: the level's chunk; idx [B, n_draws] int32 (CUDA): rows drawn for each replicate;
+    acc_level [B, 2 + 2*M*R]: view of the replicate accumulators of this level (row b may be strided by any
+    replicate stride; each row contiguous).  Adds  sum over the drawn rows  exactly as ``moments_accumulate`` would
+    for the gathered chunk ``x[:, idx[b], :]``."""
+    global launch_count
+    M, n_rows, has_coarse, sn, ss, sm = _chunk_layout(x)
+    _require_cuda(acc_level, "acc")
+    _require_cuda(idx, "idx", torch.int32)
+    K = M * basis.size
+    if idx.dim() != 2 or not idx.is_contiguous():
+        raise NativeError("idx must be a contiguous [n_replicates, n_draws] tensor")
+    B, n_draws = idx.shape
+    if acc_level.dim() != 2 or acc_level.shape != (B, 2 + 2 * K) or acc_level.stride(1) != 1:
+        raise NativeError("replicate accumulators must have shape [%d, %d] with contiguous rows" % (B, 2 + 2 * K))
+    if n_draws == 0 or B == 0:
+        return
+    if n_rows == 0:
+        raise NativeError("cannot draw from an empty chunk")
+    lib = load()
+    if M > 1 and valid is None:
+        valid = sample_mask(basis, x)
+    with _on_device(x.device):
+        ws_bytes = lib.mlmcb200_moments_resampled_workspace_bytes(basis.size, M, B)
+        if ws_bytes < 0:
+            raise NativeError("moments workspace: %s" % lib.mlmcb200_last_error().decode())
+        ws = _workspace(x.device, ws_bytes)
+        _check(lib.mlmcb200_moments_accumulate_resampled(ctypes.byref(basis), _ptr(x), n_rows, M, sn, ss, sm,
+                                                         has_coarse, _ptr(valid), _ptr(idx), n_draws, B,
+                                                         _ptr(acc_level), acc_level.stride(0), _ptr(ws), ws.numel(),
+                                                         _stream()),
+               "moments_accumulate_resampled")
+    launch_count += 2
+
+
+def finalize_levels_batched(acc):
+    """acc [B, L, 2 + 2K] (contiguous) -> CUDA tensor [B, 2*L*K + 2*K]: per replicate l_means | l_vars | mean | var."""
+    global launch_count
+    B, L, width = acc.shape
+    K = (width - 2) // 2
+    _require_cuda(acc, "acc")
+    if not acc.is_contiguous():
+        raise NativeError("replicate accumulators must be contiguous")
+    out = torch.empty((B, 2 * L * K + 2 * K), dtype=torch.float64, device=acc.device)
+    with _on_device(acc.device):
+        _check(load().mlmcb200_finalize_levels_batched(_ptr(acc), acc.stride(1), L, K, B, acc.stride(0), _ptr(out),
+                                                       _stream()), "finalize_levels_batched")
+    launch_count += 1
+    return out
 
 
 def gram_accumulate(basis, x, acc_row, mode=0, want_var=True):

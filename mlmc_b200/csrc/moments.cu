@@ -36,8 +36,9 @@ struct MomentsArgs {
     int64_t stride_n, stride_side, stride_m;
     int32_t n_comp;
     int32_t vec2;          // 1: scalar quantity in storage order, (fine, coarse) read as one 16-byte load
-    double* partial;       // [gridDim.y][2 + 2K]
+    double* partial;       // [gridDim.z][gridDim.y][2 + 2K]
     int64_t partial_stride;
+    const int32_t* idx;    // re-sampling (bootstrap): replicate z reads the rows idx[z * n + i], i < n; else NULL
 };
 
 // ---- per-moment reduction of the S samples held by this thread into its shared-memory column(s) ----
@@ -78,15 +79,16 @@ __device__ __forceinline__ void accumulate(double* __restrict__ col, int sq_off,
 
 // raw (fine, coarse) values of the S samples of one tile owned by this thread; out-of-range samples read NaN
 template <bool COARSE, int S>
-__device__ __forceinline__ void load_tile(const MomentsArgs& a, const double* base_f, int64_t n0, int TN, bool active,
-                                          double (&xf)[S], double (&xc)[S]) {
+__device__ __forceinline__ void load_tile(const MomentsArgs& a, const double* base_f, const int32_t* idx, int64_t n0,
+                                          int TN, bool active, double (&xf)[S], double (&xc)[S]) {
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        const int64_t n = n0 + (int64_t)s * TN;
+        int64_t n = n0 + (int64_t)s * TN;
         xf[s] = qnan;
         xc[s] = qnan;
         if (active && n < a.n) {
+            if (idx != nullptr) n = __ldg(idx + n);                 // re-sampled row
             if (COARSE && a.vec2) {
                 const double2 v = __ldcs(reinterpret_cast<const double2*>(a.pairs) + n);
                 xf[s] = v.x;
@@ -104,7 +106,8 @@ __device__ __forceinline__ void load_tile(const MomentsArgs& a, const double* ba
 // STAGES > 0 (FAST only): the tiles of this CTA stream through a ring of STAGES shared-memory buffers filled by TMA bulk
 // copies (cp.async.bulk + mbarrier, one elected thread), STAGES - 1 tiles ahead of the compute -- the variant for few
 // moments, where the kernel is HBM-bound and the two register-prefetched tiles per warp do not cover the DRAM latency.
-template <int KIND, bool COARSE, bool LOG, int S, bool PAIR, bool FAST, int STAGES>
+// GATHER (FAST, STAGES == 0 only): bootstrap re-sampling, sample i of replicate blockIdx.z is the row idx[z * n + i].
+template <int KIND, bool COARSE, bool LOG, int S, bool PAIR, bool FAST, int STAGES, bool GATHER>
 __global__ void __launch_bounds__(kThreads)
 moments_acc_kernel(const MomentsArgs a) {
     extern __shared__ __align__(128) double sm[];
@@ -132,6 +135,7 @@ moments_acc_kernel(const MomentsArgs a) {
     const int64_t tile_n = (int64_t)S * TN;
     const int64_t n_tiles = (a.n + tile_n - 1) / tile_n;
     const double* const base_f = a.pairs + (int64_t)m * a.stride_m;
+    const int32_t* const idx = (GATHER || (!FAST && a.idx != nullptr)) ? a.idx + (int64_t)blockIdx.z * a.n : nullptr;
     const bool count_here = (blockIdx.x == 0) && (M >= T ? tid == 0 : m == 0);
     unsigned cnt_ok = 0, cnt_rm = 0;
 
@@ -154,7 +158,26 @@ moments_acc_kernel(const MomentsArgs a) {
     auto load_fast = [&](int64_t tile) {
         const int64_t first = tile * tile_n + tid;
         const bool full = (tile + 1) * tile_n <= a.n;
-        if (COARSE) {
+        if (GATHER) {
+            // two dependent rounds of S independent loads: the row numbers (coalesced), then the rows themselves
+            // (rows are shared by all replicates: default caching, no streaming hint)
+            int32_t row[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) row[s] = (full || first + s * T < a.n) ? __ldg(idx + first + s * T) : -1;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                xf[s] = xc[s] = qnan;
+                if (row[s] >= 0) {
+                    if (COARSE) {
+                        const double2 v = __ldg(reinterpret_cast<const double2*>(a.pairs) + row[s]);
+                        xf[s] = v.x;
+                        xc[s] = v.y;
+                    } else {
+                        xf[s] = __ldg(a.pairs + (int64_t)row[s] * a.stride_n);
+                    }
+                }
+            }
+        } else if (COARSE) {
             const double2* p = reinterpret_cast<const double2*>(a.pairs) + first;
 #pragma unroll
             for (int s = 0; s < S; ++s) {
@@ -198,7 +221,7 @@ moments_acc_kernel(const MomentsArgs a) {
     } else if (FAST) {
         load_fast(blockIdx.y);
     } else {
-        load_tile<COARSE, S>(a, base_f, (int64_t)blockIdx.y * tile_n + tn, TN, active, xf, xc);
+        load_tile<COARSE, S>(a, base_f, idx, (int64_t)blockIdx.y * tile_n + tn, TN, active, xf, xc);
     }
 
     int64_t k_tile = 0;
@@ -266,7 +289,7 @@ moments_acc_kernel(const MomentsArgs a) {
                 }
                 bool good;
                 if (a.valid != nullptr) {
-                    good = in && a.valid[n] != 0;
+                    good = in && a.valid[idx != nullptr && in ? (int64_t)__ldg(idx + n) : n] != 0;
                 } else {
                     good = in && moments_finite(a.basis, tf[s]) && (!COARSE || moments_finite(a.basis, tc[s]));
                 }
@@ -281,7 +304,7 @@ moments_acc_kernel(const MomentsArgs a) {
                 ok[s] = good;
             }
             if (tile + gridDim.y < n_tiles)
-                load_tile<COARSE, S>(a, base_f, (tile + gridDim.y) * tile_n + tn, TN, active, xf, xc);
+                load_tile<COARSE, S>(a, base_f, idx, (tile + gridDim.y) * tile_n + tn, TN, active, xf, xc);
         }
 
         double* col = col0;                                      // column entry of the next moment to reduce
@@ -413,7 +436,7 @@ moments_acc_kernel(const MomentsArgs a) {
 
     // ---------------- block epilogue ----------------
     __syncthreads();
-    double* const out = a.partial + (int64_t)blockIdx.y * a.partial_stride;
+    double* const out = a.partial + ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * a.partial_stride;
     const int64_t K = (int64_t)M * R;
     if (M >= T) {
         if (active) {
@@ -465,9 +488,14 @@ moments_acc_kernel(const MomentsArgs a) {
 
 // acc[j] += sum_b partial[b][j] in a fixed order (bitwise reproducible).  One warp per output when there are many
 // partials (lanes take b = lane, lane + 32, ... then a shuffle tree), one thread per output otherwise.
+// blockIdx.y = batch entry (bootstrap replicate): its partials follow those of the previous entry, its accumulator is
+// acc_batch_stride doubles further.
 __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n_partials, int64_t stride,
-                                       int64_t len, double* __restrict__ acc, int warp_per_output) {
+                                       int64_t len, double* __restrict__ acc, int warp_per_output,
+                                       int64_t acc_batch_stride) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    partial += (int64_t)blockIdx.y * n_partials * stride;
+    acc += (int64_t)blockIdx.y * acc_batch_stride;
     if (warp_per_output) {
         const int64_t j = gid >> 5;
         const int lane = threadIdx.x & 31;
@@ -481,6 +509,51 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
         double s = 0.0;
         for (int b = 0; b < n_partials; ++b) s += partial[(int64_t)b * stride + gid];
         acc[gid] += s;
+    }
+}
+
+// ---- row numbers of the bootstrap replicates (counter-based Philox4x32-10: reproducible, no state) ----
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        c[0] = hi1 ^ c[1] ^ k0;
+        c[1] = lo1;
+        c[2] = hi0 ^ c[3] ^ k1;
+        c[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+// Replicate blockIdx.y, draws 2*g and 2*g+1 of thread g.  Draw j belongs to the row block p with
+// cum[p] <= j < cum[p+1] (block p = rows [p n / P, (p+1) n / P)) and is uniform inside it: floor(r64 * size / 2^64).
+__global__ void resample_indices_kernel(uint64_t seed, uint64_t stream_id, int64_t n_rows, int64_t n_draws,
+                                        int n_blocks, const int64_t* __restrict__ block_cum, int32_t* __restrict__ idx) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int rep = blockIdx.y;
+    if (2 * g >= n_draws) return;
+    uint32_t c[4] = {(uint32_t)g, (uint32_t)(g >> 32), (uint32_t)rep, (uint32_t)stream_id};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(stream_id >> 32));
+    const int64_t* cum = block_cum ? block_cum + (int64_t)rep * (n_blocks + 1) : nullptr;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int64_t j = 2 * g + h;
+        if (j >= n_draws) break;
+        int64_t lo = 0, size = n_rows;
+        if (cum != nullptr) {
+            int a = 0, b = n_blocks;                 // largest p with cum[p] <= j
+            while (b - a > 1) {
+                const int mid = (a + b) >> 1;
+                if (__ldg(cum + mid) <= j) a = mid;
+                else b = mid;
+            }
+            lo = (int64_t)a * n_rows / n_blocks;
+            size = (int64_t)(a + 1) * n_rows / n_blocks - lo;
+        }
+        const uint64_t r = ((uint64_t)c[2 * h + 1] << 32) | c[2 * h];
+        idx[(int64_t)rep * n_draws + j] = (int32_t)(lo + (int64_t)__umul64hi(r, (uint64_t)size));
     }
 }
 
@@ -504,10 +577,19 @@ __global__ void sample_mask_kernel(const mlmcb200_basis_t basis, const double* _
     if (lane == 0) valid[sample] = good ? 1 : 0;
 }
 
+// blockIdx.y = batch entry (bootstrap replicate): accumulators acc_batch_stride apart, outputs packed per entry as
+// [l_means (L*K) | l_vars (L*K) | mean (K) | var (K)] when out_batch_stride != 0
 __global__ void finalize_levels_kernel(const double* __restrict__ acc, int64_t acc_stride, int n_levels, int64_t K,
-                                       double* l_means, double* l_vars, double* mean, double* var) {
+                                       double* l_means, double* l_vars, double* mean, double* var,
+                                       int64_t acc_batch_stride, int64_t out_batch_stride) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
+    acc += (int64_t)blockIdx.y * acc_batch_stride;
+    const int64_t out_off = (int64_t)blockIdx.y * out_batch_stride;
+    if (l_means) l_means += out_off;
+    if (l_vars) l_vars += out_off;
+    if (mean) mean += out_off;
+    if (var) var += out_off;
     double m_tot = 0.0, v_tot = 0.0;
     for (int l = 0; l < n_levels; ++l) {
         const double* a = acc + (int64_t)l * acc_stride;
@@ -531,15 +613,20 @@ __global__ void finalize_levels_kernel(const double* __restrict__ acc, int64_t a
 
 }  // namespace
 
-int launch_reduce_partials(const double* partial, int n_partials, int64_t stride, int64_t len, double* acc,
-                           cudaStream_t st) {
+int launch_reduce_partials_batched(const double* partial, int n_partials, int64_t stride, int64_t len, double* acc,
+                                   int n_batch, int64_t acc_batch_stride, cudaStream_t st) {
     const int threads = 256;
     const int wpo = n_partials >= 32 && len <= (1 << 20) ? 1 : 0;
     const int64_t total = wpo ? len * 32 : len;
-    reduce_partials_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(partial, n_partials,
-                                                                                            stride, len, acc, wpo);
+    const dim3 grid((unsigned)((total + threads - 1) / threads), (unsigned)n_batch);
+    reduce_partials_kernel<<<grid, threads, 0, st>>>(partial, n_partials, stride, len, acc, wpo, acc_batch_stride);
     MB_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+int launch_reduce_partials(const double* partial, int n_partials, int64_t stride, int64_t len, double* acc,
+                           cudaStream_t st) {
+    return launch_reduce_partials_batched(partial, n_partials, stride, len, acc, 1, 0, st);
 }
 
 namespace {
@@ -551,6 +638,7 @@ struct Plan {
     bool pair;    // lane pairs share accumulator columns (scalar quantity)
     bool fast;    // scalar quantity in storage order: specialised addressing
     bool stream;  // few moments (HBM-bound): tiles staged through a TMA-fed shared-memory ring
+    bool gather;  // re-sampled rows (bootstrap replicates in grid.z)
 };
 
 constexpr int kStages = 4;
@@ -576,6 +664,7 @@ int plan_moments(int kind, int size, int n_comp, int64_t n, bool coarse, bool st
     p->pair = n_comp == 1 && (size_t)2 * size * kThreads * sizeof(double) > 113u * 1024u;
     if (forced >= 0 && n_comp == 1) p->pair = forced != 0;
     p->fast = false;
+    p->gather = false;
     p->stream = stream;
     const size_t smem = (size_t)(p->pair ? 1 : 2) * size * kThreads * sizeof(double);
     if (smem + 64 > 227u * 1024u) {        // 64 B: static shared memory of the kernel (sample counters)
@@ -597,9 +686,30 @@ int plan_moments(int kind, int size, int n_comp, int64_t n, bool coarse, bool st
     return 0;
 }
 
-template <int KIND, bool COARSE, bool LOG, int S, bool PAIR, bool FAST, int STAGES = 0>
+// Replicates (grid.z) x sample partitions (grid.y) of a re-sampled launch: the number of partitions per replicate is
+// chosen so that the CTAs fill whole resident waves (a 1.01-wave grid would run at half speed).
+constexpr unsigned kMaxWavesResampled = 16;
+unsigned partitions_per_replicate(unsigned wave, unsigned n_rep, int64_t tiles) {
+    unsigned best = 1;
+    double best_eff = 0.0;
+    for (unsigned m = 1; m <= kMaxWavesResampled; ++m) {
+        unsigned gy = (unsigned)(((uint64_t)m * wave) / n_rep);
+        if (gy < 1) gy = 1;
+        if ((int64_t)gy * 4 > tiles && gy > 1) break;            // keep at least 4 tiles per CTA
+        const uint64_t ctas = (uint64_t)gy * n_rep;
+        const double eff = (double)ctas / (double)(((ctas + wave - 1) / wave) * wave);
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = gy;
+        }
+    }
+    if ((int64_t)best > tiles) best = (unsigned)(tiles > 0 ? tiles : 1);
+    return best;
+}
+
+template <int KIND, bool COARSE, bool LOG, int S, bool PAIR, bool FAST, int STAGES = 0, bool GATHER = false>
 int launch_moments(const MomentsArgs& a, Plan p, cudaStream_t st) {
-    auto kern = moments_acc_kernel<KIND, COARSE, LOG, S, PAIR, FAST, STAGES>;
+    auto kern = moments_acc_kernel<KIND, COARSE, LOG, S, PAIR, FAST, STAGES, GATHER>;
     if (STAGES > 0) p.smem += (size_t)STAGES * ((size_t)S * kThreads * 16 + 8);
     // resident CTAs per SM for this variant and shared-memory size (registers may bind before shared memory);
     // the sample-partition dimension of the grid is sized to exactly one resident wave
@@ -613,7 +723,13 @@ int launch_moments(const MomentsArgs& a, Plan p, cudaStream_t st) {
         cached_smem = p.smem;
     }
     const unsigned wave = (unsigned)((sm_count() * cached_ctas + p.grid.x - 1) / p.grid.x);
-    if (p.grid.y > wave) p.grid.y = wave;
+    if (p.grid.z > 1) {
+        const int TN = a.n_comp >= kThreads ? 1 : kThreads / a.n_comp;
+        const int64_t tiles = (a.n + (int64_t)S * TN - 1) / ((int64_t)S * TN);
+        p.grid.y = partitions_per_replicate(wave, p.grid.z, tiles);
+    } else if (p.grid.y > wave) {
+        p.grid.y = wave;
+    }
     kern<<<p.grid, kThreads, p.smem, st>>>(a);
     MB_CUDA_OK(cudaGetLastError());
     return (int)p.grid.y;
@@ -621,24 +737,41 @@ int launch_moments(const MomentsArgs& a, Plan p, cudaStream_t st) {
 
 template <int KIND, bool COARSE, bool LOG, int S>
 int launch_moments_pair(const MomentsArgs& a, const Plan& p, cudaStream_t st) {
-    if (p.fast && p.stream && !p.pair) return launch_moments<KIND, COARSE, LOG, S, false, true, kStages>(a, p, st);
-    if (KIND != MLMCB200_RAW && p.fast)
-        return p.pair ? launch_moments<KIND, COARSE, LOG, S, true, true>(a, p, st)
-                      : launch_moments<KIND, COARSE, LOG, S, false, true>(a, p, st);
+    // `if constexpr` keeps the number of kernel instantiations down (each costs ~1 s of build time)
+    if constexpr (KIND != MLMCB200_FOURIER && S == 8) {
+        if (p.fast && p.stream && !p.pair) return launch_moments<KIND, COARSE, LOG, S, false, true, kStages>(a, p, st);
+    }
+    if constexpr (KIND == MLMCB200_LEGENDRE) {
+        if (p.fast && p.gather)
+            return p.pair ? launch_moments<KIND, COARSE, LOG, S, true, true, 0, true>(a, p, st)
+                          : launch_moments<KIND, COARSE, LOG, S, false, true, 0, true>(a, p, st);
+    }
+    if constexpr (KIND != MLMCB200_RAW) {
+        if (p.fast)
+            return p.pair ? launch_moments<KIND, COARSE, LOG, S, true, true>(a, p, st)
+                          : launch_moments<KIND, COARSE, LOG, S, false, true>(a, p, st);
+    }
     return p.pair ? launch_moments<KIND, COARSE, LOG, S, true, false>(a, p, st)
                   : launch_moments<KIND, COARSE, LOG, S, false, false>(a, p, st);
 }
 
 template <int KIND, bool COARSE, bool LOG>
 int launch_moments_s(const MomentsArgs& a, const Plan& p, cudaStream_t st) {
-    if (KIND == MLMCB200_FOURIER) return launch_moments_pair<KIND, COARSE, LOG, 4>(a, p, st);
-    if (!COARSE && KIND != MLMCB200_RAW && p.S == 16) return launch_moments_pair<KIND, false, LOG, 16>(a, p, st);
-    return launch_moments_pair<KIND, COARSE, LOG, 8>(a, p, st);
+    if constexpr (KIND == MLMCB200_FOURIER) {
+        return launch_moments_pair<KIND, COARSE, LOG, 4>(a, p, st);
+    } else {
+        if constexpr (!COARSE && KIND != MLMCB200_RAW) {
+            if (p.S == 16) return launch_moments_pair<KIND, false, LOG, 16>(a, p, st);
+        }
+        return launch_moments_pair<KIND, COARSE, LOG, 8>(a, p, st);
+    }
 }
 
 template <int KIND>
 int launch_moments_kind(const MomentsArgs& a, const Plan& p, bool coarse, bool is_log, cudaStream_t st) {
-    if (KIND == MLMCB200_RAW) is_log = false;
+    if constexpr (KIND == MLMCB200_RAW) {
+        return coarse ? launch_moments_s<KIND, true, false>(a, p, st) : launch_moments_s<KIND, false, false>(a, p, st);
+    }
     if (is_log)
         return coarse ? launch_moments_s<KIND, true, true>(a, p, st) : launch_moments_s<KIND, false, true>(a, p, st);
     return coarse ? launch_moments_s<KIND, true, false>(a, p, st) : launch_moments_s<KIND, false, false>(a, p, st);
@@ -657,29 +790,40 @@ extern "C" int64_t mlmcb200_moments_workspace_bytes(int32_t size, int32_t n_comp
     return (int64_t)p.grid.y * (2 + 2 * (int64_t)size * n_comp) * (int64_t)sizeof(double);
 }
 
-extern "C" int mlmcb200_moments_accumulate(const mlmcb200_basis_t* basis, const double* pairs, int64_t n,
-                                           int32_t n_comp, int64_t stride_n, int64_t stride_side,
-                                           int64_t stride_m, int32_t has_coarse, const uint8_t* valid,
-                                           double* acc, void* workspace, int64_t workspace_bytes, void* stream) {
+namespace {
+
+// shared body of the plain (idx == NULL, n_rep == 1) and the re-sampled accumulate calls
+int moments_accumulate_impl(const mlmcb200_basis_t* basis, const double* pairs, int64_t n, int32_t n_comp,
+                            int64_t stride_n, int64_t stride_side, int64_t stride_m, int32_t has_coarse,
+                            const uint8_t* valid, const int32_t* idx, int32_t n_rep, double* acc,
+                            int64_t acc_rep_stride, void* workspace, int64_t workspace_bytes, cudaStream_t st,
+                            const char* who) {
     if (check_basis(basis) != 0) return -1;
-    MB_REQUIRE(n >= 0 && n_comp >= 1, "moments_accumulate: bad n=%lld n_comp=%d", (long long)n, n_comp);
-    MB_REQUIRE(acc != nullptr && workspace != nullptr, "moments_accumulate: null acc/workspace");
-    MB_REQUIRE(n_comp == 1 || valid != nullptr, "moments_accumulate: n_comp > 1 needs the sample mask");
+    MB_REQUIRE(n >= 0 && n_comp >= 1, "%s: bad n=%lld n_comp=%d", who, (long long)n, n_comp);
+    MB_REQUIRE(acc != nullptr && workspace != nullptr, "%s: null acc/workspace", who);
+    MB_REQUIRE(n_comp == 1 || valid != nullptr, "%s: n_comp > 1 needs the sample mask", who);
     if (n == 0) return 0;
-    MB_REQUIRE(pairs != nullptr, "moments_accumulate: null pairs");
-    cudaStream_t st = (cudaStream_t)stream;
+    MB_REQUIRE(pairs != nullptr, "%s: null pairs", who);
+    const bool gather = idx != nullptr;
     Plan p;
     // few moments + contiguous 16-byte aligned scalar rows + enough samples: HBM-bound -> TMA-ring variant
     const bool fast = n_comp == 1 && valid == nullptr &&
                       (has_coarse ? (stride_n == 2 && stride_side == 1 && (reinterpret_cast<uintptr_t>(pairs) & 15) == 0)
                                   : stride_n >= 1);
-    const bool use_ring = fast && basis->size <= kStreamMaxMoments && basis->kind != MLMCB200_FOURIER &&
-                        (stride_n == 2 || (!has_coarse && stride_n == 1)) &&
-                        (reinterpret_cast<uintptr_t>(pairs) & 15) == 0 && n >= (int64_t)8 * kThreads * 8;
+    const bool use_ring = fast && !gather && basis->size <= kStreamMaxMoments && basis->kind != MLMCB200_FOURIER &&
+                          (stride_n == 2 || (!has_coarse && stride_n == 1)) &&
+                          (reinterpret_cast<uintptr_t>(pairs) & 15) == 0 && n >= (int64_t)8 * kThreads * 8;
     if (plan_moments(basis->kind, basis->size, n_comp, n, has_coarse != 0, use_ring, &p) != 0) return -1;
     const int64_t K = (int64_t)basis->size * n_comp;
     const int64_t stride = 2 + 2 * K;
-    MB_REQUIRE(workspace_bytes >= (int64_t)p.grid.y * stride * 8, "moments_accumulate: workspace too small");
+    if (gather) {
+        p.grid.z = (unsigned)n_rep;
+        p.gather = true;
+        MB_REQUIRE(workspace_bytes >= mlmcb200_moments_resampled_workspace_bytes(basis->size, n_comp, n_rep),
+                   "%s: workspace too small", who);
+    } else {
+        MB_REQUIRE(workspace_bytes >= (int64_t)p.grid.y * stride * 8, "%s: workspace too small", who);
+    }
 
     MomentsArgs a;
     a.basis = *basis;
@@ -694,9 +838,12 @@ extern "C" int mlmcb200_moments_accumulate(const mlmcb200_basis_t* basis, const 
               (reinterpret_cast<uintptr_t>(pairs) & 15) == 0) ? 1 : 0;
     a.partial = static_cast<double*>(workspace);
     a.partial_stride = stride;
-    p.fast = fast;
+    a.idx = idx;
+    // re-sampling: only the Legendre kernels have a register-blocked gather variant, the other bases take the
+    // generic kernel (row indirection at run time)
+    p.fast = fast && (!gather || basis->kind == MLMCB200_LEGENDRE);
 
-    int rc = -1;     // > 0: number of partial vectors written
+    int rc = -1;     // > 0: number of partial vectors written (per replicate)
     const bool coarse = has_coarse != 0, is_log = basis->is_log != 0;
     switch (basis->kind) {
         case MLMCB200_RAW: rc = launch_moments_kind<MLMCB200_RAW>(a, p, coarse, is_log, st); break;
@@ -705,7 +852,62 @@ extern "C" int mlmcb200_moments_accumulate(const mlmcb200_basis_t* basis, const 
         case MLMCB200_FOURIER: rc = launch_moments_kind<MLMCB200_FOURIER>(a, p, coarse, is_log, st); break;
     }
     if (rc <= 0) return rc < 0 ? rc : -1;
-    return launch_reduce_partials(a.partial, rc, stride, stride, acc, st);
+    return launch_reduce_partials_batched(a.partial, rc, stride, stride, acc, gather ? n_rep : 1, acc_rep_stride, st);
+}
+
+}  // namespace
+
+extern "C" int mlmcb200_moments_accumulate(const mlmcb200_basis_t* basis, const double* pairs, int64_t n,
+                                           int32_t n_comp, int64_t stride_n, int64_t stride_side,
+                                           int64_t stride_m, int32_t has_coarse, const uint8_t* valid,
+                                           double* acc, void* workspace, int64_t workspace_bytes, void* stream) {
+    return moments_accumulate_impl(basis, pairs, n, n_comp, stride_n, stride_side, stride_m, has_coarse, valid,
+                                   nullptr, 1, acc, 0, workspace, workspace_bytes, (cudaStream_t)stream,
+                                   "moments_accumulate");
+}
+
+extern "C" int64_t mlmcb200_moments_resampled_workspace_bytes(int32_t size, int32_t n_comp, int32_t n_rep) {
+    Plan p;
+    if (size < 1 || n_comp < 1 || n_rep < 1) return -1;
+    if (plan_moments(MLMCB200_LEGENDRE, size, n_comp, -1, true, false, &p) != 0) return -1;
+    // plan grid.y = one wave at the shared-memory bound on CTAs per SM (>= the real occupancy)
+    const int64_t ctas = (int64_t)kMaxWavesResampled * p.grid.y + n_rep;
+    return ctas * (2 + 2 * (int64_t)size * n_comp) * (int64_t)sizeof(double);
+}
+
+extern "C" int mlmcb200_moments_accumulate_resampled(const mlmcb200_basis_t* basis, const double* pairs,
+                                                     int64_t n_rows, int32_t n_comp, int64_t stride_n,
+                                                     int64_t stride_side, int64_t stride_m, int32_t has_coarse,
+                                                     const uint8_t* valid, const int32_t* idx, int64_t n_draws,
+                                                     int32_t n_rep, double* acc, int64_t acc_rep_stride,
+                                                     void* workspace, int64_t workspace_bytes, void* stream) {
+    MB_REQUIRE(idx != nullptr && n_rep >= 1 && n_rep <= 65535, "moments_accumulate_resampled: bad idx / n_rep=%d",
+               n_rep);
+    MB_REQUIRE(n_rows >= 1 && n_rows <= 0x7fffffffLL, "moments_accumulate_resampled: n_rows=%lld out of range",
+               (long long)n_rows);
+    MB_REQUIRE(acc_rep_stride >= 2 + 2 * (int64_t)n_comp * (basis ? basis->size : 0),
+               "moments_accumulate_resampled: replicate stride too small");
+    return moments_accumulate_impl(basis, pairs, n_draws, n_comp, stride_n, stride_side, stride_m, has_coarse, valid,
+                                   idx, n_rep, acc, acc_rep_stride, workspace, workspace_bytes,
+                                   (cudaStream_t)stream, "moments_accumulate_resampled");
+}
+
+extern "C" int mlmcb200_resample_indices(uint64_t seed, uint64_t stream_id, int64_t n_rows, int64_t n_draws,
+                                         int32_t n_rep, int32_t n_blocks, const int64_t* block_cum, int32_t* idx,
+                                         void* stream) {
+    MB_REQUIRE(n_rows >= 1 && n_rows <= 0x7fffffffLL && n_draws >= 0 && n_rep >= 1 && n_rep <= 65535 && idx != nullptr,
+               "resample_indices: bad arguments (n_rows=%lld n_draws=%lld n_rep=%d)", (long long)n_rows,
+               (long long)n_draws, n_rep);
+    MB_REQUIRE(n_blocks >= 1 && n_blocks <= n_rows && (n_blocks == 1 || block_cum != nullptr),
+               "resample_indices: n_blocks=%d needs the cumulative block counts", n_blocks);
+    if (n_draws == 0) return 0;
+    const int threads = 256;
+    const int64_t pairs = (n_draws + 1) / 2;
+    const dim3 grid((unsigned)((pairs + threads - 1) / threads), (unsigned)n_rep);
+    resample_indices_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(seed, stream_id, n_rows, n_draws, n_blocks,
+                                                                        n_blocks > 1 ? block_cum : nullptr, idx);
+    MB_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int mlmcb200_sample_mask(const mlmcb200_basis_t* basis, const double* pairs, int64_t n, int32_t n_comp,
@@ -727,7 +929,22 @@ extern "C" int mlmcb200_finalize_levels(const double* acc, int64_t acc_stride, i
     MB_REQUIRE(acc != nullptr && n_levels >= 1 && K >= 1 && acc_stride >= 2 + 2 * K, "finalize_levels: bad arguments");
     const int threads = 128;
     finalize_levels_kernel<<<(unsigned)((K + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
-        acc, acc_stride, n_levels, K, l_means, l_vars, mean, var);
+        acc, acc_stride, n_levels, K, l_means, l_vars, mean, var, 0, 0);
+    MB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mlmcb200_finalize_levels_batched(const double* acc, int64_t acc_stride, int32_t n_levels, int64_t K,
+                                                int32_t n_batch, int64_t acc_batch_stride, double* out,
+                                                void* stream) {
+    MB_REQUIRE(acc != nullptr && out != nullptr && n_levels >= 1 && K >= 1 && acc_stride >= 2 + 2 * K &&
+                   n_batch >= 1 && n_batch <= 65535 && acc_batch_stride >= (int64_t)n_levels * acc_stride,
+               "finalize_levels_batched: bad arguments");
+    const int threads = 128;
+    const int64_t LK = (int64_t)n_levels * K;
+    const dim3 grid((unsigned)((K + threads - 1) / threads), (unsigned)n_batch);
+    finalize_levels_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
+        acc, acc_stride, n_levels, K, out, out + LK, out + 2 * LK, out + 2 * LK + K, acc_batch_stride, 2 * LK + 2 * K);
     MB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -91,19 +91,24 @@ class Estimate:
         return fitted
 
     # ---- bootstrap (``:171-218``).  The reference's version cannot run (its ``select(subsample(...))`` indexes
-    # with a float array, quantity.py:168-169); here the sub-sampled quantity is used directly. ----
-    def est_bootstrap(self, n_subsamples=100, sample_vector=None, moments_fn=None):
+    # with a float array, quantity.py:168-169); here the sub-sampled quantity is used directly.  For plain bases all
+    # replicates are fused on the device (``quantity_estimate.bootstrap_moments``): one launch per level. ----
+    def est_bootstrap(self, n_subsamples=100, sample_vector=None, moments_fn=None, seed=None):
         if moments_fn is not None:
             self._moments_fn = moments_fn
         moments_fn = self._moments_fn
         sample_vector = determine_sample_vec(self._sample_storage.get_n_collected(),
                                              self._sample_storage.get_n_levels(), sample_vector)
-        stats = {"mean": [], "var": [], "l_means": [], "l_vars": []}
-        for _ in range(n_subsamples):
-            sub = self.quantity.subsample(sample_vec=sample_vector)
-            q_mean = qe.estimate_mean(qe.moments(sub, moments_fn=moments_fn, mom_at_bottom=False))
-            for key in stats:
-                stats[key].append(getattr(q_mean, key))
+        if qe.can_fuse_bootstrap(self.quantity, moments_fn):
+            stats = qe.bootstrap_moments(self.quantity, moments_fn, sample_vector, n_subsamples, seed=seed,
+                                         mom_at_bottom=False)
+        else:
+            stats = {"mean": [], "var": [], "l_means": [], "l_vars": []}
+            for _ in range(n_subsamples):
+                sub = self.quantity.subsample(sample_vec=sample_vector)
+                q_mean = qe.estimate_mean(qe.moments(sub, moments_fn=moments_fn, mom_at_bottom=False))
+                for key in stats:
+                    stats[key].append(getattr(q_mean, key))
         self.mean_bs_mean, self.mean_bs_var = np.mean(stats["mean"], axis=0), np.mean(stats["var"], axis=0)
         self.mean_bs_l_means = np.mean(stats["l_means"], axis=0)
         self.mean_bs_l_vars = np.mean(stats["l_vars"], axis=0)

@@ -176,6 +176,19 @@ def estimate_mean(quantity):
                 acc = _native.LevelAccumulator(n_levels, x.shape[0], device)
             _native.moments_accumulate(_native.RAW_BASIS, x, acc.level(level_id))
 
+    if acc is None and multi:
+        # A rank whose shard holds no rows still has to enter the all-reduce with zeros of the right width.
+        if plan.kind == "moments":
+            width = plan.inner.size() * plan.fn.size
+        elif plan.kind == "transformed":
+            r0 = plan.fn.base_moments().size
+            width = r0
+            gram = _native.LevelAccumulator(n_levels, r0 * r0, device)
+        elif plan.kind == "covariance":
+            width = plan.fn.size * plan.fn.size
+        else:
+            width = quantity.size()
+        acc = _native.LevelAccumulator(n_levels, width, device)
     if acc is None:
         raise Exception("All samples were masked")
     if multi:
@@ -207,6 +220,124 @@ def estimate_mean(quantity):
         pass        # scalar input quantity: both layouts coincide
     return q_mod.QuantityMean(quantity.qtype, l_means=l_means, l_vars=l_vars, n_samples=n_samples,
                               n_rm_samples=n_rm_samples, mean=mean, var=var)
+
+
+def bootstrap_moments(quantity, moments_fn, sample_vector, n_subsamples, seed=None, mom_at_bottom=False,
+                      return_indices=False):
+    """All ``n_subsamples`` bootstrap replicates of ``estimate_mean(moments(quantity.subsample(sample_vector)))``
+    (the loop body of ``Estimate.est_bootstrap``, mlmc/estimator.py:185-193) fused on the device.
+
+    Replicate b draws, per level l, ``sample_vector[l]`` rows WITH replacement (``Quantity.pick_samples``,
+    mlmc/quantity/quantity.py:307-322: a level held in several chunks is split chunk by chunk with hypergeometric
+    sizes, rows are then chosen with replacement inside each chunk) and re-estimates the level sums.  The row
+    numbers are drawn on the device (``mlmcb200_resample_indices``, counter-based Philox keyed by the seed); one
+    launch per level handles all replicates (``mlmcb200_moments_accumulate_resampled``): samples are gathered through L2, never copied.
+
+    Returns a dict of NumPy arrays ``mean, var [B, K]``, ``l_means, l_vars [B, L, K]``, ``n_samples [B, L]``
+    (+ ``indices``: per level a list of (row offset, CUDA int32 tensor [B, draws]) when asked for -- the test hook
+    that lets a CPU check repeat the estimate on exactly the same rows)."""
+    import scipy.stats
+    storage_q = quantity.get_quantity_storage()
+    storage = storage_q._storage
+    level_ids = storage_q.level_ids()
+    n_levels = int(np.max(level_ids)) + 1
+    device = q_mod._device()
+    if _dist.world_size() > 1 and not getattr(storage, "rows_are_local_shard", False):
+        raise NotImplementedError("bootstrap over row shards: run it on one rank (replicates are independent)")
+    basis = moments_fn.basis_struct()
+    n_collected = [int(n) for n in storage.get_n_collected()]
+    B = int(n_subsamples)
+    seed = int(seed) if seed is not None else int(np.random.SeedSequence().entropy % (1 << 62))
+    host_rng = np.random.default_rng(seed)
+
+    acc = None
+    width = None
+    remaining = {l: (np.full(B, int(sample_vector[l]), dtype=np.int64), n_collected[l]) for l in level_ids}
+    indices = {l: [] for l in level_ids}
+    offsets = {l: 0 for l in level_ids}
+    chunk_id = 0
+    max_draws = 1 << 30                                               # row numbers per launch (4 GB of int32)
+    for level_id, rows in storage.device_chunks(level_ids, device, keep_resident=True):
+        n_chunk = int(rows.shape[0])
+        if n_chunk == 0:
+            continue
+        x = quantity.device_samples(q_mod.DeviceChunk(level_id, rows, chunk_id))
+        chunk_id += 1
+        if acc is None:
+            width = 2 + 2 * x.shape[0] * basis.size
+            acc = torch.zeros((B, n_levels, width), dtype=torch.float64, device=device)
+        k_left, n_left = remaining[level_id]
+        if n_chunk >= n_left:                                          # last (or only) chunk takes what is left
+            sizes = k_left.copy()
+        else:
+            sizes = np.array([scipy.stats.hypergeom(n_left, int(k), n_chunk).rvs(random_state=host_rng) if k > 0
+                              else 0 for k in k_left], dtype=np.int64)
+        remaining[level_id] = (k_left - sizes, n_left - n_chunk)
+        valid = _native.sample_mask(basis, x) if x.shape[0] > 1 else None
+        level_acc = acc[:, level_id]
+        stream_id = (level_id << 32) | chunk_id
+        row_bytes = 8 * x.shape[0] * x.shape[2]
+        # draws are listed by row block (<= 16 MB of rows each) so that the CTAs working on a replicate gather from
+        # a window that stays in L2; the per-block counts are multinomial, which keeps the draws i.i.d. uniform
+        n_blocks = int(min(64, max(1, -(-n_chunk * row_bytes // (16 << 20)))))
+
+        def draw(b0, b1, k):
+            cum = None
+            if n_blocks > 1 and k >= 4096 * n_blocks:
+                edges = (np.arange(n_blocks + 1, dtype=np.int64) * n_chunk) // n_blocks
+                counts = host_rng.multinomial(k, np.diff(edges) / n_chunk, size=b1 - b0)
+                cum_h = np.zeros((b1 - b0, n_blocks + 1), dtype=np.int64)
+                np.cumsum(counts, axis=1, out=cum_h[:, 1:])
+                cum = torch.from_numpy(cum_h).to(device)
+            return _native.resample_indices(seed + b0, stream_id, n_chunk, k, b1 - b0, device, block_cum=cum)
+
+        if np.all(sizes == sizes[0]):
+            k = int(sizes[0])
+            if k > 0:
+                group = max(1, min(B, max_draws // k))
+                for b0 in range(0, B, group):
+                    b1 = min(B, b0 + group)
+                    idx = draw(b0, b1, k)
+                    _native.moments_accumulate_resampled(basis, x, idx, level_acc[b0:b1], valid=valid)
+                    if return_indices:
+                        indices[level_id].append((offsets[level_id], b0, idx))
+        else:                                                          # ragged draws: one replicate per launch
+            for b in range(B):
+                k = int(sizes[b])
+                if k == 0:
+                    continue
+                idx = draw(b, b + 1, k)
+                _native.moments_accumulate_resampled(basis, x, idx, level_acc[b:b + 1], valid=valid)
+                if return_indices:
+                    indices[level_id].append((offsets[level_id], b, idx))
+        offsets[level_id] += n_chunk
+    if acc is None:
+        raise Exception("All samples were masked")
+
+    L, K = n_levels, (width - 2) // 2
+    packed = _native.finalize_levels_batched(acc)
+    host = _to_host(torch.cat([packed, acc[:, :, 0].reshape(B, L)], dim=1).reshape(-1)).reshape(B, -1)
+    l_means = host[:, :L * K].reshape(B, L, K)
+    l_vars = host[:, L * K:2 * L * K].reshape(B, L, K)
+    mean, var = host[:, 2 * L * K:2 * L * K + K], host[:, 2 * L * K + K:2 * L * K + 2 * K]
+    n_samples = host[:, 2 * L * K + 2 * K:].astype(np.int64)
+    if not mom_at_bottom:
+        r = moments_fn.size
+        l_means = l_means.reshape(B, L, -1, r).transpose(0, 1, 3, 2).reshape(B, L, K)
+        l_vars = l_vars.reshape(B, L, -1, r).transpose(0, 1, 3, 2).reshape(B, L, K)
+        mean = mean.reshape(B, -1, r).transpose(0, 2, 1).reshape(B, K)
+        var = var.reshape(B, -1, r).transpose(0, 2, 1).reshape(B, K)
+    out = {"mean": np.array(mean), "var": np.array(var), "l_means": np.array(l_means), "l_vars": np.array(l_vars),
+           "n_samples": n_samples}
+    if return_indices:
+        out["indices"] = indices
+    return out
+
+
+def can_fuse_bootstrap(quantity, moments_fn):
+    """The fused path covers plain (non-transformed) bases up to the kernel's size limit."""
+    return (not isinstance(moments_fn, TransformedMoments) and moments_fn.size <= _native.MAX_MOMENTS
+            and quantity.get_quantity_storage() is not None)
 
 
 _host_buffers = {}

@@ -328,3 +328,55 @@ def test_bootstrap_and_subsample(golden):
     sub = value.subsample(sample_vec=[100, 50, 25])
     qm = qe.estimate_mean(qe.moments(sub, fn))
     assert list(qm.n_samples + qm.n_rm_samples) == [100, 50, 25]
+
+
+def test_fused_bootstrap_matches_oracle_on_same_rows(golden):
+    """qe.bootstrap_moments: every replicate equals the oracle's estimate on exactly the rows it drew."""
+    import torch
+    from mlmc_b200.moments import Legendre
+    from mlmc_b200.quantity import quantity_estimate as qe
+    g = golden("estimates")
+    levels = [g["A_rows%d" % l] for l in range(3)]
+    storage, value = scalar_setup(levels, [[h] for h in g["A_steps"]], g["A_n_ops"])
+    domain = tuple(g["A_domain"])
+    fn = Legendre(8, domain)
+    sample_vec = [1500, 700, 300]
+    out = qe.bootstrap_moments(value, fn, sample_vec, 6, seed=11, return_indices=True)
+    assert out["mean"].shape == (6, 8) and out["l_vars"].shape == (6, 3, 8)
+    assert np.all(out["mean"][:, 0] == 1.0) and np.all(out["var"][:, 0] == 0.0)
+    basis = orc.Basis("legendre", 8, domain)
+    for b in range(6):
+        picked = []
+        for l in range(3):
+            parts = [levels[l][off + idx[b - b0].cpu().numpy()] for off, b0, idx in out["indices"][l]
+                     if b0 <= b < b0 + idx.shape[0]]
+            picked.append(np.concatenate(parts))
+        want = orc.estimate_moments(picked, basis)
+        assert list(out["n_samples"][b]) == list(want.n_samples)
+        rel_close(out["l_means"][b], want.l_means, rtol=1e-10, atol_scale=1e-14)
+        rel_close(out["l_vars"][b], want.l_vars, rtol=1e-10, atol_scale=1e-13)
+        rel_close(out["mean"][b], want.mean, rtol=1e-10, atol_scale=1e-14)
+        rel_close(out["var"][b], want.var, rtol=1e-10, atol_scale=1e-13)
+    # same seed -> same replicates
+    again = qe.bootstrap_moments(value, fn, sample_vec, 6, seed=11)
+    assert np.array_equal(again["mean"], out["mean"]) and np.array_equal(again["l_vars"], out["l_vars"])
+
+
+def test_fused_bootstrap_statistics(golden):
+    """est_bootstrap on the fused path: the bootstrap variance of the level means estimates l_var / n
+    (estimator.py:207: ``var_bs_l_means * n``) -- statistical check with many replicates."""
+    from mlmc_b200.moments import Legendre
+    from mlmc_b200.estimator import Estimate
+    g = golden("estimates")
+    levels = [g["A_rows%d" % l] for l in range(3)]
+    storage, value = scalar_setup(levels, [[h] for h in g["A_steps"]], g["A_n_ops"])
+    fn = Legendre(5, tuple(g["A_domain"]))
+    est = Estimate(value, storage, fn)
+    est.est_bootstrap(n_subsamples=400, seed=3)
+    full_means, full_vars = est.estimate_moments()
+    l_vars, n = est.estimate_diff_vars()
+    assert np.allclose(est.mean_bs_mean, full_means, atol=5 * np.sqrt(np.max(full_vars)) + 1e-12)
+    ratio = est._bs_level_mean_variance[:, 1:] / l_vars[:, 1:]
+    assert np.all((ratio > 0.7) & (ratio < 1.4)), ratio
+    n_est = est.bs_target_var_n_estimated(1e-5)
+    assert n_est.shape == (3,) and np.all(n_est >= 0)

@@ -426,3 +426,127 @@ def test_streaming_variant_few_moments(kind, R):
         assert np.array_equal(a[:, 0], want.n_samples) and np.array_equal(a[:, 1], want.n_rm_samples)
         rel_close(out["l_means"].cpu().numpy(), want.l_means, rtol=1e-10, atol_scale=1e-14)
         rel_close(out["l_vars"].cpu().numpy(), want.l_vars, rtol=1e-10, atol_scale=1e-14)
+
+
+# ------------------------------------------------------------------------------------------------------
+# bootstrap re-sampling (estimator.py:171-218 over quantity.py:307-322): all replicates of a level in one launch
+def _resampled_case(basis_o, rows, level0, n_rep, n_draws, seed):
+    """rows float64[N,2,M]; returns (got [B, 2+2K] numpy, list of oracle LevelEstimate per replicate)."""
+    nat = native()
+    basis = to_struct(basis_o)
+    M = rows.shape[2]
+    d_rows = torch.from_numpy(np.ascontiguousarray(rows)).to(dev())
+    x = d_rows.permute(2, 0, 1)
+    if level0:
+        x = x[:, :, :1]
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, len(rows), size=(n_rep, n_draws)).astype(np.int32)
+    acc = torch.zeros((n_rep, 2 + 2 * M * basis.size), dtype=torch.float64, device=dev())
+    nat.moments_accumulate_resampled(basis, x, torch.from_numpy(idx).to(dev()), acc)
+    want = []
+    for b in range(n_rep):
+        picked = rows[idx[b]]
+        want.append(orc.estimate_moments([picked] if level0 else [picked[:1], picked], basis_o))
+    return acc.cpu().numpy(), want, idx
+
+
+@pytest.mark.parametrize("tag,kind,size,level0,log,n_comp", [
+    ("leg", "legendre", 12, False, False, 1),        # gather variant of the register-blocked scalar kernel
+    ("leg0", "legendre", 9, True, False, 1),         # level 0 (16 samples per thread)
+    ("legpair", "legendre", 60, False, False, 1),    # lane-pair accumulator columns
+    ("leglog", "legendre", 7, False, True, 1),
+    ("mono", "monomial", 5, False, False, 1),        # generic kernel with row indirection
+    ("four", "fourier", 6, True, False, 1),
+    ("vec", "legendre", 5, False, False, 3),         # vector quantity: mask indexed by storage row
+])
+def test_resampled_levels_match_oracle(tag, kind, size, level0, log, n_comp):
+    rng = np.random.default_rng(42)
+    n = 5000
+    base = rng.lognormal(0.0, 0.5, size=(n, 1, n_comp)) if log else rng.normal(size=(n, 1, n_comp))
+    rows = np.concatenate([base, base + 0.05 * rng.normal(size=(n, 1, n_comp))], axis=1)
+    if log:
+        rows = np.abs(rows) + 1e-3
+    rows[rng.integers(0, n, 25), 0, 0] = np.nan                      # masked samples
+    rows[rng.integers(0, n, 15), 1, n_comp - 1] = 1e6 if not log else 1e9   # outside the domain -> masked (safe_eval)
+    dom = (0.05, 6.0) if log else (-3.5, 3.5)
+    b = orc.Basis(kind, size, dom, log=log, safe_eval=True)
+    n_rep, n_draws = 5, 3777                                          # ragged last tile
+    got, want, idx = _resampled_case(b, rows, level0, n_rep, n_draws, seed=7)
+    K = n_comp * size
+    for r in range(n_rep):
+        est = want[r]
+        lvl = 0 if level0 else 1
+        n_ok, n_rm = int(est.n_samples[lvl]), int(est.n_rm_samples[lvl])
+        assert (int(got[r, 0]), int(got[r, 1])) == (n_ok, n_rm), (tag, r)
+        assert n_ok + n_rm == n_draws
+        rel_close(got[r, 2:2 + K] / n_ok, est.l_means[lvl], rtol=1e-10, atol_scale=1e-14)
+        var = (got[r, 2 + K:] - got[r, 2:2 + K] ** 2 / n_ok) / (n_ok - 1)
+        rel_close(var, est.l_vars[lvl], rtol=1e-9, atol_scale=1e-13)
+
+
+def test_resampled_identity_draw_equals_plain_accumulate():
+    """idx = 0..N-1 must reproduce the plain accumulate call (same tiles, same order of operations) bit for bit."""
+    nat = native()
+    rng = np.random.default_rng(3)
+    n = 40000
+    rows = rng.normal(size=(n, 2, 1))
+    rows[:, 1, 0] = rows[:, 0, 0] + 0.01 * rng.normal(size=n)
+    basis = to_struct(orc.Basis("legendre", 20, (-4.0, 4.0)))
+    x = torch.from_numpy(rows).to(dev()).permute(2, 0, 1)
+    idx = torch.arange(n, dtype=torch.int32, device=dev()).reshape(1, n)
+    acc_r = torch.zeros((1, 42), dtype=torch.float64, device=dev())
+    nat.moments_accumulate_resampled(basis, x, idx, acc_r)
+    acc_p = torch.zeros(42, dtype=torch.float64, device=dev())
+    nat.moments_accumulate(basis, x, acc_p)
+    assert torch.equal(acc_r[0, :2], acc_p[:2])
+    rel_close(acc_r[0].cpu().numpy(), acc_p.cpu().numpy(), rtol=1e-12)
+
+
+def test_resampled_many_replicates_large():
+    """Size-independent property at a larger size: with every replicate drawing the same rows, all replicates agree
+    bit for bit, and their sums equal the plain accumulate of the gathered chunk."""
+    nat = native()
+    n, k, n_rep = 300000, 250000, 37
+    g = torch.Generator(device=dev())
+    g.manual_seed(5)
+    fine = torch.randn(n, generator=g, device=dev(), dtype=torch.float64)
+    rows = torch.stack([fine, fine + 0.02 * torch.randn(n, generator=g, device=dev(), dtype=torch.float64)], dim=1)
+    x = rows.reshape(n, 2, 1).permute(2, 0, 1)
+    basis = to_struct(orc.Basis("legendre", 30, (-4.0, 4.0)))
+    one = torch.randint(0, n, (1, k), dtype=torch.int32, device=dev(), generator=g)
+    idx = one.expand(n_rep, k).contiguous()
+    acc = torch.zeros((n_rep, 62), dtype=torch.float64, device=dev())
+    nat.moments_accumulate_resampled(basis, x, idx, acc)
+    assert all(torch.equal(acc[0], acc[r]) for r in range(1, n_rep))
+    gathered = rows[one[0].long()].reshape(k, 2, 1).permute(2, 0, 1)
+    plain = torch.zeros(62, dtype=torch.float64, device=dev())
+    nat.moments_accumulate(basis, gathered, plain)
+    assert torch.equal(acc[0, :2], plain[:2])
+    rel_close(acc[0].cpu().numpy(), plain.cpu().numpy(), rtol=1e-11)
+
+
+def test_resample_indices_blocks_and_uniformity():
+    nat = native()
+    n_rows, k, n_rep, P = 1_000_003, 400_001, 3, 7
+    plain = nat.resample_indices(5, 1, n_rows, k, n_rep, dev())
+    again = nat.resample_indices(5, 1, n_rows, k, n_rep, dev())
+    other = nat.resample_indices(6, 1, n_rows, k, n_rep, dev())
+    assert torch.equal(plain, again) and not torch.equal(plain, other)
+    assert not torch.equal(plain[0], plain[1])                         # replicates differ
+    h = plain.cpu().numpy()
+    assert h.min() >= 0 and h.max() < n_rows
+    # uniform draws: mean n/2 +- 5 sigma, decile counts within 5 sigma of k/10
+    assert abs(h.mean() - (n_rows - 1) / 2) < 5 * n_rows / np.sqrt(12 * h.size)
+    dec = np.bincount((h.ravel().astype(np.int64) * 10) // n_rows, minlength=10)
+    assert np.all(np.abs(dec - h.size / 10) < 5 * np.sqrt(h.size * 0.09))
+    # block order with prescribed multinomial counts
+    rng = np.random.default_rng(0)
+    edges = (np.arange(P + 1, dtype=np.int64) * n_rows) // P
+    counts = rng.multinomial(k, np.diff(edges) / n_rows, size=n_rep)
+    cum = np.zeros((n_rep, P + 1), dtype=np.int64)
+    np.cumsum(counts, axis=1, out=cum[:, 1:])
+    blk = nat.resample_indices(5, 1, n_rows, k, n_rep, dev(), block_cum=torch.from_numpy(cum).to(dev())).cpu().numpy()
+    for r in range(n_rep):
+        block_of = np.searchsorted(edges, blk[r], side="right") - 1
+        assert np.all(np.diff(block_of) >= 0)                          # listed in block order
+        assert np.array_equal(np.bincount(block_of, minlength=P), counts[r])

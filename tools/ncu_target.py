@@ -36,5 +36,16 @@ for rep in range(3):
         w = torch.full((Q,), 1.0 / Q, device=dev, dtype=torch.float64)
         lam = torch.zeros(R, device=dev, dtype=torch.float64)
         nat.maxent_fgh(phi, w, lam, 7)
+if which == "resampled":
+    nb = 4
+    for layout in ("random", "blocked"):
+        if layout == "random":
+            idx = torch.randint(0, n, (nb, n), dtype=torch.int32, device=dev)
+        else:
+            bs = n // 16
+            seg = (torch.arange(n, device=dev) // bs).clamp(max=15).to(torch.int32)
+            idx = (torch.randint(0, bs, (nb, n), dtype=torch.int32, device=dev) + seg[None, :] * bs).contiguous()
+        acc_r = torch.zeros((nb, 2 + 2 * bench.N_MOMENTS), dtype=torch.float64, device=dev)
+        nat.moments_accumulate_resampled(basis, views[1], idx, acc_r)
 torch.cuda.synchronize()
 print("ok", float(out["mean"][1]) if which in ("all", "moments") else "")
