@@ -108,7 +108,9 @@ class _Plan:
             inner = quantity._input_quantities[0]
             scalar = inner.size() == 1
             transformed = isinstance(fn, TransformedMoments)
-            base_ok = fn.base_moments().size <= _native.MAX_MOMENTS
+            # accumulator columns of the fused kernel: 113 moments per thread, 226 with lane-pair columns (scalar
+            # quantities only); larger bases take the generic path below (moments evaluated per row slice)
+            base_ok = fn.base_moments().size <= (226 if scalar else 113)
             if quantity._fused_kind == "moments" and base_ok and not transformed:
                 self.kind = "moments"
             elif quantity._fused_kind == "moments" and base_ok and transformed and scalar \
@@ -124,6 +126,25 @@ def _level_row_ranges(storage, level_ids):
     """Row range of every level handled by this rank (contiguous shards)."""
     n_collected = storage.get_n_collected()
     return {l: _dist.shard_range(int(n_collected[l])) for l in level_ids}
+
+
+_RAW_SLICE_BYTES = 1 << 30
+
+
+def _row_slices(chunks, plan):
+    """The generic path materialises the whole quantity ([K, n, 2] doubles) per chunk: cut chunks into row slices of
+    at most ~1 GB of evaluated values (a covariance of 130 moments is 270 kB per sample)."""
+    if plan.kind != "raw":
+        yield from chunks
+        return
+    per_row = 16 * max(1, plan.quantity.size())
+    step = max(1, _RAW_SLICE_BYTES // per_row)
+    for level_id, rows in chunks:
+        if rows.shape[0] <= step:
+            yield level_id, rows
+        else:
+            for start in range(0, rows.shape[0], step):
+                yield level_id, rows[start:start + step]
 
 
 def estimate_mean(quantity):
@@ -143,8 +164,8 @@ def estimate_mean(quantity):
     gram = None         # transformed moments: Gram of the base differences
     base_basis = None
     chunk_id = 0
-    for level_id, rows in storage.device_chunks(level_ids, device, keep_resident=not sharded,
-                                                row_ranges=ranges if sharded else None):
+    for level_id, rows in _row_slices(storage.device_chunks(level_ids, device, keep_resident=not sharded,
+                                                            row_ranges=ranges if sharded else None), plan):
         if rows.shape[0] == 0:
             continue
         x = plan.inner.device_samples(q_mod.DeviceChunk(level_id, rows, chunk_id))
@@ -336,7 +357,8 @@ def bootstrap_moments(quantity, moments_fn, sample_vector, n_subsamples, seed=No
 
 def can_fuse_bootstrap(quantity, moments_fn):
     """The fused path covers plain (non-transformed) bases up to the kernel's size limit."""
-    return (not isinstance(moments_fn, TransformedMoments) and moments_fn.size <= _native.MAX_MOMENTS
+    limit = 226 if quantity.size() == 1 else 113
+    return (not isinstance(moments_fn, TransformedMoments) and moments_fn.size <= limit
             and quantity.get_quantity_storage() is not None)
 
 

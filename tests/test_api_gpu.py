@@ -380,3 +380,28 @@ def test_fused_bootstrap_statistics(golden):
     assert np.all((ratio > 0.7) & (ratio < 1.4)), ratio
     n_est = est.bs_target_var_n_estimated(1e-5)
     assert n_est.shape == (3,) and np.all(n_est >= 0)
+
+
+def test_bases_beyond_the_fused_kernel_limits(golden):
+    """More moments than the fused kernels hold (226 / 112): the generic device path (moments evaluated per row slice,
+    RAW accumulate) still gives the reference's numbers."""
+    from mlmc_b200.moments import Legendre
+    from mlmc_b200.quantity import quantity_estimate as qe
+    g = golden("estimates")
+    levels = [g["A_rows%d" % l][:400] for l in range(3)]
+    storage, value = scalar_setup(levels, [[h] for h in g["A_steps"]], g["A_n_ops"])
+    domain = tuple(g["A_domain"])
+    qm = qe.estimate_mean(qe.moments(value, Legendre(240, domain)))
+    want = orc.estimate_moments(levels, orc.Basis("legendre", 240, domain))
+    assert list(qm.n_samples) == list(want.n_samples) and list(qm.n_rm_samples) == list(want.n_rm_samples)
+    rel_close(qm.l_means, want.l_means, rtol=1e-10, atol_scale=1e-14)
+    rel_close(qm.l_vars, want.l_vars, rtol=1e-10, atol_scale=1e-13)
+    old = qe._RAW_SLICE_BYTES
+    qe._RAW_SLICE_BYTES = 1 << 22                        # several row slices per level
+    try:
+        cm = qe.estimate_mean(qe.covariance(value, Legendre(120, domain)))
+    finally:
+        qe._RAW_SLICE_BYTES = old
+    wc = orc.estimate_covariance(levels, orc.Basis("legendre", 120, domain))
+    rel_close(np.ravel(cm.mean), wc.mean, rtol=1e-8, atol_scale=1e-13)
+    rel_close(np.ravel(cm.var), wc.var, rtol=1e-8, atol_scale=1e-13)
