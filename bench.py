@@ -119,18 +119,20 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, int(est.n_samples.sum())
 
 
-def cpu_reference_run(n_rows_per_level, n_procs, chunk_rows=65536):
+def cpu_reference_run(n_rows_per_level, n_procs, chunk_rows=65536, pool=None):
     """Time the oracle port on ``n_procs`` host processes, each with its own shard of ``n_rows_per_level`` rows per
     level (the reference itself is single-threaded NumPy; sharding over processes is the most generous way to let
-    it use the host's cores).  Returns (sample-moments/s, wall seconds)."""
+    it use the host's cores).  Returns (sample-moments/s, slowest worker's seconds, wall seconds)."""
     import multiprocessing as mp
     jobs = [(1234 + 1000 * p, n_rows_per_level, chunk_rows) for p in range(n_procs)]
     t0 = time.perf_counter()
     if n_procs == 1:
         results = [_cpu_worker(jobs[0])]
+    elif pool is not None:
+        results = pool.map(_cpu_worker, jobs, chunksize=1)
     else:
-        with mp.get_context("spawn").Pool(n_procs) as pool:
-            results = pool.map(_cpu_worker, jobs)
+        with mp.get_context("spawn").Pool(n_procs) as own:
+            results = own.map(_cpu_worker, jobs, chunksize=1)
     wall = time.perf_counter() - t0
     inner = max(r[0] for r in results)
     units = N_LEVELS * n_rows_per_level * n_procs * N_MOMENTS
@@ -143,14 +145,18 @@ def run_reference_arm(args):
         return
     cores = os.cpu_count() or 1
     n_procs = max(1, min(cores, 64))
-    rows = 200_000                      # per level per process: a bounded sample of the 1e7-row workload
-    for _ in range(max(args.warmup, 0)):
-        cpu_reference_run(20_000, n_procs)
+    # per level per process: a bounded sample of the 1e7-row workload, ~2.5 s of NumPy per process and step, shrunk
+    # for long runs so that the whole arm stays within a few minutes
+    rows = 500_000 if args.steps <= 20 else max(50_000, 10_000_000 // args.steps)
+    import multiprocessing as mp
     values, ms = [], []
-    for _ in range(args.steps):
-        v, inner, _wall = cpu_reference_run(rows, n_procs)
-        values.append(v)
-        ms.append(inner * 1e3)
+    with mp.get_context("spawn").Pool(n_procs) as pool:
+        for _ in range(max(args.warmup, 0)):
+            cpu_reference_run(20_000, n_procs, pool=pool)
+        for _ in range(args.steps):
+            v, inner, _wall = cpu_reference_run(rows, n_procs, pool=pool)
+            values.append(v)
+            ms.append(inner * 1e3)
     value = float(np.median(values))
     sample = "%d processes x %d rows/level x %d levels of the cfg2 workload (oracle port, NumPy)" % (n_procs, rows, N_LEVELS)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -360,7 +366,7 @@ def run_gpu_arm(args):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         n_procs = max(1, min(os.cpu_count() or 1, 64))
-        rows_cpu = 100_000
+        rows_cpu = 1_000_000                 # ~5 s of NumPy per process; ~10-20 s wall with all cores busy
         v, inner, _wall = cpu_reference_run(rows_cpu, n_procs)
         v1, inner1, _ = cpu_reference_run(rows_cpu, 1)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": n_procs, "kind": "port",
