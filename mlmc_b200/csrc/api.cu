@@ -123,6 +123,32 @@ __global__ void dmma_peak_kernel(double* sink, int iters, double seed) {
     if (r == 123.456) sink[0] = r;
 }
 
+// NACC independent accumulator tiles per warp, fragments re-read from shared memory every step (the covariance
+// kernel's pattern): how many independent DMMA chains / warps does the tensor pipe need?
+template <int NACC>
+__global__ void dmma_chain_kernel(double* sink, int iters, double seed) {
+    __shared__ double frag[64];
+    if (threadIdx.x < 64) frag[threadIdx.x] = 1.0 + 1e-9 * threadIdx.x;
+    __syncthreads();
+    double c[2 * NACC];
+#pragma unroll
+    for (int i = 0; i < 2 * NACC; ++i) c[i] = seed + i;
+    const volatile double* fr = frag;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 32 / NACC; ++u) {
+            const double a = fr[threadIdx.x & 31], b = fr[32 + (threadIdx.x & 31)];
+#pragma unroll
+            for (int t = 0; t < NACC; ++t) dmma884(c[2 * t], c[2 * t + 1], a, b);
+        }
+    }
+    double r = 0;
+#pragma unroll
+    for (int i = 0; i < 2 * NACC; ++i) r += c[i];
+    if (r == 123.456) sink[0] = r;
+}
+
 }  // namespace
 }  // namespace mlmcb200
 
@@ -136,9 +162,12 @@ extern "C" int mlmcb200_sm_count(void) { return sm_count(); }
 
 extern "C" int mlmcb200_fp64_peak(int32_t kind, double* flops_per_s, void* stream) {
     // kind & 15: 0 DFMA (2 loop-invariant operands), 1 DMMA m8n8k4, 2 DFMA with 3 distinct register operands,
-    //            3 dependent-DFMA latency in SM cycles (returned in *flops_per_s);  kind >> 4: warps per SM (0 = 64)
-    const int base = kind & 15, warps_per_sm = kind >> 4;
-    MB_REQUIRE(flops_per_s != nullptr && base >= 0 && base <= 3, "fp64_peak: bad arguments");
+    //            3 dependent-DFMA latency in SM cycles (returned in *flops_per_s), 4 DMMA with (kind >> 12) & 15 = 1, 2, 4
+    //            or 8 independent accumulator tiles per warp and fragments from shared memory;
+    //            (kind >> 4) & 255: warps per SM (0 = 64)
+    const int base = kind & 15, warps_per_sm = (kind >> 4) & 255, n_acc = (kind >> 12) & 15;
+    MB_REQUIRE(flops_per_s != nullptr && base >= 0 && base <= 4, "fp64_peak: bad arguments");
+    MB_REQUIRE(base != 4 || n_acc == 1 || n_acc == 2 || n_acc == 4 || n_acc == 8, "fp64_peak: bad accumulator count");
     cudaStream_t st = (cudaStream_t)stream;
     double* sink = nullptr;
     MB_CUDA_OK(cudaMalloc(&sink, 16));
@@ -166,6 +195,14 @@ extern "C" int mlmcb200_fp64_peak(int32_t kind, double* flops_per_s, void* strea
             dfma_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, 0.5);
         else if (base == 1)
             dmma_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, 0.5);
+        else if (base == 4 && n_acc == 1)
+            dmma_chain_kernel<1><<<blocks, threads, 0, st>>>(sink, iters, 0.5);
+        else if (base == 4 && n_acc == 2)
+            dmma_chain_kernel<2><<<blocks, threads, 0, st>>>(sink, iters, 0.5);
+        else if (base == 4 && n_acc == 4)
+            dmma_chain_kernel<4><<<blocks, threads, 0, st>>>(sink, iters, 0.5);
+        else if (base == 4)
+            dmma_chain_kernel<8><<<blocks, threads, 0, st>>>(sink, iters, 0.5);
         else
             dfma3_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters, 0.5);
         MB_CUDA_OK(cudaGetLastError());
@@ -174,7 +211,7 @@ extern "C" int mlmcb200_fp64_peak(int32_t kind, double* flops_per_s, void* strea
         float ms = 0.f;
         MB_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
         double flops;
-        if (base == 1)
+        if (base == 1 || base == 4)
             flops = (double)blocks * (threads / 32) * iters * 32.0 * (8 * 8 * 4) * 2.0;  // 32 DMMA per warp-iteration
         else
             flops = (double)blocks * threads * iters * 64.0 * 2.0;                   // 64 DFMA per thread-iteration

@@ -14,6 +14,7 @@
 // Fragment layout of m8n8k4 (lane l): A[row l/4][k l%4], B[k l%4][col l/4], C[row l/4][cols 2(l%4), 2(l%4)+1].
 // With A = Phi^T and B = Phi (k = sample), BOTH operand fragments of moment block b are the same smem element
 // Phi[n0 + l%4][8b + l/4]; a leading dimension LD = 4 (mod 8) doubles makes that access conflict-free.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mlmcb200 {
@@ -22,8 +23,11 @@ namespace {
 constexpr int kWarps = 16;
 constexpr int kThreadsGram = kWarps * 32;
 constexpr int kMaxSlots = 3;     // tasks per warp (array bound; the plan uses 2 or 3)
-constexpr int kGenWarps = 4;     // pipelined variant: dedicated generator warps (one per SM sub-partition)
 constexpr int kMaxGroup = 2;     // blocks per task side
+// Leading dimension of the covariance tiles, a compile-time constant (4 mod 8, >= 8 * 13 + 3 for the row skew) so that
+// every fragment address of a tile is "slot base register + immediate": holds up to 13 blocks = 104 moments.
+constexpr int kLD = 108;
+constexpr int kGramMaxMoments = 104;
 
 struct GramPlan {
     int nb;          // 8x8 blocks per side
@@ -90,11 +94,37 @@ __device__ __forceinline__ void write_row(const mlmcb200_basis_t& b, double t, b
         double p0 = 1.0, p1 = t;
         row[0] = p0;
         if (R > 1) row[1] = p1;
-        for (int i = 2; i < R; ++i) {
-            const double p2 = b.kind == MLMCB200_LEGENDRE ? fma(kLegA[i] * t, p1, -(kLegB[i] * p0)) : p1 * t;
-            row[i] = p2;
-            p0 = p1;
-            p1 = p2;
+        if (b.kind == MLMCB200_LEGENDRE) {
+            // MONIC recurrence W_i = t W_{i-1} - e_i W_{i-2} (P_i = g_i W_i, applied to the sums in the epilogue): two FP64
+            // instructions per element instead of three.  Four steps per iteration, coefficient loads hoisted.
+            // W_i = fma(t, W_{i-1}, -(e_i W_{i-2})): the product is off the dependent chain (one DFMA latency per step).
+            int i = 2;
+            for (; i + 3 < R; i += 4) {
+                const double e0 = kLegCoef[i], e1 = kLegCoef[i + 1], e2 = kLegCoef[i + 2], e3 = kLegCoef[i + 3];
+                const double q0 = fma(t, p1, -(e0 * p0));
+                const double q1 = fma(t, q0, -(e1 * p1));
+                const double q2 = fma(t, q1, -(e2 * q0));
+                const double q3 = fma(t, q2, -(e3 * q1));
+                row[i] = q0;
+                row[i + 1] = q1;
+                row[i + 2] = q2;
+                row[i + 3] = q3;
+                p0 = q2;
+                p1 = q3;
+            }
+            for (; i < R; ++i) {
+                const double p2 = fma(t, p1, -(kLegCoef[i] * p0));
+                row[i] = p2;
+                p0 = p1;
+                p1 = p2;
+            }
+        } else {
+            for (int i = 2; i < R; ++i) {
+                const double p2 = p1 * t;
+                row[i] = p2;
+                p0 = p1;
+                p1 = p2;
+            }
         }
     }
     for (int i = R; i < r_pad; ++i) row[i] = 0.0;
@@ -155,6 +185,26 @@ __device__ __forceinline__ void slot_mma(double (&am)[GS][GS][2], double (&av)[G
 #undef MB_FOR_BLOCKS
 }
 
+// All k-steps of one tile for one task slot.  The fragment pointers of the slot are computed once per tile; inside
+// the 4-k-step unrolled body every shared-memory address is pointer + immediate (constant kLD, the row skew has
+// period 4 k-steps), so the loop carries no address arithmetic and the loads of a k-step can be hoisted over the DMMAs
+// of the previous one.  NS is a multiple of 16.
+template <bool COARSE, int MODE, int GS, int MASK>
+__device__ __forceinline__ void slot_tile(double (&am)[GS][GS][2], double (&av)[GS][GS][2], const double* phi_f,
+                                          const double* phi_c, const int (&off_r)[GS], const int (&off_c)[GS],
+                                          int NS) {
+    for (int k0 = 0; k0 < NS; k0 += 16) {
+        const double* pf = phi_f + (size_t)k0 * kLD;
+        const double* pc = phi_c + (size_t)k0 * kLD;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double* pfq = pf + q * 4 * kLD + q;
+            const double* pcq = pc + q * 4 * kLD + q;
+            slot_mma<COARSE, MODE, GS, MASK>(am, av, pfq, pcq, off_r, off_c);       // skew of rows k0 + 4q .. : q
+        }
+    }
+}
+
 // the block masks the planner can emit (make_plan): whole group, one column, one row, upper triangle, single blocks
 #define MB_SLOT_SWITCH(MASKVAR, CALL)                                           \
     switch (MASKVAR) {                                                          \
@@ -170,18 +220,19 @@ __device__ __forceinline__ void slot_mma(double (&am)[GS][GS][2], double (&av)[G
 
 // MODE 0: covariance sums only; 1: covariance sums + sums of squares; 2: Gram of the differences
 //
-// PIPE = true (MODE 0 / 2): warp-specialised.  The last kGenWarps warps (one per SM sub-partition) only PRODUCE basis
-//   rows -- one (sample, side) recurrence per thread, FP64 pipe -- into one of two shared-memory tiles while the other
-//   12 warps CONSUME the previous tile with DMMA (tensor pipe); one __syncthreads per tile.
-// PIPE = false (MODE 1, whose 4 accumulators per block leave no registers for a third task slot): all 16 warps
-//   produce a single, larger tile, then all consume it.
-template <bool COARSE, int MODE, int GS, bool PIPE>
+// A tile is PRODUCED (basis rows, one (sample, side) recurrence per thread on the FP64 pipe), then CONSUMED by all 16
+// warps with DMMA, in separate phases.  A warp-specialised variant that overlapped the two (4 producer warps filling
+// a second tile while 12 warps contracted the first) was slower: an FP64-pipe instruction issued while DMMAs are in
+// flight costs the tensor pipe ~10 cycles (measured: contraction alone 33.5 TFLOP/s, producers alone 1/3 of that time,
+// together 26.6 TFLOP/s), so the phases do not overlap for free and the larger single tile wins (28.6 TFLOP/s).
+template <bool COARSE, int MODE, int GS>
 __global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a) {
     extern __shared__ double sm[];
     const GramPlan& pl = a.plan;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int LD = pl.ld, NS = pl.ns, nb = pl.nb, r_pad = 8 * nb, R = a.basis.size;
-    constexpr int SLOTS = PIPE ? 3 : 2;
+    constexpr int LD = kLD;
+    const int NS = pl.ns, nb = pl.nb, r_pad = 8 * nb, R = a.basis.size;
+    constexpr int SLOTS = 2;
     const size_t tile_elems = (size_t)2 * NS * LD;             // Phi_f rows then Phi_c rows
     __shared__ unsigned cnt_sm[2];
     if (tid == 0) cnt_sm[0] = cnt_sm[1] = 0;
@@ -219,74 +270,71 @@ __global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a)
         mask[slot] = used ? pl.mk[warp][slot] : 0;
     }
 
-    // basis rows of one tile: item w = (sample s, side); every item tests both sides of its sample for validity
-    auto produce = [&](int64_t tile, double* tile_base, int first, int n_threads) {
-        for (int w = first; w < NS * n_sides; w += n_threads) {
-            const int side = w >= NS ? 1 : 0, s = w - side * NS;
+    // Basis rows of one tile: item = (sample s, side), at most one item per producing thread; every item tests both sides
+    // of its sample for validity.  The raw values of an item are FETCHED one tile ahead (registers), so the DRAM latency
+    // hides behind the contraction of the current tile.
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    auto fetch = [&](int64_t tile, int item, double& xf, double& xc) {
+        xf = xc = qnan;
+        if (item < NS * n_sides && tile < n_tiles) {
+            const int s = item >= NS ? item - NS : item;
             const int64_t n = tile * NS + s;
-            double* row = tile_base + ((size_t)side * NS + s) * LD;
-            bool good = n < a.n;
-            double t = 0.0;
-            if (good) {
-                const double xf = __ldcs(a.pairs + n * a.stride_n);
-                const double tf = a.basis.kind == MLMCB200_RAW ? xf : map_to_ref(a.basis, xf);
-                good = moments_finite(a.basis, tf);
-                t = tf;
-                if (COARSE) {
-                    const double xc = __ldcs(a.pairs + n * a.stride_n + a.stride_side);
-                    const double tc = a.basis.kind == MLMCB200_RAW ? xc : map_to_ref(a.basis, xc);
-                    good = good && moments_finite(a.basis, tc);
-                    if (side == 1) t = tc;
-                }
-                if (side == 0) {
-                    cnt_ok += good ? 1u : 0u;
-                    cnt_rm += good ? 0u : 1u;
-                }
+            if (n < a.n) {
+                xf = __ldcs(a.pairs + n * a.stride_n);
+                if (COARSE) xc = __ldcs(a.pairs + n * a.stride_n + a.stride_side);
             }
-            write_row(a.basis, t, good, row, r_pad);
         }
     };
+    auto generate = [&](int64_t tile, double* tile_base, int item, double xf, double xc) {
+        if (item >= NS * n_sides) return;
+        const int side = item >= NS ? 1 : 0, s = item - side * NS;
+        const int64_t n = tile * NS + s;
+        // rows are skewed by (s / 4) % 4 doubles: the 16 lanes of a half-warp then store to 16 distinct 8-byte
+        // bank pairs (row stride LD = 4 mod 8 alone gives only 4), and a k-step's 4 rows share one skew
+        double* row = tile_base + ((size_t)side * NS + s) * LD + ((s >> 2) & 3);
+        bool good = n < a.n;
+        double t = 0.0;
+        if (good) {
+            const double tf = a.basis.kind == MLMCB200_RAW ? xf : map_to_ref(a.basis, xf);
+            good = moments_finite(a.basis, tf);
+            t = tf;
+            if (COARSE) {
+                const double tc = a.basis.kind == MLMCB200_RAW ? xc : map_to_ref(a.basis, xc);
+                good = good && moments_finite(a.basis, tc);
+                if (side == 1) t = tc;
+            }
+            if (side == 0) {
+                cnt_ok += good ? 1u : 0u;
+                cnt_rm += good ? 0u : 1u;
+            }
+        }
+        write_row(a.basis, t, good, row, r_pad);
+    };
     auto consume = [&](const double* tile_base) {
-        const double* phi_f = tile_base;
-        const double* phi_c = tile_base + (size_t)NS * LD;
-        for (int k0 = 0; k0 < NS; k0 += 4) {
-            const double* pf = phi_f + (size_t)k0 * LD + frag_off;
-            const double* pc = phi_c + (size_t)k0 * LD + frag_off;
+        const double* phi_f = tile_base + frag_off;
+        const double* phi_c = phi_f + (size_t)NS * LD;
 #pragma unroll
-            for (int slot = 0; slot < SLOTS; ++slot) {
-                if (GS == 1) {
-                    if (mask[slot]) slot_mma<COARSE, MODE, GS, 0x1>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], pf, pc, off_r[slot], off_c[slot]);
-                } else {
-#define MB_CALL(M) slot_mma<COARSE, MODE, GS, M>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], pf, pc, off_r[slot], off_c[slot])
-                    MB_SLOT_SWITCH(mask[slot], MB_CALL)           // warp-uniform; straight-line DMMA runs inside
+        for (int slot = 0; slot < SLOTS; ++slot) {
+            if (GS == 1) {
+                if (mask[slot])
+                    slot_tile<COARSE, MODE, GS, 0x1>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], phi_f, phi_c, off_r[slot],
+                                                     off_c[slot], NS);
+            } else {
+#define MB_CALL(M) slot_tile<COARSE, MODE, GS, M>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], phi_f, phi_c, off_r[slot], off_c[slot], NS)
+                MB_SLOT_SWITCH(mask[slot], MB_CALL)               // warp-uniform, once per slot and tile
 #undef MB_CALL
-                }
             }
         }
     };
 
-    if (PIPE) {
-        constexpr int kGenThreads = kGenWarps * 32, kMmaThreads = kThreadsGram - kGenThreads;
-        const bool is_gen = tid >= kMmaThreads;
-        if (is_gen) produce(blockIdx.x, sm, tid - kMmaThreads, kGenThreads);
+    double xf_n, xc_n;                                      // raw values of this thread's item of the next tile
+    fetch(blockIdx.x, tid, xf_n, xc_n);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        generate(tile, sm, tid, xf_n, xc_n);
+        fetch(tile + gridDim.x, tid, xf_n, xc_n);
         __syncthreads();
-        int buf = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
-            if (is_gen) {
-                if (tile + gridDim.x < n_tiles)
-                    produce(tile + gridDim.x, sm + (buf ^ 1) * tile_elems, tid - kMmaThreads, kGenThreads);
-            } else {
-                consume(sm + buf * tile_elems);
-            }
-            __syncthreads();
-        }
-    } else {
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            produce(tile, sm, tid, kThreadsGram);
-            __syncthreads();
-            consume(sm);
-            __syncthreads();
-        }
+        consume(sm);
+        __syncthreads();
     }
 
     // ---- epilogue: one partial [2 + 2 R R] per CTA, upper blocks mirrored ----
@@ -308,11 +356,15 @@ __global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a)
                             const int i = 8 * I + (lane >> 2), j = 8 * J + 2 * (lane & 3) + e;
                             // diagonal blocks: keep the upper triangle and mirror it, so the result is exactly symmetric
                             if (i < R && j < R && (I != J || j >= i)) {
-                                out_m[(int64_t)i * R + j] = acc_m[slot][u][v][e];
-                                if (i != j) out_m[(int64_t)j * R + i] = acc_m[slot][u][v][e];
+                                // Legendre tiles hold the monic W_i: P_i P_j = (g_i g_j) W_i W_j
+                                const double gg = a.basis.kind == MLMCB200_LEGENDRE ? kLegAlpha[i] * kLegAlpha[j] : 1.0;
+                                const double vm = acc_m[slot][u][v][e] * gg;
+                                out_m[(int64_t)i * R + j] = vm;
+                                if (i != j) out_m[(int64_t)j * R + i] = vm;
                                 if (MODE == 1) {
-                                    out_v[(int64_t)i * R + j] = acc_v[slot][u][v][e];
-                                    if (i != j) out_v[(int64_t)j * R + i] = acc_v[slot][u][v][e];
+                                    const double vv = acc_v[slot][u][v][e] * (gg * gg);
+                                    out_v[(int64_t)i * R + j] = vv;
+                                    if (i != j) out_v[(int64_t)j * R + i] = vv;
                                 }
                             }
                         }
@@ -331,9 +383,13 @@ __global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a)
 
 int popcount4(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1); }
 
-// n_warps / n_slots: warps that contract and task slots per warp; two_tiles: double-buffered (pipelined) layout
-int make_plan(int R, int n_warps, int n_slots, bool two_tiles, GramPlan* pl, size_t* smem) {
+// n_warps / n_slots: warps that contract and task slots per warp; two_tiles: room for a second tile (unused now)
+int make_plan(int R, int n_warps, int n_slots, bool two_tiles, GramPlan* pl, size_t* smem, int fixed_ld = 0) {
     const int nb = (R + 7) / 8;
+    if (fixed_ld && R > kGramMaxMoments) {
+        set_error("gram: %d moments do not fit the shared-memory tile (max %d)", R, kGramMaxMoments);
+        return -1;
+    }
     pl->nb = nb;
     pl->gs = nb <= 5 ? 1 : 2;
     const int gs = pl->gs;
@@ -394,12 +450,13 @@ int make_plan(int R, int n_warps, int n_slots, bool two_tiles, GramPlan* pl, siz
     }
     int ld = 8 * nb;
     while (ld % 8 != 4) ++ld;
+    if (fixed_ld) ld = fixed_ld;
     pl->ld = ld;
     // tile(s) of Phi_f + Phi_c rows; NS a multiple of 4
     const size_t budget = 216u * 1024u;
     const int n_tiles = two_tiles ? 2 : 1;
     int ns = (int)(budget / ((size_t)2 * n_tiles * ld * sizeof(double)));
-    ns = (ns / 4) * 4;
+    ns = fixed_ld ? (ns / 16) * 16 : (ns / 4) * 4;      // covariance tiles: whole 4-k-step unrolled bodies
     const int cap = two_tiles ? 64 : 128;
     if (ns > cap) ns = cap;
     if (ns < 8) {
@@ -413,8 +470,7 @@ int make_plan(int R, int n_warps, int n_slots, bool two_tiles, GramPlan* pl, siz
 
 template <bool COARSE, int MODE, int GS>
 int launch_gram(const GramArgs& a, int grid, size_t smem, cudaStream_t st) {
-    constexpr bool kPipe = MODE != 1;
-    auto kern = gram_kernel<COARSE, MODE, GS, kPipe>;
+    auto kern = gram_kernel<COARSE, MODE, GS>;
     MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreadsGram, smem, st>>>(a);
     MB_CUDA_OK(cudaGetLastError());
@@ -616,8 +672,7 @@ extern "C" int mlmcb200_gram_accumulate(const mlmcb200_basis_t* basis, const dou
     a.stride_n = stride_n;
     a.stride_side = stride_side;
     size_t smem = 0;
-    const bool pipe = !(mode == 0 && want_var);                 // MODE 1 (sums + squares) is the non-pipelined variant
-    if (make_plan(basis->size, pipe ? kWarps - kGenWarps : kWarps, pipe ? 3 : 2, pipe, &a.plan, &smem) != 0) return -1;
+    if (make_plan(basis->size, kWarps, 2, false, &a.plan, &smem, kLD) != 0) return -1;
     const int64_t R2 = (int64_t)basis->size * basis->size;
     const int64_t stride = 2 + 2 * R2;
     const int64_t tiles = (n + a.plan.ns - 1) / a.plan.ns;

@@ -114,9 +114,9 @@ class _Plan:
             if quantity._fused_kind == "moments" and base_ok and not transformed:
                 self.kind = "moments"
             elif quantity._fused_kind == "moments" and base_ok and transformed and scalar \
-                    and fn.base_moments().size <= 112:
+                    and fn.base_moments().size <= 104:
                 self.kind = "transformed"
-            elif quantity._fused_kind == "covariance" and scalar and not transformed and fn.size <= 112:
+            elif quantity._fused_kind == "covariance" and scalar and not transformed and fn.size <= 104:
                 self.kind = "covariance"
             if self.kind != "raw":
                 self.inner, self.fn, self.at_bottom = inner, fn, quantity._at_bottom
