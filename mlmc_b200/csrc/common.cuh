@@ -83,6 +83,37 @@ static __device__ __noinline__ bool legendre_table_finite(double t, int size) {
     return true;
 }
 
+// sin and cos of a moderately sized argument (the Fourier basis maps the domain to [0, 2 pi]): Cody-Waite reduction by
+// pi/2 with a two-part constant (exact for |q| < 2^20) and the fdlibm kernel polynomials on [-pi/4, pi/4]; ~25 FP64
+// instructions instead of the ~70 of the general-range library routine, to which larger arguments fall back.
+// Absolute error < 2e-16.
+__device__ __forceinline__ void sincos_bounded(double t, double* s, double* c) {
+    if (!(fabs(t) < 1.0e5)) {
+        sincos(t, s, c);
+        return;
+    }
+    const double qd = rint(t * 6.36619772367581382433e-01);                 // 2 / pi
+    const int q = (int)qd;
+    double r = fma(-qd, 1.57079632673412561417e+00, t);                     // pi/2, leading 33 bits
+    r = fma(-qd, 6.07710050650619224932e-11, r);                            // pi/2, tail
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sr = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const double sv = (q & 1) ? cr : sr, cv = (q & 1) ? sr : cr;
+    *s = (q & 2) ? -sv : sv;
+    *c = ((q + 1) & 2) ? -cv : cv;
+}
+
 // Does the moment vector of the mapped value t contain no NaN?  (mask_nan_samples,
 // mlmc/quantity/quantity_estimate.py:6-14, applied to Moments.eval_all of this value.)
 __device__ __forceinline__ bool moments_finite(const mlmcb200_basis_t& b, double t) {

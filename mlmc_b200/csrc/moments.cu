@@ -403,8 +403,8 @@ moments_acc_kernel(const MomentsArgs a) {
                 cfk[s] = cck[s] = ok[s] ? 1.0 : 0.0;
                 cf1[s] = sf1[s] = cc1[s] = sc1[s] = 0.0;
                 if (ok[s] && R > 1) {
-                    sincos(tf[s], &sf1[s], &cf1[s]);
-                    if (COARSE) sincos(tc[s], &sc1[s], &cc1[s]);
+                    sincos_bounded(tf[s], &sf1[s], &cf1[s]);
+                    if (COARSE) sincos_bounded(tc[s], &sc1[s], &cc1[s]);
                 }
             }
             MB_ACC(0, cfk, cck);
@@ -557,24 +557,45 @@ __global__ void resample_indices_kernel(uint64_t seed, uint64_t stream_id, int64
     }
 }
 
+// GROUP threads per sample (a warp, or a whole 256-thread CTA for wide quantities so that even a level of a few
+// hundred samples keeps enough loads in flight); threads stride over the components of both sides, kUnroll independent
+// loads in flight per thread (a plain loop keeps ONE load in flight and is latency-bound: 1.7 ms vs 0.3 ms at cfg5).
+template <int GROUP>
 __global__ void sample_mask_kernel(const mlmcb200_basis_t basis, const double* __restrict__ pairs, int64_t n,
                                    int n_comp, int64_t stride_n, int64_t stride_side, int64_t stride_m,
                                    int n_sides, uint8_t* __restrict__ valid) {
-    // one warp per sample; lanes stride over the components of both sides
-    const int64_t sample = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (sample >= n) return;
+    constexpr int kUnroll = 8;
+    const int64_t sample = GROUP == 32 ? ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5 : (int64_t)blockIdx.x;
+    const int lane = GROUP == 32 ? (threadIdx.x & 31) : (int)threadIdx.x;
+    if (sample >= n) return;                         // GROUP == 32: whole warps leave; else never taken
     bool good = true;
     const double* row = pairs + sample * stride_n;
     for (int side = 0; side < n_sides; ++side) {
-        for (int mm = lane; mm < n_comp; mm += 32) {
-            double x = __ldg(row + side * stride_side + (int64_t)mm * stride_m);
-            double t = basis.kind == MLMCB200_RAW ? x : map_to_ref(basis, x);
+        const double* p = row + side * stride_side;
+        int mm = lane;
+        for (; mm + GROUP * (kUnroll - 1) < n_comp; mm += GROUP * kUnroll) {
+            double x[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) x[u] = __ldg(p + (int64_t)(mm + GROUP * u) * stride_m);
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const double t = basis.kind == MLMCB200_RAW ? x[u] : map_to_ref(basis, x[u]);
+                good = good && moments_finite(basis, t);
+            }
+        }
+        for (; mm < n_comp; mm += GROUP) {
+            const double x = __ldg(p + (int64_t)mm * stride_m);
+            const double t = basis.kind == MLMCB200_RAW ? x : map_to_ref(basis, x);
             good = good && moments_finite(basis, t);
         }
     }
-    good = __all_sync(0xffffffffu, good);
-    if (lane == 0) valid[sample] = good ? 1 : 0;
+    if (GROUP == 32) {
+        good = __all_sync(0xffffffffu, good);
+        if (lane == 0) valid[sample] = good ? 1 : 0;
+    } else {
+        const int all = __syncthreads_and(good ? 1 : 0);
+        if (lane == 0) valid[sample] = all ? 1 : 0;
+    }
 }
 
 // blockIdx.y = batch entry (bootstrap replicate): accumulators acc_batch_stride apart, outputs packed per entry as
@@ -675,7 +696,9 @@ int plan_moments(int kind, int size, int n_comp, int64_t n, bool coarse, bool st
     if (ctas_per_sm > 8) ctas_per_sm = 8;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const int gx = n_comp >= kThreads ? (n_comp + kThreads - 1) / kThreads : 1;
-    int gy = (sm_count() * ctas_per_sm + gx - 1) / gx;
+    // gx == 1: one resident wave of sample partitions.  gx > 1 (vector quantity, one CTA column per 128 components):
+    // the launch picks the partition count that fills whole waves (up to 2); this is its upper bound (workspace).
+    int gy = gx == 1 ? sm_count() * ctas_per_sm : (2 * sm_count() * ctas_per_sm) / gx + 1;
     if (n >= 0) {
         const int TN = n_comp >= kThreads ? 1 : kThreads / n_comp;
         const int64_t tiles = (n + (int64_t)p->S * TN - 1) / ((int64_t)p->S * TN);
@@ -686,19 +709,20 @@ int plan_moments(int kind, int size, int n_comp, int64_t n, bool coarse, bool st
     return 0;
 }
 
-// Replicates (grid.z) x sample partitions (grid.y) of a re-sampled launch: the number of partitions per replicate is
-// chosen so that the CTAs fill whole resident waves (a 1.01-wave grid would run at half speed).
+// Sample partitions (grid.y) of a launch with `columns` CTA columns (component blocks x bootstrap replicates): chosen so
+// that columns x partitions fills whole resident waves of `slots` CTAs -- a 1.07-wave grid runs at half speed.
 constexpr unsigned kMaxWavesResampled = 16;
-unsigned partitions_per_replicate(unsigned wave, unsigned n_rep, int64_t tiles) {
+constexpr unsigned kMaxWavesVector = 2;
+unsigned choose_partitions(unsigned slots, unsigned columns, int64_t tiles, unsigned max_waves) {
     unsigned best = 1;
     double best_eff = 0.0;
-    for (unsigned m = 1; m <= kMaxWavesResampled; ++m) {
-        unsigned gy = (unsigned)(((uint64_t)m * wave) / n_rep);
+    for (unsigned m = 1; m <= max_waves; ++m) {
+        unsigned gy = (unsigned)(((uint64_t)m * slots) / columns);
         if (gy < 1) gy = 1;
         if ((int64_t)gy * 4 > tiles && gy > 1) break;            // keep at least 4 tiles per CTA
-        const uint64_t ctas = (uint64_t)gy * n_rep;
-        const double eff = (double)ctas / (double)(((ctas + wave - 1) / wave) * wave);
-        if (eff > best_eff + 1e-9) {
+        const uint64_t ctas = (uint64_t)gy * columns;
+        const double eff = (double)ctas / (double)(((ctas + slots - 1) / slots) * slots);
+        if (eff > best_eff + 0.02) {                              // a further wave must pay for its CTA start-up cost
             best_eff = eff;
             best = gy;
         }
@@ -722,13 +746,16 @@ int launch_moments(const MomentsArgs& a, Plan p, cudaStream_t st) {
         cached_ctas = ctas > 0 ? ctas : 1;
         cached_smem = p.smem;
     }
-    const unsigned wave = (unsigned)((sm_count() * cached_ctas + p.grid.x - 1) / p.grid.x);
+    const unsigned slots = (unsigned)(sm_count() * cached_ctas);
+    const int TN = a.n_comp >= kThreads ? 1 : kThreads / a.n_comp;
+    const int64_t tiles = (a.n + (int64_t)S * TN - 1) / ((int64_t)S * TN);
     if (p.grid.z > 1) {
-        const int TN = a.n_comp >= kThreads ? 1 : kThreads / a.n_comp;
-        const int64_t tiles = (a.n + (int64_t)S * TN - 1) / ((int64_t)S * TN);
-        p.grid.y = partitions_per_replicate(wave, p.grid.z, tiles);
-    } else if (p.grid.y > wave) {
-        p.grid.y = wave;
+        p.grid.y = choose_partitions(slots, p.grid.x * p.grid.z, tiles, kMaxWavesResampled);
+    } else if (p.grid.x > 1) {
+        const unsigned gy = choose_partitions(slots, p.grid.x, tiles, kMaxWavesVector);
+        if (gy < p.grid.y) p.grid.y = gy;
+    } else if (p.grid.y > slots) {
+        p.grid.y = slots;
     }
     kern<<<p.grid, kThreads, p.smem, st>>>(a);
     MB_CUDA_OK(cudaGetLastError());
@@ -917,9 +944,14 @@ extern "C" int mlmcb200_sample_mask(const mlmcb200_basis_t* basis, const double*
     MB_REQUIRE(n >= 0 && n_comp >= 1 && valid != nullptr, "sample_mask: bad arguments");
     if (n == 0) return 0;
     const int threads = 256;
-    const int64_t blocks = (n * 32 + threads - 1) / threads;
-    sample_mask_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-        *basis, pairs, n, n_comp, stride_n, stride_side, stride_m, has_coarse ? 2 : 1, valid);
+    if (n_comp >= 2048 && n <= 0x7fffffffLL) {
+        sample_mask_kernel<256><<<(unsigned)n, threads, 0, (cudaStream_t)stream>>>(
+            *basis, pairs, n, n_comp, stride_n, stride_side, stride_m, has_coarse ? 2 : 1, valid);
+    } else {
+        const int64_t blocks = (n * 32 + threads - 1) / threads;
+        sample_mask_kernel<32><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+            *basis, pairs, n, n_comp, stride_n, stride_side, stride_m, has_coarse ? 2 : 1, valid);
+    }
     MB_CUDA_OK(cudaGetLastError());
     return 0;
 }

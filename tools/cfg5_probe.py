@@ -41,3 +41,26 @@ ts = []
 for _ in range(8):
     t0 = time.perf_counter(); qm = qe.estimate_mean(qe.moments(field, fn)); torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
 print("gc disabled           :", [round(t, 2) for t in ts])
+
+# kernel-level breakdown (CUDA events around each launch group)
+from mlmc_b200 import _native as nat
+dev = torch.device("cuda:0")
+basis = fn.basis_struct()
+rows_dev = [torch.from_numpy(lv).to(dev) for lv in levels]
+acc = nat.LevelAccumulator(5, M * 32, dev)
+def ev():
+    return torch.cuda.Event(enable_timing=True)
+for rep in range(2):
+    t_mask = t_acc = 0.0
+    for l, rows in enumerate(rows_dev):
+        x = rows.permute(2, 0, 1)
+        if l == 0:
+            x = x[:, :, :1]
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record(); valid = nat.sample_mask(basis, x); e1.record()
+        nat.moments_accumulate(basis, x, acc.level(l), valid=valid); e2.record()
+        torch.cuda.synchronize()
+        t_mask += e0.elapsed_time(e1); t_acc += e1.elapsed_time(e2)
+    e0, e1 = ev(), ev()
+    e0.record(); out = acc.finalize(); e1.record(); torch.cuda.synchronize()
+    print("sample_mask %.3f ms, moments kernels %.3f ms, finalize %.3f ms" % (t_mask, t_acc, e0.elapsed_time(e1)))
