@@ -215,7 +215,7 @@ if want("cfg5"):
     t_gpu, qm = timed(lambda: qe.estimate_mean(qe.moments(field, fn)), reps=3)
     storage.resident_fraction = 0.0
     storage.drop_device_copies()
-    t_host, _ = timed(lambda: qe.estimate_mean(qe.moments(field, fn)), reps=2)
+    t_host, _ = timed(lambda: qe.estimate_mean(qe.moments(field, fn)), reps=5)
     n_loc = 50
     # oracle on the first 50 locations, with the sample mask of ALL locations (a sample is dropped if any of the
     # 1e4 locations leaves the domain): remove those samples from the slice first
