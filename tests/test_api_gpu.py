@@ -405,3 +405,33 @@ def test_bases_beyond_the_fused_kernel_limits(golden):
     wc = orc.estimate_covariance(levels, orc.Basis("legendre", 120, domain))
     rel_close(np.ravel(cm.mean), wc.mean, rtol=1e-8, atol_scale=1e-13)
     rel_close(np.ravel(cm.var), wc.var, rtol=1e-8, atol_scale=1e-13)
+
+
+def test_fused_bootstrap_streamed_chunks(golden):
+    """A level that arrives in several device chunks: hypergeometric split of the draws over the chunks
+    (quantity.py:317), ragged draws per replicate -- every replicate still equals the oracle on its own rows."""
+    from mlmc_b200.moments import Legendre
+    from mlmc_b200.quantity import quantity_estimate as qe
+    g = golden("estimates")
+    levels = [g["A_rows%d" % l] for l in range(3)]
+    storage, value = scalar_setup(levels, [[h] for h in g["A_steps"]], g["A_n_ops"])
+    storage.resident_fraction = 0.0            # stream from the host ...
+    storage.device_chunk_bytes = 16 * 700      # ... 700 rows at a time
+    domain = tuple(g["A_domain"])
+    fn = Legendre(6, domain)
+    sample_vec = [900, 400, 150]
+    out = qe.bootstrap_moments(value, fn, sample_vec, 5, seed=2, return_indices=True)
+    basis = orc.Basis("legendre", 6, domain)
+    n_chunks = [len({off for off, _, _ in out["indices"][l]}) for l in range(3)]
+    assert max(n_chunks) > 1
+    for b in range(5):
+        picked = []
+        for l in range(3):
+            parts = [levels[l][off + idx[b - b0].cpu().numpy()] for off, b0, idx in out["indices"][l]
+                     if b0 <= b < b0 + idx.shape[0]]
+            picked.append(np.concatenate(parts))
+            assert len(picked[-1]) == sample_vec[l]
+        want = orc.estimate_moments(picked, basis)
+        assert list(out["n_samples"][b]) == list(want.n_samples)
+        rel_close(out["l_means"][b], want.l_means, rtol=1e-10, atol_scale=1e-14)
+        rel_close(out["l_vars"][b], want.l_vars, rtol=1e-10, atol_scale=1e-13)
