@@ -147,6 +147,18 @@ int mlmcb200_finalize_levels_batched(const double* acc, int64_t acc_stride, int3
                                      int32_t n_batch, int64_t acc_batch_stride, double* out, void* stream);
 
 /*
+ * Order statistics for Estimate.estimate_domain (mlmc/estimator.py:275-302): the reference takes
+ * np.percentile(fine, [100 q, 100 (1 - q)]) of a level's fine samples.  For every fraction f in frac[0..n_frac)
+ * (host array, values in [0, 1]) this finds, among the non-NaN entries x[i * stride], i < n (device), the two
+ * neighbouring order statistics numpy interpolates between: with pos = f * (n_valid - 1),
+ *     out[2 k] = sorted[floor(pos)],  out[2 k + 1] = sorted[min(floor(pos) + 1, n_valid - 1)],  out[2 n_frac] = n_valid
+ * (device, doubles).  Exact radix selection on the 64-bit keys (six histogram passes), no sort and no copy of x.
+ */
+int64_t mlmcb200_percentile_workspace_bytes(int32_t n_frac);
+int mlmcb200_percentile_stats(const double* x, int64_t n, int64_t stride, const double* frac, int32_t n_frac,
+                              double* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * Max-entropy functional pieces on a fixed node set (mlmc/tool/simple_distribution.py:254-327):
  *     rho_q = exp(clip(-phi_q . lam_scaled, -200, 200)),   lam_scaled = lambda / sigma
  *     out[0]               = sum_q w_q rho_q                       (integral term of _calculate_functional)

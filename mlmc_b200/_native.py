@@ -50,6 +50,9 @@ _SIGNATURES = {
                                                 _c_vp]),
     "mlmcb200_finalize_levels_batched": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i64, _c_i32, _c_i64, _c_vp,
                                                         _c_vp]),
+    "mlmcb200_percentile_workspace_bytes": (_c_i64, [_c_i32]),
+    "mlmcb200_percentile_stats": (ctypes.c_int, [_c_vp, _c_i64, _c_i64, ctypes.POINTER(_c_dbl), _c_i32, _c_vp, _c_vp,
+                                                 _c_i64, _c_vp]),
     "mlmcb200_maxent_workspace_bytes": (_c_i64, [_c_i64, _c_i32]),
     "mlmcb200_maxent_fgh": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp, _c_vp,
                                            _c_i64, _c_vp]),
@@ -314,6 +317,31 @@ def finalize_levels_batched(acc):
                                                        _stream()), "finalize_levels_batched")
     launch_count += 1
     return out
+
+
+def percentile_stats(values, fracs):
+    """Neighbouring order statistics of a CUDA float64 vector (any stride) for ``np.percentile``-style fractions.
+
+    Returns (stats [len(fracs), 2] NumPy, n_valid): ``stats[k] = sorted[floor(pos)], sorted[floor(pos) + 1]`` with
+    ``pos = fracs[k] * (n_valid - 1)`` over the non-NaN entries -- exact values, found by radix selection."""
+    global launch_count
+    _require_cuda(values, "values")
+    if values.dim() != 1 or values.numel() == 0:
+        raise NativeError("percentile_stats needs a non-empty 1-D tensor")
+    fracs = [float(f) for f in fracs]
+    lib = load()
+    arr = (_c_dbl * len(fracs))(*fracs)
+    out = torch.empty(2 * len(fracs) + 1, dtype=torch.float64, device=values.device)
+    with _on_device(values.device):
+        ws_bytes = lib.mlmcb200_percentile_workspace_bytes(len(fracs))
+        if ws_bytes < 0:
+            raise NativeError("percentile_stats: at most 8 fractions per call")
+        ws = _workspace(values.device, ws_bytes)
+        _check(lib.mlmcb200_percentile_stats(_ptr(values), values.numel(), values.stride(0), arr, len(fracs),
+                                             _ptr(out), _ptr(ws), ws.numel(), _stream()), "percentile_stats")
+    launch_count += 12
+    host = out.cpu().numpy()
+    return host[:-1].reshape(len(fracs), 2), int(host[-1])
 
 
 def gram_accumulate(basis, x, acc_row, mode=0, want_var=True):

@@ -141,7 +141,6 @@ class Estimate:
             chunk_spec = next(sample_storage.chunks(n_samples=int(n_collected[level_id])))
             storage_q = quantity.get_quantity_storage()
             fine = quantity.device_samples(storage_q.device_chunk(chunk_spec))[..., 0].reshape(-1)
-            fine = fine[~torch.isnan(fine)]
             ranges.append(_percentiles(fine, [100 * quantile, 100 * (1 - quantile)]))
         ranges = np.array(ranges)
         return np.min(ranges[:, 0]), np.max(ranges[:, 1])
@@ -171,19 +170,22 @@ class Estimate:
 
 
 def _percentiles(values, percents):
-    """``np.percentile(values, percents)`` (default linear interpolation) of a CUDA vector: device sort, then
-    numpy's own index arithmetic and lerp on the two neighbouring order statistics (bit-identical result)."""
-    ordered, _ = torch.sort(values)
-    n = ordered.numel()
+    """``np.percentile(values, percents)`` (default linear interpolation) of a CUDA vector, NaN entries ignored: the
+    two neighbouring order statistics of every percentile come from the device (exact radix selection,
+    ``mlmcb200_percentile_stats``), then numpy's own lerp (``_lerp`` in numpy/lib/_function_base_impl.py) on the
+    host -- the result is bit-identical to ``np.percentile`` of the non-NaN values."""
+    from . import _native
+    fracs = np.true_divide(np.asarray(percents, dtype=float), 100)
+    stats, n = _native.percentile_stats(values, fracs)
+    if n == 0:
+        raise Exception("All samples were masked")
     out = []
-    for frac in np.true_divide(np.asarray(percents, dtype=float), 100):
-        pos = frac * (n - 1)
-        lo = int(np.floor(pos))
-        hi = min(lo + 1, n - 1)
-        a, b = (float(v) for v in ordered[[lo, hi]].cpu())
-        t = pos - lo
-        diff = b - a
-        out.append(b - diff * (1 - t) if t >= 0.5 else a + diff * t)
+    with np.errstate(invalid="ignore"):                  # infinite order statistics give NaN, as in numpy
+        for frac, (a, b) in zip(fracs, stats):
+            pos = frac * (n - 1)
+            t = pos - np.floor(pos)
+            diff = b - a
+            out.append(b - diff * (1 - t) if t >= 0.5 else a + diff * t)
     return np.array(out)
 
 

@@ -550,3 +550,45 @@ def test_resample_indices_blocks_and_uniformity():
         block_of = np.searchsorted(edges, blk[r], side="right") - 1
         assert np.all(np.diff(block_of) >= 0)                          # listed in block order
         assert np.array_equal(np.bincount(block_of, minlength=P), counts[r])
+
+
+# ------------------------------------------------------------------------------------------------------
+# order statistics for estimate_domain (estimator.py:299: np.percentile of the fine samples)
+@pytest.mark.parametrize("case", ["normal", "dups", "tiny1", "tiny2", "tiny3", "signed_zero_inf", "strided", "big"])
+def test_percentile_stats_equal_numpy(case):
+    from mlmc_b200.estimator import _percentiles
+    nat = native()
+    rng = np.random.default_rng(11)
+    stride = 1
+    if case == "normal":
+        x = rng.normal(size=100_003)
+        x[rng.integers(0, x.size, 500)] = np.nan
+    elif case == "dups":
+        x = rng.integers(-5, 6, size=50_000).astype(float)
+    elif case.startswith("tiny"):
+        x = rng.normal(size=int(case[-1]))
+    elif case == "signed_zero_inf":
+        x = np.concatenate([rng.normal(size=1000), [0.0, -0.0, np.inf, -np.inf, 1e-310, -1e-310, np.nan]])
+    elif case == "strided":
+        x = rng.lognormal(size=(20_000, 3))
+        stride = 3
+    else:
+        x = rng.standard_cauchy(size=3_000_000)
+    t = torch.from_numpy(x).to(dev())
+    values = t[:, 1] if stride == 3 else t
+    host = x[:, 1] if stride == 3 else x
+    host = host[~np.isnan(host)]
+    fracs = [0.0, 0.001, 0.01, 0.25, 0.5, 0.99, 0.9999, 1.0]
+    stats, n = nat.percentile_stats(values, fracs)
+    assert n == host.size
+    srt = np.sort(host)
+    for f, (a, b) in zip(fracs, stats):
+        pos = f * (n - 1)
+        lo = int(np.floor(pos))
+        hi = min(lo + 1, n - 1)
+        assert a == srt[lo] and b == srt[hi], (case, f, a, srt[lo], b, srt[hi])
+    percents = [100 * f for f in fracs]
+    with np.errstate(invalid="ignore"):
+        want = np.percentile(host, percents)
+    got = _percentiles(values, percents)
+    assert np.array_equal(got, want, equal_nan=True), (case, got, want)
