@@ -327,6 +327,25 @@ def run_gpu_arm(args):
     e2e_value = units_per_rank * world / (float(e2e_s.item()) / e2e_steps)
     clocks = sampler.stop() if rank == 0 else None
 
+    # What bounds e2e: the pinned host -> device copy of the step's inputs, measured with ALL ranks copying at once
+    # (the ranks of one box share PCIe switches and host memory).  Slowest rank's rate, like the e2e time.
+    from mlmc_b200.sample_storage import stream_levels
+    segments = [(l, storage._host_tensor(l)) for l in range(N_LEVELS)]
+    h2d_ms = []
+    for rep in range(3):
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        t0 = time.perf_counter()
+        for _level, _rows in stream_levels(segments, device, storage.device_chunk_bytes):
+            pass                                   # the same double-buffered chunk copies, no kernels
+        torch.cuda.synchronize()
+        h2d_ms.append((time.perf_counter() - t0) * 1e3)
+    h2d_t = torch.tensor([min(h2d_ms[1:])], dtype=torch.float64, device=device)
+    if world > 1:
+        td.all_reduce(h2d_t, op=td.ReduceOp.MAX)
+    h2d_gbs_slowest = bytes_per_rank / (float(h2d_t.item()) * 1e-3) / 1e9
+
     if rank != 0:
         if world > 1:
             td.barrier()
@@ -383,7 +402,11 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(bytes_per_rank * world),
                     "d2h_bytes_per_step": int(d2h_bytes * world), "steps": e2e_steps,
                     "api": "Estimate.estimate_diff_vars_regression + estimate_n_samples_for_target_variance on a "
-                           "pinned-host Memory storage"},
+                           "pinned-host Memory storage",
+                    "ms_per_step": float(e2e_s.item()) / e2e_steps * 1e3,
+                    "h2d_only_ms": float(h2d_t.item()),
+                    "h2d_gbs_per_gpu_all_ranks_copying": h2d_gbs_slowest,
+                    "bound": "PCIe / host memory: the bare pinned copy of the same bytes, all ranks at once"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "n_estimated": [int(v) for v in n_estimated], "n_estimated_e2e": [int(v) for v in n_est_e2e],
