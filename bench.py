@@ -219,10 +219,33 @@ def run_gpu_arm(args):
         views.append(rows.permute(2, 0, 1))
     result = {}
 
+    # the levels are independent until the finalize: each runs on its own stream (a fork / join inside the graph), so
+    # the ramp and tail of one level's one-wave launch overlap the next level's kernel
+    level_streams = [torch.cuda.Stream(device) for _ in range(N_LEVELS - 1)]
+    concurrent_levels = os.environ.get("BENCH_CONCURRENT_LEVELS", "1") != "0"
+
     def enqueue_step():
         acc.acc.zero_()
-        for l in range(N_LEVELS):
-            nat.moments_accumulate(basis, views[l], acc.level(l))
+        main = torch.cuda.current_stream()
+        if not concurrent_levels:
+            for l in range(N_LEVELS):
+                nat.moments_accumulate(basis, views[l], acc.level(l))
+        else:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            joins = []
+            for l in range(N_LEVELS):
+                st = main if l == 0 else level_streams[l - 1]
+                if st is not main:
+                    st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    nat.moments_accumulate(basis, views[l], acc.level(l))
+                    if st is not main:
+                        ev = torch.cuda.Event()
+                        ev.record(st)
+                        joins.append(ev)
+            for ev in joins:
+                main.wait_event(ev)
         if world > 1:
             td.all_reduce(acc.acc)
         result.update(acc.finalize())

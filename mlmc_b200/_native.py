@@ -178,7 +178,9 @@ _workspaces = {}
 
 
 def _workspace(device, n_bytes):
-    key = (device.type, device.index)
+    """Scratch buffer of the launching stream (partial sums): launches on one stream are ordered, launches on
+    different streams (levels running concurrently) must not share it."""
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < n_bytes:
         ws = torch.empty(max(int(n_bytes), 1 << 20), dtype=torch.uint8, device=device)
