@@ -183,6 +183,8 @@ def _workspace(device, n_bytes):
     key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < n_bytes:
+        if len(_workspaces) >= 32:                      # many short-lived streams: do not hoard their buffers
+            _workspaces.clear()
         ws = torch.empty(max(int(n_bytes), 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
