@@ -435,3 +435,31 @@ def test_fused_bootstrap_streamed_chunks(golden):
         assert list(out["n_samples"][b]) == list(want.n_samples)
         rel_close(out["l_means"][b], want.l_means, rtol=1e-10, atol_scale=1e-14)
         rel_close(out["l_vars"][b], want.l_vars, rtol=1e-10, atol_scale=1e-13)
+
+
+@pytest.mark.parametrize("r_base", [12, 25])
+def test_construct_density_equals_oracle_pipeline(r_base):
+    """The whole data-driven chain (covariance pass -> orthogonalisation -> moments of the orthogonal basis from the
+    level sums -> max-ent fit) against the same chain in the oracle, on the same samples: PDF values within 1e-6
+    (north_star), in practice 1e-14."""
+    from mlmc_b200.moments import Legendre
+    from mlmc_b200.estimator import Estimate
+    rng = np.random.default_rng(42)
+    steps = orc.level_steps(3, (0.5, 0.005))
+    levels = [orc.synth_level_rows(rng.normal(size=n), steps[l], steps[l - 1] if l else None)
+              for l, n in enumerate([200000, 20000, 2000])]
+    storage, value = scalar_setup(levels, [[h] for h in steps])
+    domain = tuple(stats.norm.ppf([0.001, 0.999]))
+    est = Estimate(value, storage, Legendre(r_base, domain))
+    distr_obj, info, result, moments_obj = est.construct_density(tol=1e-8, orth_moments_tol=1e-4)
+    b = orc.Basis("legendre", r_base, domain)
+    oc = orc.estimate_covariance(levels, b)
+    l_mat, _, _ = orc.orthogonalize_moments(oc.mean.reshape(r_base, r_base), 1e-4)
+    assert l_mat.shape[0] == moments_obj.size
+    ob = orc.Basis("legendre", r_base, domain, matrix=l_mat)
+    om = orc.estimate_moments(levels, ob)
+    data = np.stack([om.mean, np.ones_like(om.mean)], axis=1)
+    ofit = orc.maxent_fit(ob, data, domain, tol=1e-8, n_panels=distr_obj._n_panels)
+    xs = np.linspace(domain[0], domain[1], 201)
+    want = orc.maxent_density(ob, ofit.multipliers, np.ones(len(om.mean)), xs)
+    assert np.max(np.abs(distr_obj.density(xs) - want)) < 1e-6 * max(1.0, np.max(want))

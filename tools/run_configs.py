@@ -195,6 +195,30 @@ if want("cfg4"):
                        np.ones(len(mu)), xs)), "max_abs_pdf_err_vs_truncated_normal": pdf_err}
     print("cfg4", out["cfg4"], flush=True)
 
+# ------------------------------------------------------------------------------------------------ cfg4 (data-driven)
+if want("cfg4"):
+    # Estimate.construct_density on cfg2-shaped samples: covariance pass (DMMA) -> orthogonalisation -> moments of
+    # the orthogonal basis from the level sums -> max-ent fit; the whole call, levels resident in HBM
+    n = 10_000_000
+    steps = orc.level_steps(3, (0.5, 0.005))
+    levels = [synth_device(n, steps[l], steps[l - 1] if l else None, 1234 + 1000 * l).cpu() for l in range(3)]
+    storage, value = scalar_quantity(levels, steps, [orc.synth_n_ops(h) for h in steps])
+    dom = tuple(stats.norm.ppf([0.001, 0.999]))
+    xs = np.linspace(dom[0], dom[1], 201)
+    inner = slice(10, -10)                                  # the fit has a boundary layer in the outer 5 % of the domain
+    out["cfg4_data_driven"] = {"samples": 3 * n}
+    for r_base in (12, 25):
+        est = Estimate(value, storage, Legendre(r_base, dom))
+        t_cd, (dobj, info_d, res_d, mom_d) = timed(lambda: est.construct_density(tol=1e-8, orth_moments_tol=1e-4),
+                                                   reps=3)
+        err = np.abs(dobj.density(xs) - stats.norm.pdf(xs))
+        out["cfg4_data_driven"]["legendre_%d" % r_base] = {
+            "construct_density_ms": t_cd * 1e3, "orthogonal_moments": int(mom_d.size), "success": bool(res_d.success),
+            "fun_norm": float(res_d.fun_norm), "nit": int(res_d.nit),
+            "max_abs_pdf_err_vs_normal_interior": float(np.max(err[inner])), "max_abs_pdf_err_vs_normal": float(np.max(err))}
+    print("cfg4_data_driven", out["cfg4_data_driven"], flush=True)
+    del levels, storage, value, est
+
 # ------------------------------------------------------------------------------------------------ cfg5
 if want("cfg5"):
     M = 10_000
