@@ -121,7 +121,10 @@ moments_acc_kernel(const MomentsArgs a) {
     // thread -> (component, sample lane)
     int m, tn, TN;
     bool active;
-    if (M >= T) {
+    // more than T/2 components: one thread per component (a single sample lane per CTA either way; the epilogue then
+    // writes each thread's own columns instead of reducing K outputs over one lane)
+    const bool by_comp = 2 * M > T;
+    if (by_comp) {
         m = blockIdx.x * T + tid;
         tn = 0;
         TN = 1;
@@ -136,7 +139,7 @@ moments_acc_kernel(const MomentsArgs a) {
     const int64_t n_tiles = (a.n + tile_n - 1) / tile_n;
     const double* const base_f = a.pairs + (int64_t)m * a.stride_m;
     const int32_t* const idx = (GATHER || (!FAST && a.idx != nullptr)) ? a.idx + (int64_t)blockIdx.z * a.n : nullptr;
-    const bool count_here = (blockIdx.x == 0) && (M >= T ? tid == 0 : m == 0);
+    const bool count_here = (blockIdx.x == 0) && (by_comp ? tid == 0 : m == 0);
     unsigned cnt_ok = 0, cnt_rm = 0;
 
     // the moment index is kept out of the vector address arithmetic (column pointer + constant steps) so that the loop
@@ -438,7 +441,7 @@ moments_acc_kernel(const MomentsArgs a) {
     __syncthreads();
     double* const out = a.partial + ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * a.partial_stride;
     const int64_t K = (int64_t)M * R;
-    if (M >= T) {
+    if (by_comp) {
         if (active) {
             for (int r = 0; r < R; ++r) {
                 const double al = (KIND == MLMCB200_LEGENDRE) ? kLegAlpha[r] : 1.0;
@@ -557,44 +560,55 @@ __global__ void resample_indices_kernel(uint64_t seed, uint64_t stream_id, int64
     }
 }
 
-// GROUP threads per sample (a warp, or a whole 256-thread CTA for wide quantities so that even a level of a few
-// hundred samples keeps enough loads in flight); threads stride over the components of both sides, kUnroll independent
-// loads in flight per thread (a plain loop keeps ONE load in flight and is latency-bound: 1.7 ms vs 0.3 ms at cfg5).
-template <int GROUP>
+// valid[] starts at 1; every (sample, side, component) value is visited once, flat and coalesced, 8 independent loads
+// in flight per thread, and a value outside the domain clears its sample's flag (all writers store the same 0: no
+// atomics, no per-sample reduction).  HBM-bound for any number of components.
+// IDX: uint32_t when the number of values fits (one 32-bit division per value; a 64-bit division costs ~100 instructions
+// and made the pass compute-bound), uint64_t otherwise.
+template <typename IDX>
 __global__ void sample_mask_kernel(const mlmcb200_basis_t basis, const double* __restrict__ pairs, int64_t n,
                                    int n_comp, int64_t stride_n, int64_t stride_side, int64_t stride_m,
                                    int n_sides, uint8_t* __restrict__ valid) {
     constexpr int kUnroll = 8;
-    const int64_t sample = GROUP == 32 ? ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5 : (int64_t)blockIdx.x;
-    const int lane = GROUP == 32 ? (threadIdx.x & 31) : (int)threadIdx.x;
-    if (sample >= n) return;                         // GROUP == 32: whole warps leave; else never taken
-    bool good = true;
-    const double* row = pairs + sample * stride_n;
-    for (int side = 0; side < n_sides; ++side) {
-        const double* p = row + side * stride_side;
-        int mm = lane;
-        for (; mm + GROUP * (kUnroll - 1) < n_comp; mm += GROUP * kUnroll) {
-            double x[kUnroll];
+    const int64_t per = (int64_t)n_sides * n_comp, total = n * per;
+    const IDX per_i = (IDX)per;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x * kUnroll;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x * kUnroll + threadIdx.x; base < total; base += step) {
+        double x[kUnroll];
+        int64_t smp[kUnroll];
+        // (sample, offset in the sample) of the first value by ONE division, of the following ones incrementally
+        IDX si = (IDX)base / per_i;
+        uint32_t r = (uint32_t)((IDX)base - si * per_i);
+        int64_t s = (int64_t)si;
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) x[u] = __ldg(p + (int64_t)(mm + GROUP * u) * stride_m);
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const double t = basis.kind == MLMCB200_RAW ? x[u] : map_to_ref(basis, x[u]);
-                good = good && moments_finite(basis, t);
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t e = base + (int64_t)u * blockDim.x;
+            smp[u] = -1;
+            x[u] = 0.0;
+            if (e < total) {
+                const int side = r >= (uint32_t)n_comp ? 1 : 0, mm = (int)r - side * n_comp;      // n_sides <= 2
+                smp[u] = s;
+                x[u] = __ldg(pairs + s * stride_n + side * stride_side + (int64_t)mm * stride_m);
+            }
+            r += blockDim.x;
+            if (r >= (uint32_t)per) {
+                if (per >= (int64_t)blockDim.x) {
+                    r -= (uint32_t)per;
+                    ++s;
+                } else {
+                    const uint32_t q = r / (uint32_t)per;
+                    r -= q * (uint32_t)per;
+                    s += q;
+                }
             }
         }
-        for (; mm < n_comp; mm += GROUP) {
-            const double x = __ldg(p + (int64_t)mm * stride_m);
-            const double t = basis.kind == MLMCB200_RAW ? x : map_to_ref(basis, x);
-            good = good && moments_finite(basis, t);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (smp[u] >= 0) {
+                const double t = basis.kind == MLMCB200_RAW ? x[u] : map_to_ref(basis, x[u]);
+                if (!moments_finite(basis, t)) valid[smp[u]] = 0;
+            }
         }
-    }
-    if (GROUP == 32) {
-        good = __all_sync(0xffffffffu, good);
-        if (lane == 0) valid[sample] = good ? 1 : 0;
-    } else {
-        const int all = __syncthreads_and(good ? 1 : 0);
-        if (lane == 0) valid[sample] = all ? 1 : 0;
     }
 }
 
@@ -944,14 +958,18 @@ extern "C" int mlmcb200_sample_mask(const mlmcb200_basis_t* basis, const double*
     MB_REQUIRE(n >= 0 && n_comp >= 1 && valid != nullptr, "sample_mask: bad arguments");
     if (n == 0) return 0;
     const int threads = 256;
-    if (n_comp >= 2048 && n <= 0x7fffffffLL) {
-        sample_mask_kernel<256><<<(unsigned)n, threads, 0, (cudaStream_t)stream>>>(
+    cudaStream_t st = (cudaStream_t)stream;
+    MB_CUDA_OK(cudaMemsetAsync(valid, 1, (size_t)n, st));
+    const int64_t total = n * (int64_t)n_comp * (has_coarse ? 2 : 1);
+    int64_t blocks = (total + threads * 8 - 1) / (threads * 8);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (total < 0xffffffffLL)
+        sample_mask_kernel<uint32_t><<<(unsigned)blocks, threads, 0, st>>>(
             *basis, pairs, n, n_comp, stride_n, stride_side, stride_m, has_coarse ? 2 : 1, valid);
-    } else {
-        const int64_t blocks = (n * 32 + threads - 1) / threads;
-        sample_mask_kernel<32><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+    else
+        sample_mask_kernel<uint64_t><<<(unsigned)blocks, threads, 0, st>>>(
             *basis, pairs, n, n_comp, stride_n, stride_side, stride_m, has_coarse ? 2 : 1, valid);
-    }
     MB_CUDA_OK(cudaGetLastError());
     return 0;
 }
