@@ -263,30 +263,36 @@ def bootstrap_moments(quantity, moments_fn, sample_vector, n_subsamples, seed=No
     level_ids = storage_q.level_ids()
     n_levels = int(np.max(level_ids)) + 1
     device = q_mod._device()
-    if _dist.world_size() > 1 and not getattr(storage, "rows_are_local_shard", False):
-        raise NotImplementedError("bootstrap over row shards: run it on one rank (replicates are independent)")
     basis = moments_fn.basis_struct()
     n_collected = [int(n) for n in storage.get_n_collected()]
-    B = int(n_subsamples)
+    # Multi-GPU: replicates are independent units -> rank r computes the replicates [r B / P, (r + 1) B / P) on the whole
+    # levels and one all-gather of the small per-replicate results follows (no data-path collective).  Needs the same
+    # seed on every rank.  (A storage of rank-local shards is bootstrapped locally, rank by rank.)
+    n_total = int(n_subsamples)
+    shard_replicates = _dist.world_size() > 1 and not getattr(storage, "rows_are_local_shard", False)
+    if shard_replicates and seed is None:
+        raise ValueError("multi-GPU bootstrap: pass the same `seed` on every rank")
+    b_lo, b_hi = _dist.shard_range(n_total) if shard_replicates else (0, n_total)
+    B = b_hi - b_lo
     seed = int(seed) if seed is not None else int(np.random.SeedSequence().entropy % (1 << 62))
-    host_rng = np.random.default_rng(seed)
+    host_rng = np.random.default_rng([seed, b_lo])
+    seed_dev = seed + b_lo                                          # replicate b draws with key (seed + b, ...)
 
-    acc = None
-    width = None
+    width = 2 + 2 * quantity.size() * basis.size
+    acc = torch.zeros((B, n_levels, width), dtype=torch.float64, device=device)
+    seen_rows = False
     remaining = {l: (np.full(B, int(sample_vector[l]), dtype=np.int64), n_collected[l]) for l in level_ids}
     indices = {l: [] for l in level_ids}
     offsets = {l: 0 for l in level_ids}
     chunk_id = 0
     max_draws = 1 << 30                                               # row numbers per launch (4 GB of int32)
-    for level_id, rows in storage.device_chunks(level_ids, device, keep_resident=True):
+    for level_id, rows in (storage.device_chunks(level_ids, device, keep_resident=True) if B > 0 else ()):
         n_chunk = int(rows.shape[0])
         if n_chunk == 0:
             continue
         x = quantity.device_samples(q_mod.DeviceChunk(level_id, rows, chunk_id))
         chunk_id += 1
-        if acc is None:
-            width = 2 + 2 * x.shape[0] * basis.size
-            acc = torch.zeros((B, n_levels, width), dtype=torch.float64, device=device)
+        seen_rows = True
         k_left, n_left = remaining[level_id]
         if n_chunk >= n_left:                                          # last (or only) chunk takes what is left
             sizes = k_left.copy()
@@ -310,7 +316,7 @@ def bootstrap_moments(quantity, moments_fn, sample_vector, n_subsamples, seed=No
                 cum_h = np.zeros((b1 - b0, n_blocks + 1), dtype=np.int64)
                 np.cumsum(counts, axis=1, out=cum_h[:, 1:])
                 cum = torch.from_numpy(cum_h).to(device)
-            return _native.resample_indices(seed + b0, stream_id, n_chunk, k, b1 - b0, device, block_cum=cum)
+            return _native.resample_indices(seed_dev + b0, stream_id, n_chunk, k, b1 - b0, device, block_cum=cum)
 
         if np.all(sizes == sizes[0]):
             k = int(sizes[0])
@@ -321,7 +327,7 @@ def bootstrap_moments(quantity, moments_fn, sample_vector, n_subsamples, seed=No
                     idx = draw(b0, b1, k)
                     _native.moments_accumulate_resampled(basis, x, idx, level_acc[b0:b1], valid=valid)
                     if return_indices:
-                        indices[level_id].append((offsets[level_id], b0, idx))
+                        indices[level_id].append((offsets[level_id], b_lo + b0, idx))
         else:                                                          # ragged draws: one replicate per launch
             for b in range(B):
                 k = int(sizes[b])
@@ -330,14 +336,27 @@ def bootstrap_moments(quantity, moments_fn, sample_vector, n_subsamples, seed=No
                 idx = draw(b, b + 1, k)
                 _native.moments_accumulate_resampled(basis, x, idx, level_acc[b:b + 1], valid=valid)
                 if return_indices:
-                    indices[level_id].append((offsets[level_id], b, idx))
+                    indices[level_id].append((offsets[level_id], b_lo + b, idx))
         offsets[level_id] += n_chunk
-    if acc is None:
+    if B > 0 and not seen_rows:
         raise Exception("All samples were masked")
 
     L, K = n_levels, (width - 2) // 2
-    packed = _native.finalize_levels_batched(acc)
-    host = _to_host(torch.cat([packed, acc[:, :, 0].reshape(B, L)], dim=1).reshape(-1)).reshape(B, -1)
+    packed = torch.cat([_native.finalize_levels_batched(acc), acc[:, :, 0].reshape(B, L)], dim=1) if B > 0 else \
+        torch.empty((0, 2 * L * K + 2 * K + L), dtype=torch.float64, device=device)
+    if shard_replicates:
+        import torch.distributed as td
+        world = _dist.world_size()
+        b_max = -(-n_total // world)                                   # equal-sized pieces for the all-gather
+        piece = torch.zeros((b_max, packed.shape[1]), dtype=torch.float64, device=device)
+        piece[:B] = packed
+        gathered = torch.empty((world * b_max, packed.shape[1]), dtype=torch.float64, device=device)
+        td.all_gather_into_tensor(gathered, piece, group=_dist._state["group"])
+        keep = [r * b_max + i for r in range(world) for i in range(_dist.shard_range(n_total, r, world)[1]
+                                                                  - _dist.shard_range(n_total, r, world)[0])]
+        packed = gathered[torch.tensor(keep, device=device)]
+        B = n_total
+    host = _to_host(packed.reshape(-1)).reshape(B, -1)
     l_means = host[:, :L * K].reshape(B, L, K)
     l_vars = host[:, L * K:2 * L * K].reshape(B, L, K)
     mean, var = host[:, 2 * L * K:2 * L * K + K], host[:, 2 * L * K + K:2 * L * K + 2 * K]

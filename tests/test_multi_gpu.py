@@ -38,8 +38,16 @@ def _worker(rank, world, port, out_dir):
     value = make_root_quantity(storage, spec)["v"][0.0]["0"][0, 0]
     qm = qe.estimate_mean(qe.moments(value, Legendre(12, tuple(g["A_domain"]))))
     cm = qe.estimate_mean(qe.covariance(value, Legendre(8, tuple(g["A_domain"]))))
+    # bootstrap: replicates are sharded over the ranks, every rank ends up with all of them
+    bs = qe.bootstrap_moments(value, Legendre(6, tuple(g["A_domain"])), [800, 400, 200], 5, seed=4)
+    bs1 = None
+    if rank == 0:                                   # the same call on one rank (sharding off) for comparison
+        dist.disable()
+        bs1 = qe.bootstrap_moments(value, Legendre(6, tuple(g["A_domain"])), [800, 400, 200], 5, seed=4)
+        dist.enable(rank, world)
     np.savez(os.path.join(out_dir, "r%d.npz" % rank), l_means=qm.l_means, l_vars=qm.l_vars, n=qm.n_samples,
-             n_rm=qm.n_rm_samples, cov=cm.mean, cov_var=cm.var)
+             n_rm=qm.n_rm_samples, cov=cm.mean, cov_var=cm.var, bs_l_means=bs["l_means"], bs_n=bs["n_samples"],
+             bs1_l_means=bs1["l_means"] if bs1 is not None else np.zeros(0))
     import torch.distributed as td
     td.barrier()
     td.destroy_process_group()
@@ -61,3 +69,9 @@ def test_two_gpu_sharded_estimate(tmp_path, golden):
         assert np.allclose(out["l_vars"], g["A_leg_l_vars"], rtol=1e-10, atol=1e-15)
         assert np.allclose(out["cov"], g["A_cov_mean"], rtol=1e-8, atol=1e-14)
         assert np.allclose(out["cov_var"], g["A_cov_var"], rtol=1e-8, atol=1e-16)
+    a, b = (np.load(os.path.join(str(tmp_path), "r%d.npz" % r)) for r in range(2))
+    assert a["bs_l_means"].shape == (5, 3, 6) and np.array_equal(a["bs_l_means"], b["bs_l_means"])
+    assert np.array_equal(a["bs_n"], b["bs_n"]) and np.all(a["bs_n"].sum(axis=1) > 0)
+    # replicates 0..1 live on rank 0 in both runs (same keys): identical; the rest are valid but differently seeded
+    assert np.array_equal(a["bs_l_means"][:2], a["bs1_l_means"][:2])
+    assert np.all(np.abs(a["bs_l_means"][:, :, 0].sum(axis=1) - 1.0) < 1e-12)
