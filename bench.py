@@ -255,7 +255,13 @@ def run_gpu_arm(args):
         enqueue_step()                                   # warm up allocations outside the capture
         torch.cuda.synchronize()
         graph = None
-        if world == 1:
+        # N > 1: plain stream launches by default; BENCH_GRAPH_MULTI=1 captures the all-reduce with the kernels (NCCL
+        # supports stream capture; measured 0.653 vs 0.659 ms per step at N = 2 -- not worth a capture failure mode)
+        if world == 1 or os.environ.get("BENCH_GRAPH_MULTI", "0") == "1":
+            if world > 1:
+                enqueue_step()                           # a second eager step: NCCL sets up its channels lazily
+                torch.cuda.synchronize()
+                td.barrier()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
                 enqueue_step()
