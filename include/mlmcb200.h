@@ -80,6 +80,7 @@ int mlmcb200_sample_mask(const mlmcb200_basis_t* basis, const double* pairs, int
  * so a level may be streamed in any number of chunks; zero acc first.
  * `valid` (from mlmcb200_sample_mask) is required when n_comp > 1 and may be NULL when n_comp == 1.
  * `workspace` must hold mlmcb200_moments_workspace_bytes(...) bytes.
+ * Limit: basis->size <= 226 for n_comp == 1, <= 113 otherwise (per-thread accumulator columns in shared memory).
  */
 int64_t mlmcb200_moments_workspace_bytes(int32_t size, int32_t n_comp);
 int mlmcb200_moments_accumulate(const mlmcb200_basis_t* basis, const double* pairs, int64_t n, int32_t n_comp,
@@ -123,6 +124,7 @@ int mlmcb200_moments_accumulate_resampled(const mlmcb200_basis_t* basis, const d
  * Both are dense contractions Phi^T Phi and run on FP64 tensor-core tiles (DMMA m8n8k4).
  * mode: 0 = covariance (above); 1 = Gram of the differences, sum_n d_i d_j with d = phi(f) - phi(c),
  * which is what TransformedMoments needs for its variances (var(L d) = L G L^T), want_var ignored.
+ * Limit: basis->size <= 104 (13 blocks of 8 moments in the shared-memory tile); larger sizes return an error.
  */
 int64_t mlmcb200_gram_workspace_bytes(int32_t size);
 int mlmcb200_gram_accumulate(const mlmcb200_basis_t* basis, const double* pairs, int64_t n,

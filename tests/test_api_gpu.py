@@ -383,7 +383,7 @@ def test_fused_bootstrap_statistics(golden):
 
 
 def test_bases_beyond_the_fused_kernel_limits(golden):
-    """More moments than the fused kernels hold (226 / 112): the generic device path (moments evaluated per row slice,
+    """More moments than the fused kernels hold (226 / 104): the generic device path (moments evaluated per row slice,
     RAW accumulate) still gives the reference's numbers."""
     from mlmc_b200.moments import Legendre
     from mlmc_b200.quantity import quantity_estimate as qe
