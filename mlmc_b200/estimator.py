@@ -90,6 +90,32 @@ class Estimate:
         fitted[1:] = np.exp(design @ coef)
         return fitted
 
+    def _variance_of_variance(self, n_samples=None):
+        """Variance of log(X), X ~ chi^2 with ``n - 1`` degrees of freedom scaled by ``1 / (n - 1)`` (``:136-169``;
+        tiny host quadrature, the reference computes it for its regression weights and then overrides them)."""
+        import scipy.integrate
+        import scipy.stats
+        if n_samples is None:
+            n_samples = self._n_created_samples
+        if hasattr(self, "_saved_var_var"):
+            ns, var_var = self._saved_var_var
+            if len(ns) == len(n_samples) and np.sum(np.abs(np.array(ns) - np.array(n_samples))) == 0:
+                return var_var
+        out = []
+        for ns in n_samples:
+            df = ns - 1
+            std_est = np.sqrt(2 / df)
+
+            def log_chi_pdf(x, df=df):
+                return np.exp(x) * df * scipy.stats.chi2.pdf(np.exp(x) * df, df=df)
+
+            def moment(m, std_est=std_est):
+                return scipy.integrate.quad(lambda x: x ** m * log_chi_pdf(x), -100 * std_est, 100 * std_est)[0]
+            mean = moment(1)
+            out.append(moment(2) - mean ** 2)
+        self._saved_var_var = (n_samples, np.array(out))
+        return np.array(out)
+
     # ---- bootstrap (``:171-218``).  The reference's version cannot run (its ``select(subsample(...))`` indexes
     # with a float array, quantity.py:168-169); here the sub-sampled quantity is used directly.  For plain bases all
     # replicates are fused on the device (``quantity_estimate.bootstrap_moments``): one launch per level. ----
@@ -189,6 +215,33 @@ def _percentiles(values, percents):
     return np.array(out)
 
 
+def estimate_domain(quantity, sample_storage, quantile=None):
+    """Module-level variant (``:344-363``): percentiles of EVERY level's own fine samples (at most ``N_0`` rows of
+    each).  The reference's version cannot run (it passes an ``n_samples`` keyword its ``ChunkSpec`` does not have);
+    this is what it evidently means.  Order statistics from the device (``mlmcb200_percentile_stats``)."""
+    if quantile is None:
+        quantile = 0.01
+    n_first = int(sample_storage.get_n_collected()[0])
+    storage_q = quantity.get_quantity_storage()
+    ranges = []
+    for level_id in range(sample_storage.get_n_levels()):
+        chunk_spec = next(sample_storage.chunks(level_id=level_id, n_samples=n_first))
+        fine = quantity.device_samples(storage_q.device_chunk(chunk_spec))[..., 0].reshape(-1)
+        ranges.append(_percentiles(fine, [100 * quantile, 100 * (1 - quantile)]))
+    ranges = np.array(ranges)
+    return np.min(ranges[:, 0]), np.max(ranges[:, 1])
+
+
+def calc_level_params(step_range, n_levels):
+    """``:388-398``: geometric sequence of level steps as ``[[h_0], [h_1], ...]``."""
+    assert step_range[0] > step_range[1]
+    level_parameters = []
+    for i_level in range(n_levels):
+        level_param = 1 if n_levels == 1 else i_level / (n_levels - 1)
+        level_parameters.append([step_range[0] ** (1 - level_param) * step_range[1] ** level_param])
+    return level_parameters
+
+
 def estimate_n_samples_for_target_variance(target_variance, prescribe_vars, n_ops, n_levels):
     """Optimal samples per level for a target variance, maximum over moments (``estimator.py:366-385``):
     ``n_l = max_r clip(round(sqrt(V_lr / C_l) * sum_k sqrt(V_kr C_k) / eps), 2, V_lr L / eps)``."""
@@ -209,9 +262,6 @@ def determine_level_parameters(n_levels, step_range):
         frac = 1 if n_levels == 1 else i_level / (n_levels - 1)
         params.append([step_range[0] ** (1 - frac) * step_range[1] ** frac])
     return params
-
-
-calc_level_params = determine_level_parameters
 
 
 def determine_sample_vec(n_collected_samples, n_levels, sample_vector=None):

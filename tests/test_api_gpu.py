@@ -463,3 +463,22 @@ def test_construct_density_equals_oracle_pipeline(r_base):
     xs = np.linspace(domain[0], domain[1], 201)
     want = orc.maxent_density(ob, ofit.multipliers, np.ones(len(om.mean)), xs)
     assert np.max(np.abs(distr_obj.density(xs) - want)) < 1e-6 * max(1.0, np.max(want))
+
+
+def test_module_level_domain_and_helpers(golden):
+    """estimator.estimate_domain (module level: every level's own fine samples), calc_level_params,
+    _variance_of_variance."""
+    from mlmc_b200 import estimator
+    from mlmc_b200.moments import Legendre
+    g = golden("estimates")
+    levels = [g["A_rows%d" % l] for l in range(3)]
+    storage, value = scalar_setup(levels, [[h] for h in g["A_steps"]], g["A_n_ops"])
+    lo, hi = estimator.estimate_domain(value, storage, quantile=0.01)
+    n0 = len(levels[0])
+    with np.errstate(invalid="ignore"):
+        want = np.array([np.percentile(lv[:n0, 0, 0][~np.isnan(lv[:n0, 0, 0])], [1, 99]) for lv in levels])
+    assert lo == want[:, 0].min() and hi == want[:, 1].max()
+    assert estimator.calc_level_params((0.5, 0.005), 3) == [[0.5], [0.5 ** 0.5 * 0.005 ** 0.5], [0.005]]
+    est = estimator.Estimate(value, storage, Legendre(4, (lo, hi)))
+    vv = est._variance_of_variance([10, 100, 1000])
+    assert vv.shape == (3,) and np.all(np.diff(vv) < 0) and abs(vv[2] - 2 / 999) < 2e-4
