@@ -31,15 +31,47 @@ def _device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_rule_cache = {}        # (domain, n_panels, degree) -> (nodes, weights); + device -> CUDA copies.  A few entries.
+_pinned_cache = {}      # size -> pinned staging vectors of the fit loop
+
+
 def gauss_panels(domain, n_panels, degree=21):
     """Composite Gauss-Legendre nodes / weights on ``n_panels`` equal panels of ``domain`` (the construction of
-    ``_update_quadrature``, ``:222-231``, on a fixed partition)."""
-    pt, w = np.polynomial.legendre.leggauss(degree)
-    edges = np.linspace(domain[0], domain[1], n_panels + 1)
-    a, b = edges[:-1, None], edges[1:, None]
-    nodes = (pt[None, :] + 1) / 2 * (b - a) + a
-    weights = w[None, :] * (b - a) / 2
-    return nodes.ravel(), weights.ravel()
+    ``_update_quadrature``, ``:222-231``, on a fixed partition).  Read-only arrays, memoised."""
+    key = (float(domain[0]), float(domain[1]), int(n_panels), int(degree))
+    hit = _rule_cache.get(key)
+    if hit is None:
+        pt, w = np.polynomial.legendre.leggauss(degree)
+        edges = np.linspace(domain[0], domain[1], n_panels + 1)
+        a, b = edges[:-1, None], edges[1:, None]
+        nodes = ((pt[None, :] + 1) / 2 * (b - a) + a).ravel()
+        weights = (w[None, :] * (b - a) / 2).ravel()
+        nodes.setflags(write=False)
+        weights.setflags(write=False)
+        if len(_rule_cache) >= 16:
+            _rule_cache.clear()
+        hit = _rule_cache[key] = (nodes, weights)
+    return hit
+
+
+def _gauss_panels_on(device, domain, n_panels, degree):
+    """The same rule as CUDA tensors (memoised per device)."""
+    key = (float(domain[0]), float(domain[1]), int(n_panels), int(degree), str(device))
+    hit = _rule_cache.get(key)
+    if hit is None:
+        nodes, weights = gauss_panels(domain, n_panels, degree)
+        hit = _rule_cache[key] = (torch.from_numpy(nodes.copy()).to(device), torch.from_numpy(weights.copy()).to(device))
+    return hit
+
+
+def _pinned_vectors(size):
+    hit = _pinned_cache.get(size)
+    if hit is None:
+        if len(_pinned_cache) >= 16:
+            _pinned_cache.clear()
+        hit = _pinned_cache[size] = (torch.empty(1 + size + size * size, dtype=torch.float64).pin_memory(),
+                                     torch.empty(size, dtype=torch.float64).pin_memory())
+    return hit
 
 
 class SimpleDistribution:
@@ -123,14 +155,12 @@ class SimpleDistribution:
         nodes, weights = gauss_panels(self.domain, self._n_panels, self._gauss_degree)
         self._quad_points = nodes
         self._quad_weights = weights
-        self._nodes_dev = torch.from_numpy(nodes).to(dev)
-        self._weights_dev = torch.from_numpy(weights).to(dev)
+        self._nodes_dev, self._weights_dev = _gauss_panels_on(dev, self.domain, self._n_panels, self._gauss_degree)
         self._quad_moments_dev = self.moments_fn.eval_all(self._nodes_dev, self.approx_size).contiguous()
         self._sigma_dev = torch.from_numpy(np.ascontiguousarray(self._moment_errs)).to(dev)
         self._lam_dev = torch.empty(self.approx_size, dtype=torch.float64, device=dev)
         self._out_dev = torch.zeros(1 + self.approx_size + self.approx_size ** 2, dtype=torch.float64, device=dev)
-        self._out_host = torch.empty(self._out_dev.shape, dtype=torch.float64).pin_memory()
-        self._lam_host = torch.empty(self.approx_size, dtype=torch.float64).pin_memory()
+        self._out_host, self._lam_host = _pinned_vectors(self.approx_size)
         self._cache_key = None
 
     @property
@@ -263,8 +293,9 @@ def _weighted_contraction(moments_fn, density, n_panels):
     by the same fused kernel (multipliers = 0 => rho = 1, weights = w * p)."""
     dev = _device()
     nodes, weights = gauss_panels(moments_fn.domain, n_panels)
+    nodes_dev, _ = _gauss_panels_on(dev, moments_fn.domain, n_panels, 21)
     pdf_w = np.asarray(density(nodes), dtype=np.float64) * weights
-    phi = moments_fn.eval_all(torch.from_numpy(nodes).to(dev)).contiguous()
+    phi = moments_fn.eval_all(nodes_dev).contiguous()
     r = phi.shape[1]
     out = _native.maxent_fgh(phi, torch.from_numpy(pdf_w).to(dev), torch.zeros(r, dtype=torch.float64, device=dev))
     out = out.cpu().numpy()
