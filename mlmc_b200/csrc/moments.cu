@@ -449,6 +449,21 @@ moments_acc_kernel(const MomentsArgs a) {
                 out[2 + K + (int64_t)m * R + r] = sm[(R + r) * T + tid] * (al * al);
             }
         }
+    } else if (!PAIR && TN <= 16) {
+        // few sample lanes per component: one THREAD per output sums its lanes serially; outputs are walked components
+        // fastest, so consecutive threads read consecutive shared-memory columns (a warp per output would spend
+        // two shuffle trees on 2..16 values and cost as much as the main loop at M = 64)
+        for (int o = tid; o < (int)K; o += T) {
+            const int r = o / M, mm = o - r * M;
+            double s1 = 0.0, s2 = 0.0;
+            for (int j = 0; j < TN; ++j) {
+                s1 += sm[r * T + j * M + mm];
+                s2 += sm[(R + r) * T + j * M + mm];
+            }
+            const double al = (KIND == MLMCB200_LEGENDRE) ? kLegAlpha[r] : 1.0;
+            out[2 + (int64_t)mm * R + r] = s1 * al;
+            out[2 + K + (int64_t)mm * R + r] = s2 * (al * al);
+        }
     } else {
         const int warp = tid >> 5, lane = tid & 31, n_warps = T >> 5;
         for (int k = warp; k < (int)K; k += n_warps) {
