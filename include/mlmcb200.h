@@ -78,7 +78,8 @@ int mlmcb200_sample_mask(const mlmcb200_basis_t* basis, const double* pairs, int
  *     acc[2 + K + k] = sum_n d_k^2,   K = n_comp * size,  k = m * size + r  (mom_at_bottom order)
  * where d = phi_r(fine_m) - phi_r(coarse_m) (level 0: phi_r(fine_m)).  The call ADDS the chunk into acc,
  * so a level may be streamed in any number of chunks; zero acc first.
- * `valid` (from mlmcb200_sample_mask) is required when n_comp > 1 and may be NULL when n_comp == 1.
+ * `valid` (from mlmcb200_sample_mask) is required when n_comp > 128; for 1 < n_comp <= 128 it may be NULL: the kernel
+ * then combines the components' domain tests per sample itself (and size <= 112).  NULL when n_comp == 1.
  * `workspace` must hold mlmcb200_moments_workspace_bytes(...) bytes.
  * Limit: basis->size <= 226 for n_comp == 1, <= 113 otherwise (per-thread accumulator columns in shared memory).
  */

@@ -233,8 +233,8 @@ def moments_accumulate(basis, x, acc_row, valid=None):
     if n == 0:
         return
     lib = load()
-    if M > 1 and valid is None:
-        valid = sample_mask(basis, x)
+    if M > 1 and valid is None and not (M <= 128 and basis.size <= 112):
+        valid = sample_mask(basis, x)          # wide quantities: mask pass; narrow ones are masked inside the kernel
     with _on_device(x.device):
         key = (basis.size, M)
         ws_bytes = _ws_bytes_cache.get(key)
@@ -292,7 +292,7 @@ def moments_accumulate_resampled(basis, x, idx, acc_level, valid=None):
     if n_rows == 0:
         raise NativeError("cannot draw from an empty chunk")
     lib = load()
-    if M > 1 and valid is None:
+    if M > 1 and valid is None and not (M <= 128 and basis.size <= 112):
         valid = sample_mask(basis, x)
     with _on_device(x.device):
         ws_bytes = lib.mlmcb200_moments_resampled_workspace_bytes(basis.size, M, B)

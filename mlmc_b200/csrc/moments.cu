@@ -39,6 +39,8 @@ struct MomentsArgs {
     double* partial;       // [gridDim.z][gridDim.y][2 + 2K]
     int64_t partial_stride;
     const int32_t* idx;    // re-sampling (bootstrap): replicate z reads the rows idx[z * n + i], i < n; else NULL
+    int32_t fuse_mask;     // vector quantity whose components all live in this CTA, no `valid` given: the kernel combines
+                           // the components' domain tests per sample itself (shared-memory flags, two barriers per tile)
 };
 
 // ---- per-moment reduction of the S samples held by this thread into its shared-memory column(s) ----
@@ -279,6 +281,7 @@ moments_acc_kernel(const MomentsArgs a) {
             if (STAGES == 0 && tile + gridDim.y < n_tiles) load_fast(tile + gridDim.y);
         } else {
             const int64_t n0 = tile * tile_n + tn;
+            bool own[S];                                   // this component's verdict on the sample, then the sample's
 #pragma unroll
             for (int s = 0; s < S; ++s) {
                 const int64_t n = n0 + (int64_t)s * TN;
@@ -290,12 +293,34 @@ moments_acc_kernel(const MomentsArgs a) {
                     tf[s] = map_to_ref_t<LOG>(a.basis, xf[s]);
                     tc[s] = COARSE ? map_to_ref_t<LOG>(a.basis, xc[s]) : 0.0;
                 }
-                bool good;
                 if (a.valid != nullptr) {
-                    good = in && a.valid[idx != nullptr && in ? (int64_t)__ldg(idx + n) : n] != 0;
+                    own[s] = in && a.valid[idx != nullptr && in ? (int64_t)__ldg(idx + n) : n] != 0;
                 } else {
-                    good = in && moments_finite(a.basis, tf[s]) && (!COARSE || moments_finite(a.basis, tc[s]));
+                    own[s] = in && moments_finite(a.basis, tf[s]) && (!COARSE || moments_finite(a.basis, tc[s]));
                 }
+            }
+            if (a.fuse_mask) {
+                // mask_nan_samples across the components of a sample: flag per (s, sample lane), double-buffered over
+                // tiles so that the reset for tile t+1 cannot overtake a late reader of tile t
+                unsigned char* const flag = reinterpret_cast<unsigned char*>(sm + (size_t)n_cols * T) +
+                                            (size_t)(k_tile & 1) * (S * TN);
+                if (active && m == 0) {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) flag[s * TN + tn] = 1;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    if (active && n0 + (int64_t)s * TN < a.n && !own[s]) flag[s * TN + tn] = 0;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int s = 0; s < S; ++s) own[s] = active && n0 + (int64_t)s * TN < a.n && flag[s * TN + tn] != 0;
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const bool in = active && n0 + (int64_t)s * TN < a.n;
+                const bool good = own[s];
                 if (count_here && in) {
                     cnt_ok += good ? 1u : 0u;
                     cnt_rm += good ? 0u : 1u;
@@ -857,7 +882,8 @@ int moments_accumulate_impl(const mlmcb200_basis_t* basis, const double* pairs, 
     if (check_basis(basis) != 0) return -1;
     MB_REQUIRE(n >= 0 && n_comp >= 1, "%s: bad n=%lld n_comp=%d", who, (long long)n, n_comp);
     MB_REQUIRE(acc != nullptr && workspace != nullptr, "%s: null acc/workspace", who);
-    MB_REQUIRE(n_comp == 1 || valid != nullptr, "%s: n_comp > 1 needs the sample mask", who);
+    MB_REQUIRE(n_comp == 1 || valid != nullptr || n_comp <= kThreads,
+               "%s: more than %d components need the sample mask (mlmcb200_sample_mask)", who, kThreads);
     if (n == 0) return 0;
     MB_REQUIRE(pairs != nullptr, "%s: null pairs", who);
     const bool gather = idx != nullptr;
@@ -895,6 +921,12 @@ int moments_accumulate_impl(const mlmcb200_basis_t* basis, const double* pairs, 
     a.partial = static_cast<double*>(workspace);
     a.partial_stride = stride;
     a.idx = idx;
+    a.fuse_mask = (n_comp > 1 && valid == nullptr) ? 1 : 0;
+    if (a.fuse_mask) {
+        p.smem += 1024;                                      // 2 x S x TN flag bytes
+        MB_REQUIRE(p.smem + 64 <= 227u * 1024u, "%s: size %d with the in-kernel sample mask exceeds the shared memory",
+                   who, basis->size);
+    }
     // re-sampling: only the Legendre kernels have a register-blocked gather variant, the other bases take the
     // generic kernel (row indirection at run time)
     p.fast = fast && (!gather || basis->kind == MLMCB200_LEGENDRE);
