@@ -230,6 +230,16 @@ class Quantity:
     def __rmod__(self, other):
         return Quantity.create_quantity([Quantity.wrap(other), self], Quantity.mod_op)
 
+    # conveniences the reference leaves to ``np.negative(q)`` / ``np.abs(q)`` / ``np.power(q, p)``
+    def __neg__(self):
+        return Quantity._method(np.negative, "__call__", self)
+
+    def __abs__(self):
+        return Quantity._method(np.absolute, "__call__", self)
+
+    def __pow__(self, other):
+        return Quantity._method(np.power, "__call__", self, other)
+
     # ---- comparisons -> sample masks (quantity.py:245-303) ----
     @staticmethod
     def _process_mask(x, y, op):
@@ -272,8 +282,10 @@ class Quantity:
 
     @staticmethod
     def _method(ufunc, method, *args, **kwargs):
-        if method != "__call__" or kwargs:
-            raise NotImplementedError("only plain ufunc calls are supported on quantities")
+        if method == "reduce":
+            return Quantity._reduce(ufunc, *args, **kwargs)
+        if method != "__call__" or any(v is not None and v != (None,) for v in kwargs.values()):
+            raise NotImplementedError("only plain ufunc calls and reductions over the components are supported")
         name = _UFUNC_TO_TORCH.get(ufunc.__name__, ufunc.__name__)
         torch_fn = getattr(torch, name, None)
         if torch_fn is None:
@@ -284,6 +296,26 @@ class Quantity:
         quantities = [Quantity.wrap(arg) for arg in args]
         result_qtype = Quantity._result_qtype(ufunc_call, quantities)
         return Quantity(quantity_type=result_qtype, input_quantities=list(quantities), operation=ufunc_call)
+
+    @staticmethod
+    def _reduce(ufunc, quantity, axis=0, keepdims=False, **kwargs):
+        """``np.max / np.min / np.sum / np.prod / np.all / np.any`` of a quantity over its COMPONENT axis
+        (``np.max(q, axis=0, keepdims=True)`` in test/test_quantity_concept.py:382-392) -> one-component quantity."""
+        if any(v is not None and v != (None,) for v in kwargs.values()):
+            raise NotImplementedError("reduction options %s are not supported on quantities" % sorted(kwargs))
+        if axis not in (0, (0,)):
+            raise NotImplementedError("quantities reduce over axis 0 (the components) only")
+        name = {"maximum": "amax", "minimum": "amin", "add": "sum", "multiply": "prod", "logical_and": "all",
+                "logical_or": "any"}.get(ufunc.__name__)
+        if name is None:
+            raise NotImplementedError("numpy reduction of %s has no device implementation" % ufunc.__name__)
+        torch_fn = getattr(torch, name)
+
+        def reduce_call(chunk):
+            return torch_fn(chunk, dim=0, keepdim=True)          # a chunk always keeps its [M, n, S] shape
+        quantity = Quantity.wrap(quantity)
+        result_qtype = Quantity._result_qtype(reduce_call, [quantity])
+        return Quantity(quantity_type=result_qtype, input_quantities=[quantity], operation=reduce_call)
 
     @staticmethod
     def wrap(value):
@@ -316,7 +348,10 @@ class Quantity:
                 break
         if probe is None:
             probe = DeviceChunk(None, None)
-        result = method(*[q.device_samples(probe) for q in quantities])
+        try:
+            result = method(*[q.device_samples(probe) for q in quantities])
+        except RuntimeError as exc:              # torch's broadcasting error; numpy raises ValueError here
+            raise ValueError(str(exc))
         return qt.ArrayType(shape=result.shape[0], qtype=Quantity._get_base_qtype(quantities))
 
     # ---- composition (quantity.py:396-523) ----

@@ -192,6 +192,9 @@ def estimate_mean(quantity):
                 acc = _native.LevelAccumulator(n_levels, basis.size * basis.size, device)
             _native.gram_accumulate(basis, x, acc.level(level_id), mode=0, want_var=True)
         else:
+            if x.dtype == torch.bool:
+                # the reference fails the same way: numpy refuses ``fine - coarse`` on boolean chunks
+                raise TypeError("estimate_mean of a boolean quantity (use it in select(), or cast it)")
             x = x if x.dtype == torch.float64 else x.to(torch.float64)
             if acc is None:
                 acc = _native.LevelAccumulator(n_levels, x.shape[0], device)
