@@ -482,3 +482,27 @@ def test_module_level_domain_and_helpers(golden):
     est = estimator.Estimate(value, storage, Legendre(4, (lo, hi)))
     vv = est._variance_of_variance([10, 100, 1000])
     assert vv.shape == (3,) and np.all(np.diff(vv) < 0) and abs(vv[2] - 2 / 999) < 2e-4
+
+
+def test_allocation_grows_as_target_variance_shrinks(golden):
+    """Property of the reference's (skipped) test/test_estimate.py: the n-sample allocation grows monotonically while
+    the target variance decreases; the covariance estimate is symmetric; the allocation follows the oracle's."""
+    from mlmc_b200 import estimator
+    from mlmc_b200.moments import Legendre
+    g = golden("estimates")
+    levels = [g["A_rows%d" % l] for l in range(3)]
+    storage, value = scalar_setup(levels, [[h] for h in g["A_steps"]], g["A_n_ops"])
+    domain = tuple(g["A_domain"])
+    est = estimator.Estimate(value, storage, Legendre(15, domain))
+    variances, n_ops = est.estimate_diff_vars_regression(None)
+    prev = np.zeros(3)
+    for target in (1e-3, 1e-5, 1e-7, 1e-9):
+        n_est = estimator.estimate_n_samples_for_target_variance(target, variances, n_ops, n_levels=3)
+        assert np.all(n_est >= prev) and np.any(n_est > prev)
+        prev = n_est
+    want_vars = orc.regress_level_variances(orc.estimate_moments(levels, orc.Basis("legendre", 15, domain)).l_vars,
+                                            g["A_steps"])
+    rel_close(variances, want_vars, rtol=1e-9)
+    assert np.array_equal(n_est, orc.n_samples_for_target_variance(1e-9, want_vars, n_ops, 3))
+    cov, _ = est.estimate_covariance()
+    assert np.array_equal(cov, cov.T)
