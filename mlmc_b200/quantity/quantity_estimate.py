@@ -7,7 +7,7 @@ device chunks ``[M, n, 2]`` through the fused kernels:
 =====================================  ======================================================================
 quantity                               kernels
 =====================================  ======================================================================
-``moments(q, basis)``                  ``mlmcb200_moments_accumulate`` (+ ``sample_mask`` when M > 1)
+``moments(q, basis)``                  ``mlmcb200_moments_accumulate`` (+ ``sample_mask`` when M > 128)
 ``moments(q, TransformedMoments)``     moments sums of the base functions + DMMA Gram of the differences,
                                        then mean' = L s, sum d'^2 = diag(L G L^T)   (scalar q)
 ``covariance(q, basis)`` (scalar q)    ``mlmcb200_gram_accumulate`` (DMMA), sums and sums of squares
