@@ -224,6 +224,10 @@ def run_gpu_arm(args):
     level_streams = [torch.cuda.Stream(device) for _ in range(N_LEVELS - 1)]
     concurrent_levels = os.environ.get("BENCH_CONCURRENT_LEVELS", "1") != "0"
 
+    # N > 1: the sum of the level accumulators over the ranks rides in the finalize launch (NVLink peer memory,
+    # mlmcb200_allreduce_finalize_levels); checked against the NCCL all-reduce once, NCCL stays the fallback
+    use_peer = [False]
+
     def enqueue_step():
         acc.acc.zero_()
         main = torch.cuda.current_stream()
@@ -246,10 +250,21 @@ def run_gpu_arm(args):
                         joins.append(ev)
             for ev in joins:
                 main.wait_event(ev)
-        if world > 1:
+        if world > 1 and not use_peer[0]:
             td.all_reduce(acc.acc)
-        result.update(acc.finalize())
+        result.update(acc.finalize(peer=mdist.peer_state(acc.acc.numel()) if use_peer[0] else None))
 
+    if world > 1 and os.environ.get("BENCH_PEER_REDUCE", "1") != "0" and mdist.enable_peer_reduce():
+        enqueue_step()
+        torch.cuda.synchronize()
+        want = result["packed"].clone()
+        use_peer[0] = True
+        enqueue_step()
+        torch.cuda.synchronize()
+        good = torch.tensor([int(torch.allclose(result["packed"], want, rtol=1e-13, atol=0.0, equal_nan=False)
+                                 and not mdist.peer_error())], device=device)
+        td.all_reduce(good, op=td.ReduceOp.MIN)
+        use_peer[0] = bool(good.item())
     side = torch.cuda.Stream(device)
     with torch.cuda.stream(side):
         enqueue_step()                                   # warm up allocations outside the capture
@@ -257,7 +272,8 @@ def run_gpu_arm(args):
         graph = None
         # N > 1: plain stream launches by default; BENCH_GRAPH_MULTI=1 captures the all-reduce with the kernels (NCCL
         # supports stream capture; measured 0.653 vs 0.659 ms per step at N = 2 -- not worth a capture failure mode)
-        if world == 1 or os.environ.get("BENCH_GRAPH_MULTI", "0") == "1":
+        # (with the peer-memory reduce the step holds no NCCL call at all and is captured like the single-GPU step)
+        if world == 1 or use_peer[0] or os.environ.get("BENCH_GRAPH_MULTI", "0") == "1":
             if world > 1:
                 enqueue_step()                           # a second eager step: NCCL sets up its channels lazily
                 torch.cuda.synchronize()
@@ -427,6 +443,8 @@ def run_gpu_arm(args):
             "config": {"workload": workload_name(n_rows), "levels": N_LEVELS, "samples_per_level_per_gpu": n_rows,
                        "n_moments": N_MOMENTS, "l2_policy": "inputs (%.0f MB per step per GPU) exceed the 126 MB L2"
                        % (bytes_per_rank / 1e6), "parallelism": "sample-sharded x%d, one all-reduce of level sums" % world,
+                       "reduce": ("none" if world == 1 else "NVLink peer memory, fused with the finalize launch"
+                                  if use_peer[0] else "NCCL all-reduce"),
                        "launch": "CUDA graph" if graph is not None else "stream"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(bytes_per_rank * world),
                     "d2h_bytes_per_step": int(d2h_bytes * world), "steps": e2e_steps,

@@ -150,6 +150,30 @@ int mlmcb200_finalize_levels_batched(const double* acc, int64_t acc_stride, int3
                                      int32_t n_batch, int64_t acc_batch_stride, double* out, void* stream);
 
 /*
+ * Multi-GPU: finalize fused with the cross-rank SUM of the level accumulators over NVLink peer memory (one launch,
+ * no NCCL call, no host synchronisation).  The reference has no distributed estimation; this replaces the
+ * "all-reduce, then mlmcb200_finalize_levels" pair of the sample-sharded estimate.
+ *   peer_buffer_bytes / peer_alloc : every rank allocates one exchange buffer (cudaMalloc, zeroed) and gets its
+ *                                    64-byte cudaIpc handle, which the host side exchanges between the ranks
+ *   peer_open / peer_close         : map / unmap another rank's buffer in this process
+ *   allreduce_finalize_levels      : acc [n_levels][acc_stride] of this rank is added over all ranks IN RANK ORDER
+ *                                    (bit-identical sums everywhere) and written back to acc; l_means / l_vars /
+ *                                    mean / var as mlmcb200_finalize_levels.  peer_buffers: DEVICE array [world] of the
+ *                                    ranks' buffers as mapped here (own buffer at index rank).  Collective: every
+ *                                    rank must call it the same number of times.  Waits at most ~1 s for the peers,
+ *                                    then writes NaN results and sets the error word (mlmcb200_peer_error).
+ */
+int64_t mlmcb200_peer_buffer_bytes(int32_t world, int64_t slot_doubles);
+int mlmcb200_peer_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);
+int mlmcb200_peer_open(const unsigned char* handle64, void** dev_ptr);
+int mlmcb200_peer_close(void* dev_ptr);
+int mlmcb200_peer_free(void* dev_ptr);
+int mlmcb200_peer_error(const void* own_buffer, int32_t world, int64_t slot_doubles, int32_t* error);
+int mlmcb200_allreduce_finalize_levels(double* acc, int64_t acc_stride, int32_t n_levels, int64_t K, int32_t rank,
+                                       int32_t world, void* const* peer_buffers, int64_t slot_doubles,
+                                       double* l_means, double* l_vars, double* mean, double* var, void* stream);
+
+/*
  * Order statistics for Estimate.estimate_domain (mlmc/estimator.py:275-302): the reference takes
  * np.percentile(fine, [100 q, 100 (1 - q)]) of a level's fine samples.  For every fraction f in frac[0..n_frac)
  * (host array, values in [0, 1]) this finds, among the non-NaN entries x[i * stride], i < n (device), the two

@@ -50,6 +50,14 @@ _SIGNATURES = {
                                                 _c_vp]),
     "mlmcb200_finalize_levels_batched": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i64, _c_i32, _c_i64, _c_vp,
                                                         _c_vp]),
+    "mlmcb200_peer_buffer_bytes": (_c_i64, [_c_i32, _c_i64]),
+    "mlmcb200_peer_alloc": (ctypes.c_int, [_c_i64, ctypes.POINTER(_c_vp), ctypes.POINTER(ctypes.c_ubyte)]),
+    "mlmcb200_peer_open": (ctypes.c_int, [ctypes.POINTER(ctypes.c_ubyte), ctypes.POINTER(_c_vp)]),
+    "mlmcb200_peer_close": (ctypes.c_int, [_c_vp]),
+    "mlmcb200_peer_free": (ctypes.c_int, [_c_vp]),
+    "mlmcb200_peer_error": (ctypes.c_int, [_c_vp, _c_i32, _c_i64, ctypes.POINTER(_c_i32)]),
+    "mlmcb200_allreduce_finalize_levels": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i64, _c_i32, _c_i32, _c_vp, _c_i64,
+                                                          _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "mlmcb200_percentile_workspace_bytes": (_c_i64, [_c_i32]),
     "mlmcb200_percentile_stats": (ctypes.c_int, [_c_vp, _c_i64, _c_i64, ctypes.POINTER(_c_dbl), _c_i32, _c_vp, _c_vp,
                                                  _c_i64, _c_vp]),
@@ -159,13 +167,24 @@ class LevelAccumulator:
     def level(self, l):
         return self.acc[l]
 
-    def finalize(self):
-        """-> dict of CUDA tensors l_means [L,K], l_vars [L,K], mean [K], var [K] (one launch)."""
+    def finalize(self, peer=None):
+        """-> dict of CUDA tensors l_means [L,K], l_vars [L,K], mean [K], var [K] (one launch).
+
+        ``peer`` (``mlmc_b200.dist.peer_state()``): the launch first adds the accumulators of all ranks over NVLink
+        peer memory (``mlmcb200_allreduce_finalize_levels``); ``self.acc`` then holds the global sums."""
         global launch_count
         dev = self.acc.device
         L, K = self.n_levels, self.K
         out = torch.empty((2 * L + 2, K), dtype=torch.float64, device=dev)
         l_means, l_vars, mean, var = out[:L], out[L:2 * L], out[2 * L], out[2 * L + 1]
+        if peer is not None:
+            with torch.cuda.device(dev):
+                _check(load().mlmcb200_allreduce_finalize_levels(
+                    _ptr(self.acc), self.acc.stride(0), L, K, peer["rank"], peer["world"], _ptr(peer["ptrs"]),
+                    peer["slot"], _ptr(l_means), _ptr(l_vars), _ptr(mean), _ptr(var), _stream()),
+                    "allreduce_finalize_levels")
+            launch_count += 1
+            return {"l_means": l_means, "l_vars": l_vars, "mean": mean, "var": var, "packed": out}
         with torch.cuda.device(dev):
             _check(load().mlmcb200_finalize_levels(_ptr(self.acc), self.acc.stride(0), L, K, _ptr(l_means),
                                                    _ptr(l_vars), _ptr(mean), _ptr(var), _stream()),

@@ -14,7 +14,7 @@ import os
 
 import torch
 
-_state = {"enabled": False, "rank": 0, "world": 1, "group": None}
+_state = {"enabled": False, "rank": 0, "world": 1, "group": None, "peer": None}
 
 
 def enable(rank=None, world=None, group=None):
@@ -29,6 +29,77 @@ def enable(rank=None, world=None, group=None):
 
 def disable():
     _state.update(enabled=False, rank=0, world=1, group=None)
+
+
+def enable_peer_reduce(slot_doubles=16384):
+    """Set up the NVLink peer-memory exchange buffers of ``mlmcb200_allreduce_finalize_levels`` (one per rank, mapped
+    into every other rank through cudaIpc handles; all ranks of the default group must sit on ONE node).  Collective.
+    Afterwards ``estimate_mean`` adds the level sums and finalizes in a single launch whenever the accumulators fit a
+    slot; wider ones keep the NCCL all-reduce.  Returns True on success, False (and stays on NCCL) otherwise."""
+    import ctypes
+    import torch.distributed as td
+    from . import _native
+    if _state["peer"] is not None:
+        return True
+    if world_size() < 2 or world_size() > 16 or not torch.cuda.is_available():
+        return False
+    lib = _native.load()
+    world, rank_ = _state["world"], _state["rank"]
+    ok = True
+    own = ctypes.c_void_p()
+    handle = (ctypes.c_ubyte * 64)()
+    n_bytes = lib.mlmcb200_peer_buffer_bytes(world, slot_doubles)
+    if n_bytes < 0 or lib.mlmcb200_peer_alloc(n_bytes, ctypes.byref(own), handle) != 0:
+        ok = False
+    handles = [None] * world
+    td.all_gather_object(handles, bytes(handle) if ok else None, group=_state["group"])
+    ptrs, opened = [], []
+    if ok and all(h is not None for h in handles):
+        for r in range(world):
+            if r == rank_:
+                ptrs.append(own.value)
+                continue
+            p = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+            if lib.mlmcb200_peer_open(buf, ctypes.byref(p)) != 0:
+                ok = False
+                break
+            ptrs.append(p.value)
+            opened.append(p.value)
+    else:
+        ok = False
+    flags = [None] * world
+    td.all_gather_object(flags, ok, group=_state["group"])                  # all or nobody
+    if not all(flags):
+        for p in opened:
+            lib.mlmcb200_peer_close(ctypes.c_void_p(p))
+        if own.value:
+            lib.mlmcb200_peer_free(own)
+        return False
+    device = torch.device("cuda", torch.cuda.current_device())
+    _state["peer"] = {"rank": rank_, "world": world, "slot": int(slot_doubles), "own": own.value, "opened": opened,
+                      "ptrs": torch.tensor(ptrs, dtype=torch.int64, device=device)}
+    return True
+
+
+def peer_state(n_doubles=None):
+    """The peer-reduce set-up if it is active (and ``n_doubles`` fit a slot), else None."""
+    peer = _state["peer"] if _state["enabled"] else None
+    if peer is not None and n_doubles is not None and n_doubles > peer["slot"]:
+        return None
+    return peer
+
+
+def peer_error():
+    """True if a fused reduce gave up waiting for a peer (its results are NaN)."""
+    import ctypes
+    from . import _native
+    peer = _state["peer"]
+    if peer is None:
+        return False
+    err = ctypes.c_int32(0)
+    _native.load().mlmcb200_peer_error(ctypes.c_void_p(peer["own"]), peer["world"], peer["slot"], ctypes.byref(err))
+    return err.value != 0
 
 
 def world_size():

@@ -215,14 +215,19 @@ def estimate_mean(quantity):
         acc = _native.LevelAccumulator(n_levels, width, device)
     if acc is None:
         raise Exception("All samples were masked")
+    peer = None
     if multi:
-        _dist.all_reduce_sum(acc.acc)
-        if gram is not None:
-            _dist.all_reduce_sum(gram.acc)
+        # scalar-sized accumulators: the sum over the ranks rides in the finalize launch (NVLink peer memory);
+        # anything else: one NCCL all-reduce
+        peer = _dist.peer_state(acc.acc.numel()) if plan.kind != "transformed" else None
+        if peer is None:
+            _dist.all_reduce_sum(acc.acc)
+            if gram is not None:
+                _dist.all_reduce_sum(gram.acc)
 
     if plan.kind == "transformed":
         acc = _transform_sums(acc, gram, plan.fn, device)
-    out = acc.finalize()
+    out = acc.finalize(peer=peer)
     packed_dev = torch.cat([out["packed"].reshape(-1), acc.acc[:, :2].reshape(-1)])
     packed = _to_host(packed_dev)                                                    # single D2H copy
     L, K = acc.n_levels, acc.K

@@ -45,9 +45,18 @@ def _worker(rank, world, port, out_dir):
         dist.disable()
         bs1 = qe.bootstrap_moments(value, Legendre(6, tuple(g["A_domain"])), [800, 400, 200], 5, seed=4)
         dist.enable(rank, world)
+    # the same estimates with the sum over the ranks fused into the finalize launch (NVLink peer memory)
+    peer_ok = dist.enable_peer_reduce()
+    peer = {}
+    if peer_ok:
+        for rep in range(3):                        # several epochs: the two exchange buffers alternate
+            qm2 = qe.estimate_mean(qe.moments(value, Legendre(12, tuple(g["A_domain"]))))
+            cm2 = qe.estimate_mean(qe.covariance(value, Legendre(8, tuple(g["A_domain"]))))
+        peer = dict(p_l_means=qm2.l_means, p_l_vars=qm2.l_vars, p_n=qm2.n_samples, p_cov=cm2.mean, p_cov_var=cm2.var,
+                    p_err=int(dist.peer_error()))
     np.savez(os.path.join(out_dir, "r%d.npz" % rank), l_means=qm.l_means, l_vars=qm.l_vars, n=qm.n_samples,
              n_rm=qm.n_rm_samples, cov=cm.mean, cov_var=cm.var, bs_l_means=bs["l_means"], bs_n=bs["n_samples"],
-             bs1_l_means=bs1["l_means"] if bs1 is not None else np.zeros(0))
+             bs1_l_means=bs1["l_means"] if bs1 is not None else np.zeros(0), peer_ok=int(peer_ok), **peer)
     import torch.distributed as td
     td.barrier()
     td.destroy_process_group()
@@ -75,3 +84,13 @@ def test_two_gpu_sharded_estimate(tmp_path, golden):
     # replicates 0..1 live on rank 0 in both runs (same keys): identical; the rest are valid but differently seeded
     assert np.array_equal(a["bs_l_means"][:2], a["bs1_l_means"][:2])
     assert np.all(np.abs(a["bs_l_means"][:, :, 0].sum(axis=1) - 1.0) < 1e-12)
+    # fused peer-memory reduce: same numbers as the NCCL route (two ranks: a + b either way), no time-out
+    assert int(a["peer_ok"]) == int(b["peer_ok"])
+    if int(a["peer_ok"]):
+        for out in (a, b):
+            assert int(out["p_err"]) == 0
+            assert np.array_equal(out["p_n"], out["n"])
+            assert np.array_equal(out["p_l_means"], out["l_means"]) and np.array_equal(out["p_l_vars"], out["l_vars"])
+            assert np.array_equal(out["p_cov"], out["cov"]) and np.array_equal(out["p_cov_var"], out["cov_var"])
+    else:
+        print("peer-memory reduce not available on this box (cudaIpc); NCCL route tested only")
