@@ -261,7 +261,9 @@ def run_gpu_arm(args):
         use_peer[0] = True
         enqueue_step()
         torch.cuda.synchronize()
-        good = torch.tensor([int(torch.allclose(result["packed"], want, rtol=1e-13, atol=0.0, equal_nan=False)
+        # (more than two ranks: NCCL adds in its own order, the peer kernel in rank order -- rounding-level differences
+        # in the sums, amplified by the cancellation in the variances)
+        good = torch.tensor([int(torch.allclose(result["packed"], want, rtol=1e-8, atol=1e-14, equal_nan=False)
                                  and not mdist.peer_error())], device=device)
         td.all_reduce(good, op=td.ReduceOp.MIN)
         use_peer[0] = bool(good.item())
