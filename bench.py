@@ -267,6 +267,8 @@ def run_gpu_arm(args):
                                  and not mdist.peer_error())], device=device)
         td.all_reduce(good, op=td.ReduceOp.MIN)
         use_peer[0] = bool(good.item())
+        if not use_peer[0]:
+            mdist.disable_peer_reduce()                  # the public API (e2e pass) stays on NCCL as well
     side = torch.cuda.Stream(device)
     with torch.cuda.stream(side):
         enqueue_step()                                   # warm up allocations outside the capture

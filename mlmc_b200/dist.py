@@ -82,6 +82,11 @@ def enable_peer_reduce(slot_doubles=16384):
     return True
 
 
+def disable_peer_reduce():
+    """Back to the NCCL all-reduce (the exchange buffers stay mapped until the process exits)."""
+    _state["peer"] = None
+
+
 def peer_state(n_doubles=None):
     """The peer-reduce set-up if it is active (and ``n_doubles`` fit a slot), else None."""
     peer = _state["peer"] if _state["enabled"] else None
