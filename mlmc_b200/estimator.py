@@ -113,8 +113,9 @@ class Estimate:
                 return scipy.integrate.quad(lambda x: x ** m * log_chi_pdf(x), -100 * std_est, 100 * std_est)[0]
             mean = moment(1)
             out.append(moment(2) - mean ** 2)
-        self._saved_var_var = (n_samples, np.array(out))
-        return np.array(out)
+        out = np.array(out)
+        self._saved_var_var = (n_samples, out)
+        return out
 
     # ---- bootstrap (``:171-218``).  The reference's version cannot run (its ``select(subsample(...))`` indexes
     # with a float array, quantity.py:168-169); here the sub-sampled quantity is used directly.  For plain bases all

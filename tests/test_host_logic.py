@@ -134,3 +134,45 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_estimator_host_helpers():
+    """Host-only pieces of mlmc/estimator.py: level parameters, sample vectors, variance of the log-chi^2 variance
+    estimate (estimator.py:136-169, :388-431)."""
+    from mlmc_b200 import estimator
+    assert estimator.calc_level_params((0.5, 0.005), 1) == [[0.005]]
+    params = estimator.calc_level_params((0.5, 0.005), 3)
+    assert params[0] == [0.5] and params[2] == [0.005] and abs(params[1][0] - 0.05) < 1e-15
+    assert np.allclose(np.squeeze(estimator.determine_level_parameters(3, (0.5, 0.005))), [0.5, 0.05, 0.005])
+    assert list(estimator.determine_sample_vec([100, 50, 10], 3)) == [100, 50, 10]
+    assert list(estimator.determine_sample_vec([100, 50, 10], 3, sample_vector=[7, 5, 3])) == [7, 5, 3]
+    est = estimator.Estimate(None, None)
+    vv = est._variance_of_variance([10, 100, 1000])
+    assert vv.shape == (3,) and np.all(np.diff(vv) < 0)
+    assert abs(vv[2] - 2 / 999) < 2e-4                      # var(log chi2_df / df) -> 2 / df
+    assert est._variance_of_variance([10, 100, 1000]) is vv   # memoised for the same n_samples
+    # regression leaves moment 0 and single-level / two-level inputs alone
+    raw = np.array([[0.0, 1.0, 2.0], [0.0, 0.1, 0.3], [0.0, 0.02, 0.05]])
+    reg = est._all_moments_variance_regression(raw, np.array([0.5, 0.05, 0.005]))
+    assert np.array_equal(reg[0], raw[0]) and np.all(reg[:, 0] == 0) and np.allclose(reg[1:, 1:], raw[1:, 1:])
+    assert np.array_equal(est._all_moments_variance_regression(raw[:2], np.array([0.5, 0.05])), raw[:2])
+
+
+def test_gauss_rule_is_memoised_and_read_only():
+    from mlmc_b200.tool.simple_distribution import gauss_panels
+    a = gauss_panels((0.0, 2.0), 5)
+    b = gauss_panels((0.0, 2.0), 5)
+    assert a[0] is b[0] and a[1] is b[1]
+    assert not a[0].flags.writeable and abs(a[1].sum() - 2.0) < 1e-14
+    assert gauss_panels((0.0, 2.0), 6)[0].size == 6 * 21
+
+
+def test_replicate_shards_cover_all_replicates():
+    """Bootstrap replicates are sharded with the same rule as rows."""
+    from mlmc_b200 import dist
+    for n_rep in (1, 5, 100, 301):
+        for world in (2, 3, 8):
+            ranges = [dist.shard_range(n_rep, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n_rep
+            assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+    assert dist.peer_state() is None and dist.peer_error() is False       # nothing set up in a plain process
