@@ -1,6 +1,6 @@
 import os, sys, time, cProfile, pstats
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import mlmc_oracle as orc
 from mlmc_b200.moments import Fourier
 from mlmc_b200.sample_storage import Memory

@@ -16,7 +16,7 @@ import numpy as np
 import scipy.stats as stats
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import mlmc_oracle as orc  # noqa: E402
 from mlmc_b200 import _native as nat  # noqa: E402
 from mlmc_b200.moments import Legendre, Fourier  # noqa: E402
