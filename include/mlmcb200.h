@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MLMCB200_ABI_VERSION 1
+#define MLMCB200_ABI_VERSION 2
 
 /* mlmcb200_basis_t.kind */
 #define MLMCB200_RAW       0   /* identity, size 1: phi_0(x) = x, no transform (plain estimate_mean of a quantity) */
@@ -101,14 +101,16 @@ int mlmcb200_moments_accumulate(const mlmcb200_basis_t* basis, const double* pai
 /*
  * Row numbers for mlmcb200_moments_accumulate_resampled, drawn on the device: idx[b * n_draws + j], b < n_rep, is
  * uniform on [0, n_rows) WITH replacement (RNG.choice of Quantity.pick_samples, mlmc/quantity/quantity.py:318-319).
- * Counter-based Philox4x32-10 keyed by (seed, stream_id, replicate, draw): the same arguments give the same numbers.
+ * Counter-based Philox4x32-10: key (seed, stream_id), counter (draw, rep_offset + b) -- replicate rep_offset + b gets
+ * the same rows whatever the grouping of the replicates into calls (or their sharding over ranks).
  * n_blocks > 1 orders each replicate's draws by row block (block p = rows [p n_rows / P, (p+1) n_rows / P)) so that
  * concurrent CTAs gather from an L2-sized window: block_cum (device, [n_rep][n_blocks + 1], block_cum[b][0] = 0,
  * block_cum[b][P] = n_draws) are the caller's cumulative MULTINOMIAL block counts -- the draws are then exactly
  * i.i.d. uniform rows, listed in block order (the level sums do not depend on the order).
  */
 int mlmcb200_resample_indices(uint64_t seed, uint64_t stream_id, int64_t n_rows, int64_t n_draws, int32_t n_rep,
-                              int32_t n_blocks, const int64_t* block_cum, int32_t* idx, void* stream);
+                              int32_t rep_offset, int32_t n_blocks, const int64_t* block_cum, int32_t* idx,
+                              void* stream);
 int64_t mlmcb200_moments_resampled_workspace_bytes(int32_t size, int32_t n_comp, int32_t n_rep);
 int mlmcb200_moments_accumulate_resampled(const mlmcb200_basis_t* basis, const double* pairs, int64_t n_rows,
                                           int32_t n_comp, int64_t stride_n, int64_t stride_side, int64_t stride_m,
@@ -143,6 +145,22 @@ int mlmcb200_finalize_levels(const double* acc, int64_t acc_stride, int32_t n_le
                              double* l_means, double* l_vars, double* mean, double* var, void* stream);
 
 /*
+ * Covariance level sums from moment level sums.  The reference forms per-sample outer products phi_i phi_j
+ * (mlmc/quantity/quantity_estimate.py:131-147) and sums them; products of Legendre / monomial / trigonometric
+ * functions are exact linear combinations of a longer basis of the same family (phi_i phi_j = sum_k C[ij][k] phi_k,
+ * k < K0), and the NaN mask depends on the domain only, so per level
+ *     sum_n d_ij = sum_k C[ij][k] * (sum_n d_k)
+ * with the sums of mlmcb200_moments_accumulate over the K0-function basis.  This call applies such a map:
+ *     acc_out[l][2 + m K1 + o] = sum_k mat_t[k K1 + o] * acc_in[l][2 + m K0 + k],   o < K1, m < n_comp, l < n_levels
+ * (mat_t: device, [K0][K1] row-major), copies the two counts and fills the sums of squares of acc_out with NaN
+ * (mlmcb200_finalize_levels then yields NaN variances: entry variances need mlmcb200_gram_accumulate).
+ * Also the map TransformedMoments (mlmc/moments.py:256-259) applies under the sums.
+ */
+int mlmcb200_level_sums_transform(const double* acc_in, int64_t in_stride, int32_t n_levels, int32_t K0,
+                                  int32_t n_comp, const double* mat_t, int32_t K1, double* acc_out,
+                                  int64_t out_stride, void* stream);
+
+/*
  * The same for n_batch accumulator sets acc_batch_stride doubles apart (the replicates of est_bootstrap,
  * mlmc/estimator.py:185-193): out[b] = [l_means (L*K) | l_vars (L*K) | mean (K) | var (K)], packed per entry.
  */
@@ -160,8 +178,12 @@ int mlmcb200_finalize_levels_batched(const double* acc, int64_t acc_stride, int3
  *                                    (bit-identical sums everywhere) and written back to acc; l_means / l_vars /
  *                                    mean / var as mlmcb200_finalize_levels.  peer_buffers: DEVICE array [world] of the
  *                                    ranks' buffers as mapped here (own buffer at index rank).  Collective: every
- *                                    rank must call it the same number of times.  Waits at most ~1 s for the peers,
- *                                    then writes NaN results and sets the error word (mlmcb200_peer_error).
+ *                                    rank must call it the same number of times.  Waits at most
+ *                                    MLMCB200_PEER_TIMEOUT_MS (environment, default 30 000) for the peers; a rank that
+ *                                    gives up marks the epoch in every peer, so late ranks fail it as well.  A failed call
+ *                                    leaves acc (the LOCAL sums) untouched, writes NaN results, status[0] = 1 (device,
+ *                                    may be NULL; 0 on success) and sets the sticky error word (mlmcb200_peer_error):
+ *                                    the caller then falls back to an all-reduce + mlmcb200_finalize_levels.
  */
 int64_t mlmcb200_peer_buffer_bytes(int32_t world, int64_t slot_doubles);
 int mlmcb200_peer_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);
@@ -171,7 +193,8 @@ int mlmcb200_peer_free(void* dev_ptr);
 int mlmcb200_peer_error(const void* own_buffer, int32_t world, int64_t slot_doubles, int32_t* error);
 int mlmcb200_allreduce_finalize_levels(double* acc, int64_t acc_stride, int32_t n_levels, int64_t K, int32_t rank,
                                        int32_t world, void* const* peer_buffers, int64_t slot_doubles,
-                                       double* l_means, double* l_vars, double* mean, double* var, void* stream);
+                                       double* l_means, double* l_vars, double* mean, double* var, double* status,
+                                       void* stream);
 
 /*
  * Order statistics for Estimate.estimate_domain (mlmc/estimator.py:275-302): the reference takes

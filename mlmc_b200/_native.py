@@ -16,6 +16,7 @@ _c_i32, _c_i64, _c_dbl, _c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double,
 
 RAW, LEGENDRE, MONOMIAL, FOURIER = 0, 1, 2, 3
 MAX_MOMENTS = 256
+ABI_VERSION = 2
 
 
 class BasisStruct(ctypes.Structure):
@@ -38,7 +39,7 @@ _SIGNATURES = {
     "mlmcb200_moments_accumulate": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_i32, _c_i64,
                                                    _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
     "mlmcb200_resample_indices": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, _c_i64, _c_i64, _c_i32, _c_i32,
-                                                 _c_vp, _c_vp, _c_vp]),
+                                                 _c_i32, _c_vp, _c_vp, _c_vp]),
     "mlmcb200_moments_resampled_workspace_bytes": (_c_i64, [_c_i32, _c_i32, _c_i32]),
     "mlmcb200_moments_accumulate_resampled": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_i32,
                                                              _c_i64, _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_i64,
@@ -50,6 +51,8 @@ _SIGNATURES = {
                                                 _c_vp]),
     "mlmcb200_finalize_levels_batched": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i64, _c_i32, _c_i64, _c_vp,
                                                         _c_vp]),
+    "mlmcb200_level_sums_transform": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i32, _c_i32, _c_vp, _c_i32, _c_vp,
+                                                     _c_i64, _c_vp]),
     "mlmcb200_peer_buffer_bytes": (_c_i64, [_c_i32, _c_i64]),
     "mlmcb200_peer_alloc": (ctypes.c_int, [_c_i64, ctypes.POINTER(_c_vp), ctypes.POINTER(ctypes.c_ubyte)]),
     "mlmcb200_peer_open": (ctypes.c_int, [ctypes.POINTER(ctypes.c_ubyte), ctypes.POINTER(_c_vp)]),
@@ -57,7 +60,7 @@ _SIGNATURES = {
     "mlmcb200_peer_free": (ctypes.c_int, [_c_vp]),
     "mlmcb200_peer_error": (ctypes.c_int, [_c_vp, _c_i32, _c_i64, ctypes.POINTER(_c_i32)]),
     "mlmcb200_allreduce_finalize_levels": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i64, _c_i32, _c_i32, _c_vp, _c_i64,
-                                                          _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
+                                                          _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "mlmcb200_percentile_workspace_bytes": (_c_i64, [_c_i32]),
     "mlmcb200_percentile_stats": (ctypes.c_int, [_c_vp, _c_i64, _c_i64, ctypes.POINTER(_c_dbl), _c_i32, _c_vp, _c_vp,
                                                  _c_i64, _c_vp]),
@@ -101,7 +104,7 @@ def load():
                 fn = getattr(lib, name)
                 fn.restype = res
                 fn.argtypes = args
-            if lib.mlmcb200_abi_version() != 1:
+            if lib.mlmcb200_abi_version() != ABI_VERSION:
                 raise NativeError("libmlmcb200.so ABI version mismatch")
             _lib = lib
     return _lib
@@ -160,9 +163,10 @@ def _chunk_layout(x):
 class LevelAccumulator:
     """Device-side level sums for ``n_levels`` levels of ``K`` statistics each: [L, 2 + 2K] float64."""
 
-    def __init__(self, n_levels, K, device):
+    def __init__(self, n_levels, K, device, zero=True):
         self.n_levels, self.K = n_levels, K
-        self.acc = torch.zeros((n_levels, 2 + 2 * K), dtype=torch.float64, device=device)
+        alloc = torch.zeros if zero else torch.empty
+        self.acc = alloc((n_levels, 2 + 2 * K), dtype=torch.float64, device=device)
 
     def level(self, l):
         return self.acc[l]
@@ -171,20 +175,23 @@ class LevelAccumulator:
         """-> dict of CUDA tensors l_means [L,K], l_vars [L,K], mean [K], var [K] (one launch).
 
         ``peer`` (``mlmc_b200.dist.peer_state()``): the launch first adds the accumulators of all ranks over NVLink
-        peer memory (``mlmcb200_allreduce_finalize_levels``); ``self.acc`` then holds the global sums."""
+        peer memory (``mlmcb200_allreduce_finalize_levels``); ``self.acc`` then holds the global sums.  The result then
+        carries ``status`` (CUDA tensor [1]): 1.0 if the launch gave up waiting for a peer -- ``self.acc`` still holds
+        the LOCAL sums and the caller must reduce another way (``quantity_estimate.estimate_mean`` does)."""
         global launch_count
         dev = self.acc.device
         L, K = self.n_levels, self.K
         out = torch.empty((2 * L + 2, K), dtype=torch.float64, device=dev)
         l_means, l_vars, mean, var = out[:L], out[L:2 * L], out[2 * L], out[2 * L + 1]
         if peer is not None:
+            status = torch.empty(1, dtype=torch.float64, device=dev)
             with torch.cuda.device(dev):
                 _check(load().mlmcb200_allreduce_finalize_levels(
                     _ptr(self.acc), self.acc.stride(0), L, K, peer["rank"], peer["world"], _ptr(peer["ptrs"]),
-                    peer["slot"], _ptr(l_means), _ptr(l_vars), _ptr(mean), _ptr(var), _stream()),
+                    peer["slot"], _ptr(l_means), _ptr(l_vars), _ptr(mean), _ptr(var), _ptr(status), _stream()),
                     "allreduce_finalize_levels")
             launch_count += 1
-            return {"l_means": l_means, "l_vars": l_vars, "mean": mean, "var": var, "packed": out}
+            return {"l_means": l_means, "l_vars": l_vars, "mean": mean, "var": var, "packed": out, "status": status}
         with torch.cuda.device(dev):
             _check(load().mlmcb200_finalize_levels(_ptr(self.acc), self.acc.stride(0), L, K, _ptr(l_means),
                                                    _ptr(l_vars), _ptr(mean), _ptr(var), _stream()),
@@ -269,8 +276,9 @@ def moments_accumulate(basis, x, acc_row, valid=None):
     launch_count += 2
 
 
-def resample_indices(seed, stream_id, n_rows, n_draws, n_rep, device, block_cum=None):
-    """int32 CUDA tensor [n_rep, n_draws] of row numbers drawn uniformly with replacement from ``range(n_rows)``.
+def resample_indices(seed, stream_id, n_rows, n_draws, n_rep, device, block_cum=None, rep_offset=0):
+    """int32 CUDA tensor [n_rep, n_draws] of row numbers drawn uniformly with replacement from ``range(n_rows)``;
+    row b holds the draws of the GLOBAL replicate ``rep_offset + b`` (independent of the grouping into calls).
     ``block_cum`` ([n_rep, P + 1] int64 CUDA, cumulative multinomial block counts) lists each replicate's draws in
     row-block order (L2-friendly gather); reproducible for equal arguments."""
     global launch_count
@@ -283,7 +291,8 @@ def resample_indices(seed, stream_id, n_rows, n_draws, n_rep, device, block_cum=
         n_blocks = block_cum.shape[1] - 1
     with _on_device(idx.device):
         _check(load().mlmcb200_resample_indices(int(seed) & (2 ** 64 - 1), int(stream_id) & (2 ** 64 - 1), n_rows,
-                                                n_draws, n_rep, n_blocks, _ptr(block_cum), _ptr(idx), _stream()),
+                                                n_draws, n_rep, int(rep_offset), n_blocks, _ptr(block_cum), _ptr(idx),
+                                                _stream()),
                "resample_indices")
     launch_count += 1
     return idx
@@ -338,6 +347,23 @@ def finalize_levels_batched(acc):
     with _on_device(acc.device):
         _check(load().mlmcb200_finalize_levels_batched(_ptr(acc), acc.stride(1), L, K, B, acc.stride(0), _ptr(out),
                                                        _stream()), "finalize_levels_batched")
+    launch_count += 1
+    return out
+
+
+def level_sums_transform(acc_in, n_comp, mat_t):
+    """LevelAccumulator whose sums are ``mat_t^T`` applied to the sums of ``acc_in`` (per level and component);
+    mat_t: CUDA float64 ``[K0, K1]``.  Counts are copied, sums of squares become NaN."""
+    global launch_count
+    _require_cuda(mat_t, "mat_t")
+    K0, K1 = mat_t.shape
+    if not mat_t.is_contiguous() or acc_in.K != n_comp * K0:
+        raise NativeError("level_sums_transform: mat_t must be contiguous [K0, K1] with n_comp * K0 == %d" % acc_in.K)
+    out = LevelAccumulator(acc_in.n_levels, n_comp * K1, acc_in.acc.device, zero=False)
+    with _on_device(acc_in.acc.device):
+        _check(load().mlmcb200_level_sums_transform(_ptr(acc_in.acc), acc_in.acc.stride(0), acc_in.n_levels, K0,
+                                                    n_comp, _ptr(mat_t), K1, _ptr(out.acc), out.acc.stride(0),
+                                                    _stream()), "level_sums_transform")
     launch_count += 1
     return out
 

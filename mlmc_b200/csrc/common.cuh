@@ -36,9 +36,6 @@ int check_basis(const mlmcb200_basis_t* b);
 #include "legendre_tables.inc"
 static __constant__ double kLegCoef[MLMCB200_MAX_MOMENTS + 8] = MLMCB200_LEG_COEF_INIT;   // padded: prefetch
 static __constant__ double kLegAlpha[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_ALPHA_INIT;
-// P_i = (kLegA[i] t) P_{i-1} - kLegB[i] P_{i-2}: the un-scaled recurrence with correctly rounded ratios
-static __constant__ double kLegA[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_A_INIT;
-static __constant__ double kLegB[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_B_INIT;
 
 // defined in moments.cu: acc[j] += sum_b partial[b * stride + j], j < len, fixed order (bitwise reproducible)
 int launch_reduce_partials(const double* partial, int n_partials, int64_t stride, int64_t len, double* acc,

@@ -55,18 +55,6 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-// Warp-uniformly predicated DMMA (no branch, no re-convergence barrier around the mma.sync)
-__device__ __forceinline__ void dmma_if(unsigned on, double& c0, double& c1, double a, double b) {
-    asm volatile(
-        "{\n"
-        " .reg .pred p;\n"
-        " setp.ne.u32 p, %4, 0;\n"
-        " @p mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-        "}\n"
-        : "+d"(c0), "+d"(c1)
-        : "d"(a), "d"(b), "r"(on));
-}
-
 // One basis row (R values, zero-padded to 8*nb) into shared memory.  Zero row for a dropped sample.
 __device__ __forceinline__ void write_row(const mlmcb200_basis_t& b, double t, bool good, double* row, int r_pad) {
     const int R = b.size;

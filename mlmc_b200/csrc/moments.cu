@@ -572,12 +572,15 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
 
 // Replicate blockIdx.y, draws 2*g and 2*g+1 of thread g.  Draw j belongs to the row block p with
 // cum[p] <= j < cum[p+1] (block p = rows [p n / P, (p+1) n / P)) and is uniform inside it: floor(r64 * size / 2^64).
+// The Philox counter carries the GLOBAL replicate number (rep_offset + blockIdx.y) and the key only the seed and the
+// stream id, so a replicate's draws do not depend on how the replicates are grouped into launches or sharded over ranks.
 __global__ void resample_indices_kernel(uint64_t seed, uint64_t stream_id, int64_t n_rows, int64_t n_draws,
-                                        int n_blocks, const int64_t* __restrict__ block_cum, int32_t* __restrict__ idx) {
+                                        int n_blocks, const int64_t* __restrict__ block_cum, int32_t* __restrict__ idx,
+                                        uint32_t rep_offset) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int rep = blockIdx.y;
     if (2 * g >= n_draws) return;
-    uint32_t c[4] = {(uint32_t)g, (uint32_t)(g >> 32), (uint32_t)rep, (uint32_t)stream_id};
+    uint32_t c[4] = {(uint32_t)g, (uint32_t)(g >> 32), rep_offset + (uint32_t)rep, (uint32_t)stream_id};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(stream_id >> 32));
     const int64_t* cum = block_cum ? block_cum + (int64_t)rep * (n_blocks + 1) : nullptr;
 #pragma unroll
@@ -684,6 +687,30 @@ __global__ void finalize_levels_kernel(const double* __restrict__ acc, int64_t a
     }
     if (mean) mean[k] = m_tot;
     if (var) var[k] = v_tot;
+}
+
+// Linear map of level sums (products of basis functions are linear combinations of a longer basis of the same family,
+// so the covariance level sums are C . (level sums of 2R-1 moments)): per level l and component m
+//     out[l][2 + m K1 + o] = sum_k mat_t[k K1 + o] * in[l][2 + m K0 + k]      (k ascending: reproducible)
+// counts copied, the sums of squares of `out` are set to NaN (a linear map of sums says nothing about them).
+__global__ void level_sums_transform_kernel(const double* __restrict__ in, int64_t in_stride, int K0, int n_comp,
+                                            const double* __restrict__ mat_t, int K1, double* __restrict__ out,
+                                            int64_t out_stride) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y / n_comp, m = blockIdx.y - l * n_comp;
+    const double* src = in + (int64_t)l * in_stride;
+    double* dst = out + (int64_t)l * out_stride;
+    if (o == 0 && m == 0) {
+        dst[0] = src[0];
+        dst[1] = src[1];
+    }
+    if (o >= K1) return;
+    const double* s = src + 2 + (int64_t)m * K0;
+    double v = 0.0;
+    for (int k = 0; k < K0; ++k) v = fma(__ldg(mat_t + (int64_t)k * K1 + o), s[k], v);
+    const int64_t K = (int64_t)n_comp * K1;
+    dst[2 + (int64_t)m * K1 + o] = v;
+    dst[2 + K + (int64_t)m * K1 + o] = __longlong_as_double(0x7ff8000000000000LL);
 }
 
 }  // namespace
@@ -981,11 +1008,12 @@ extern "C" int mlmcb200_moments_accumulate_resampled(const mlmcb200_basis_t* bas
 }
 
 extern "C" int mlmcb200_resample_indices(uint64_t seed, uint64_t stream_id, int64_t n_rows, int64_t n_draws,
-                                         int32_t n_rep, int32_t n_blocks, const int64_t* block_cum, int32_t* idx,
-                                         void* stream) {
-    MB_REQUIRE(n_rows >= 1 && n_rows <= 0x7fffffffLL && n_draws >= 0 && n_rep >= 1 && n_rep <= 65535 && idx != nullptr,
-               "resample_indices: bad arguments (n_rows=%lld n_draws=%lld n_rep=%d)", (long long)n_rows,
-               (long long)n_draws, n_rep);
+                                         int32_t n_rep, int32_t rep_offset, int32_t n_blocks, const int64_t* block_cum,
+                                         int32_t* idx, void* stream) {
+    MB_REQUIRE(n_rows >= 1 && n_rows <= 0x7fffffffLL && n_draws >= 0 && n_rep >= 1 && n_rep <= 65535 && idx != nullptr &&
+                   rep_offset >= 0,
+               "resample_indices: bad arguments (n_rows=%lld n_draws=%lld n_rep=%d rep_offset=%d)", (long long)n_rows,
+               (long long)n_draws, n_rep, rep_offset);
     MB_REQUIRE(n_blocks >= 1 && n_blocks <= n_rows && (n_blocks == 1 || block_cum != nullptr),
                "resample_indices: n_blocks=%d needs the cumulative block counts", n_blocks);
     if (n_draws == 0) return 0;
@@ -993,7 +1021,8 @@ extern "C" int mlmcb200_resample_indices(uint64_t seed, uint64_t stream_id, int6
     const int64_t pairs = (n_draws + 1) / 2;
     const dim3 grid((unsigned)((pairs + threads - 1) / threads), (unsigned)n_rep);
     resample_indices_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(seed, stream_id, n_rows, n_draws, n_blocks,
-                                                                        n_blocks > 1 ? block_cum : nullptr, idx);
+                                                                        n_blocks > 1 ? block_cum : nullptr, idx,
+                                                                        (uint32_t)rep_offset);
     MB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1027,6 +1056,21 @@ extern "C" int mlmcb200_finalize_levels(const double* acc, int64_t acc_stride, i
     const int threads = 128;
     finalize_levels_kernel<<<(unsigned)((K + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
         acc, acc_stride, n_levels, K, l_means, l_vars, mean, var, 0, 0);
+    MB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mlmcb200_level_sums_transform(const double* acc_in, int64_t in_stride, int32_t n_levels, int32_t K0,
+                                             int32_t n_comp, const double* mat_t, int32_t K1, double* acc_out,
+                                             int64_t out_stride, void* stream) {
+    MB_REQUIRE(acc_in != nullptr && acc_out != nullptr && mat_t != nullptr && n_levels >= 1 && K0 >= 1 && K1 >= 1 &&
+                   n_comp >= 1 && (int64_t)n_levels * n_comp <= 65535 &&
+                   in_stride >= 2 + 2 * (int64_t)n_comp * K0 && out_stride >= 2 + 2 * (int64_t)n_comp * K1,
+               "level_sums_transform: bad arguments");
+    const int threads = 128;
+    const dim3 grid((unsigned)((K1 + threads - 1) / threads), (unsigned)(n_levels * n_comp));
+    level_sums_transform_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(acc_in, in_stride, K0, n_comp, mat_t, K1,
+                                                                            acc_out, out_stride);
     MB_CUDA_OK(cudaGetLastError());
     return 0;
 }

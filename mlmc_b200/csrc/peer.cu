@@ -8,10 +8,14 @@
 // waits until all flags of the current epoch have arrived in its OWN buffer, adds the P slots in rank order (so every
 // rank forms bit-identical sums) and finalizes.  No host synchronisation, capturable in a CUDA graph (the epoch
 // counter lives in device memory), two exchange buffers alternate by epoch parity so a fast rank cannot overwrite data
-// a slow rank still reads.  Waiting is bounded: after ~1 s without the peers' flags the kernel gives up, marks the
-// error word and writes NaN results instead of hanging the GPU.
+// a slow rank still reads.  Waiting is bounded (MLMCB200_PEER_TIMEOUT_MS, default 30 s, measured on %globaltimer): a rank
+// that gives up POISONS the epoch in every peer's header, so a rank that arrives late fails the same epoch instead of
+// returning sums its partner never saw; a failed launch leaves the local sums in `acc` untouched, writes NaN results,
+// sets the sticky error word and `status[0] = 1` -- the host then repeats the reduction with NCCL on every rank
+// (mlmc_b200/quantity/quantity_estimate.py).
 //
 // Intended for the small accumulators of scalar quantities (slot <= 64 k doubles); wide quantities keep NCCL.
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -44,7 +48,15 @@ struct PeerArgs {
     double* l_vars;
     double* mean;
     double* var;
+    double* status;           // [1]: 0 = reduced, 1 = gave up (acc keeps the local sums); may be NULL
+    unsigned long long timeout_ns;
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
 
@@ -54,7 +66,8 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_finalize_kernel(c
     const int tid = threadIdx.x;
     const int world = a.lay.world;
     char* const mine = a.peers[a.rank];
-    unsigned* const header = reinterpret_cast<unsigned*>(mine + a.lay.header_offset_bytes());   // [0] epoch, [1] error
+    // header: [0] epoch, [1] sticky error, [2] epoch some rank gave up on (written by that rank into EVERY buffer)
+    unsigned* const header = reinterpret_cast<unsigned*>(mine + a.lay.header_offset_bytes());
     if (tid == 0) {
         epoch_s = header[0] + 1u;
         failed_s = 0;
@@ -80,25 +93,31 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_finalize_kernel(c
         unsigned* flag = reinterpret_cast<unsigned*>(a.peers[tid] + a.lay.flags_offset_bytes()) + buf * kMaxWorld + a.rank;
         *reinterpret_cast<volatile unsigned*>(flag) = e;
         const unsigned* wait_on = reinterpret_cast<const unsigned*>(mine + a.lay.flags_offset_bytes()) + buf * kMaxWorld + tid;
+        const unsigned long long t0 = globaltimer_ns();
         int spins = 0;
         while (ld_volatile_u32(wait_on) != e) {
             __nanosleep(200);
-            if (++spins > (1 << 22)) {                  // ~1 s
+            if ((++spins & 255) == 0 && globaltimer_ns() - t0 > a.timeout_ns) {
                 failed_s = 1;
                 break;
             }
         }
     }
     __syncthreads();
+    if (failed_s != 0 && tid < world)                   // tell everybody (a late rank must fail this epoch too)
+        *reinterpret_cast<volatile unsigned*>(reinterpret_cast<unsigned*>(a.peers[tid] + a.lay.header_offset_bytes()) + 2) = e;
     __threadfence_system();
+    __syncthreads();
+    if (tid == 0 && ld_volatile_u32(header + 2) == e) failed_s = 1;
+    __syncthreads();
     const bool failed = failed_s != 0;
     // 4. global sums in rank order (identical on every rank), written back to acc
     const double* slots = reinterpret_cast<const double*>(mine) + a.lay.data_offset(buf, 0);
-    for (int64_t i = tid; i < n; i += kPeerThreads) {
+    for (int64_t i = tid; i < n && !failed; i += kPeerThreads) {
         double s = 0.0;
         for (int r = 0; r < world; ++r) s += __ldcv(slots + (int64_t)r * a.lay.slot_doubles + i);
         const int64_t l = i / row, j = i - l * row;
-        a.acc[l * a.acc_stride + j] = failed ? __longlong_as_double(0x7ff8000000000000LL) : s;
+        a.acc[l * a.acc_stride + j] = s;
     }
     __syncthreads();
     // 5. finalize (quantity_estimate.py:72-77, quantity.py:592-593), same operations as finalize_levels_kernel
@@ -107,12 +126,14 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_finalize_kernel(c
         for (int l = 0; l < a.n_levels; ++l) {
             const double* r = a.acc + (int64_t)l * a.acc_stride;
             const double cnt = r[0], s = r[2 + k], sq = r[2 + a.K + k];
-            const double lm = __ddiv_rn(s, cnt);
+            const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+            double lm = __ddiv_rn(s, cnt);
             double lv;
             if (cnt > 1.0)
                 lv = __ddiv_rn(__dsub_rn(sq, __ddiv_rn(__dmul_rn(s, s), cnt)), cnt - 1.0);
             else
                 lv = __longlong_as_double(0x7ff0000000000000LL);
+            if (failed) lm = lv = qnan;
             if (a.l_means) a.l_means[(int64_t)l * a.K + k] = lm;
             if (a.l_vars) a.l_vars[(int64_t)l * a.K + k] = lv;
             m_tot = __dadd_rn(m_tot, lm);
@@ -124,7 +145,18 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_finalize_kernel(c
     if (tid == 0) {
         header[0] = e;
         if (failed) header[1] = 1u;
+        if (a.status) a.status[0] = failed ? 1.0 : 0.0;
     }
+}
+
+unsigned long long peer_timeout_ns() {
+    static unsigned long long cached = 0;
+    if (cached == 0) {
+        const char* e = getenv("MLMCB200_PEER_TIMEOUT_MS");
+        const double ms = e ? atof(e) : 30000.0;
+        cached = (unsigned long long)((ms > 1.0 ? ms : 1.0) * 1e6);
+    }
+    return cached;
 }
 
 }  // namespace
@@ -183,7 +215,7 @@ extern "C" int mlmcb200_peer_error(const void* own_buffer, int32_t world, int64_
 extern "C" int mlmcb200_allreduce_finalize_levels(double* acc, int64_t acc_stride, int32_t n_levels, int64_t K,
                                                   int32_t rank, int32_t world, void* const* peer_buffers,
                                                   int64_t slot_doubles, double* l_means, double* l_vars, double* mean,
-                                                  double* var, void* stream) {
+                                                  double* var, double* status, void* stream) {
     MB_REQUIRE(acc != nullptr && peer_buffers != nullptr && n_levels >= 1 && K >= 1 && acc_stride >= 2 + 2 * K,
                "allreduce_finalize_levels: bad arguments");
     MB_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "allreduce_finalize_levels: rank %d of %d",
@@ -202,6 +234,8 @@ extern "C" int mlmcb200_allreduce_finalize_levels(double* acc, int64_t acc_strid
     a.l_vars = l_vars;
     a.mean = mean;
     a.var = var;
+    a.status = status;
+    a.timeout_ns = peer_timeout_ns();
     peer_allreduce_finalize_kernel<<<1, kPeerThreads, 0, (cudaStream_t)stream>>>(a);
     MB_CUDA_OK(cudaGetLastError());
     return 0;

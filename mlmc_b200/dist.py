@@ -14,7 +14,7 @@ import os
 
 import torch
 
-_state = {"enabled": False, "rank": 0, "world": 1, "group": None, "peer": None}
+_state = {"enabled": False, "rank": 0, "world": 1, "group": None, "peer": None, "peer_fallbacks": 0}
 
 
 def enable(rank=None, world=None, group=None):
@@ -93,6 +93,15 @@ def peer_state(n_doubles=None):
     if peer is not None and n_doubles is not None and n_doubles > peer["slot"]:
         return None
     return peer
+
+
+def note_peer_fallback():
+    """Count an estimate whose fused peer reduce timed out and was redone with NCCL (``peer_fallbacks()``)."""
+    _state["peer_fallbacks"] += 1
+
+
+def peer_fallbacks():
+    return _state["peer_fallbacks"]
 
 
 def peer_error():

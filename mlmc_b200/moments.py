@@ -94,6 +94,29 @@ class Moments:
     def base_moments(self):
         return self
 
+    # ---- products of the basis functions as linear combinations of a longer basis of the same family ----
+    def _product_coefficients(self):
+        """-> (size of the extended basis E, C[R, R, E]) with ``phi_i phi_j = sum_k C[i, j, k] phi_k``; None where
+        the family has no such closed form."""
+        return None
+
+    def product_table(self):
+        """Linearisation of the outer product: ``(extended moments object, C_t)`` with
+        ``C_t[k, i * R + j]`` float64 ``[E, R*R]`` such that ``phi_i(x) phi_j(x) = sum_k C_t[k, i R + j] phi^E_k(x)``
+        for every x -- and, because both sides are NaN for exactly the same samples (the mask depends on the domain
+        only), ``estimate_mean(covariance(q, fn)).mean = C . estimate_mean(moments(q, fn^E)).mean`` level by level.
+        Memoised.  None if the family does not linearise."""
+        hit = getattr(self, "_product_table", None)
+        if hit is None:
+            coef = self._product_coefficients()
+            if coef is None:
+                return None
+            ext, c = coef
+            r = self.size
+            hit = (self.change_size(ext), np.ascontiguousarray(c.reshape(r * r, ext).T))
+            self._product_table = hit
+        return hit
+
     def _eval_device(self, value, size):
         """value: CUDA float64 tensor of any shape -> CUDA tensor ``value.shape + (size,)``."""
         flat = value.reshape(-1)
@@ -142,6 +165,15 @@ class Monomial(Moments):
     def eval(self, i, value):
         return self._eval_all(value, i + 1)[..., i]
 
+    def _product_coefficients(self):
+        """``t^i t^j = t^(i+j)``"""
+        r = self.size
+        ext = 2 * r - 1
+        c = np.zeros((r, r, ext))
+        i, j = np.meshgrid(np.arange(r), np.arange(r), indexing="ij")
+        c[i, j, i + j] = 1.0
+        return ext, c
+
 
 class Fourier(Moments):
     """``1, cos t, sin t, cos 2t, ...`` on ref_domain (0, 2 pi) (``mlmc/moments.py:133-162``)."""
@@ -150,6 +182,46 @@ class Fourier(Moments):
     def __init__(self, size, domain=(0, 2 * np.pi), ref_domain=None, log=False, safe_eval=True):
         self.ref_domain = ref_domain if ref_domain is not None else (0, 2 * np.pi)
         super().__init__(size, domain, log=log, safe_eval=safe_eval)
+
+    def _product_coefficients(self):
+        """Product-to-sum: column 2k-1 = cos(k t), column 2k = sin(k t), column 0 = 1.
+        ``cos a cos b = (cos(a-b) + cos(a+b)) / 2``, ``sin a sin b = (cos(a-b) - cos(a+b)) / 2``,
+        ``sin a cos b = (sin(a+b) + sin(a-b)) / 2``."""
+        r = self.size
+        k_max = r // 2                                   # highest harmonic present (cos only when r is even)
+        # the extended basis must hold cos / sin of 2 k_max, except that sin(2 k_max) never appears with r even
+        ext = 4 * k_max + 1 if r % 2 == 1 else 4 * k_max
+        ext = max(ext, r)
+        c = np.zeros((r, r, ext))
+
+        def col(kind, k):                                # kind 0: cos, 1: sin
+            if k == 0:
+                return (0, 1.0) if kind == 0 else (None, 0.0)
+            if k < 0:
+                idx, sign = col(kind, -k)
+                return idx, (sign if kind == 0 else -sign)
+            return (2 * k - 1 if kind == 0 else 2 * k), 1.0
+
+        def harmonic(i):
+            return (0, 0) if i == 0 else ((i + 1) // 2, 0 if i % 2 == 1 else 1)
+
+        for i in range(r):
+            ki, ti = harmonic(i)
+            for j in range(r):
+                kj, tj = harmonic(j)
+                if ti == 0 and tj == 0:
+                    terms = [(0, ki - kj, 0.5), (0, ki + kj, 0.5)]
+                elif ti == 1 and tj == 1:
+                    terms = [(0, ki - kj, 0.5), (0, ki + kj, -0.5)]
+                elif ti == 1 and tj == 0:
+                    terms = [(1, ki + kj, 0.5), (1, ki - kj, 0.5)]
+                else:
+                    terms = [(1, ki + kj, 0.5), (1, kj - ki, 0.5)]
+                for kind, k, w in terms:
+                    idx, sign = col(kind, k)
+                    if idx is not None:
+                        c[i, j, idx] += w * sign
+        return ext, c
 
 
 class Legendre(Moments):
@@ -164,6 +236,25 @@ class Legendre(Moments):
             self.diff_mat[k, k + 1::2] = 2 * k + 1
         self.diff2_mat = self.diff_mat @ self.diff_mat
         super().__init__(size, domain, log, safe_eval)
+
+    def _product_coefficients(self):
+        """Adams' formula (1878): ``P_m P_n = sum_{r <= min(m, n)} A_r A_{m-r} A_{n-r} / A_{m+n-r}
+        (2m + 2n - 4r + 1) / (2m + 2n - 2r + 1) P_{m+n-2r}``, ``A_r = (2r - 1)!! / r! = binom(2r, r) / 2^r``
+        (the powers of two cancel).  All coefficients are positive and each (m, n) row sums to 1, so the combination
+        is a convex one.  Evaluated in exact rational arithmetic, rounded once."""
+        from fractions import Fraction
+        from math import comb
+        r_size = self.size
+        ext = 2 * r_size - 1
+        a = [comb(2 * k, k) for k in range(ext + 1)]
+        c = np.zeros((r_size, r_size, ext))
+        for m in range(r_size):
+            for n in range(m, r_size):
+                for r in range(m + 1):
+                    val = Fraction(a[r] * a[m - r] * a[n - r] * (2 * m + 2 * n - 4 * r + 1),
+                                   a[m + n - r] * (2 * m + 2 * n - 2 * r + 1))
+                    c[m, n, m + n - 2 * r] = c[n, m, m + n - 2 * r] = float(val)
+        return ext, c
 
     def _apply_matrix(self, value, size, mat):
         table = self._eval_all(value, size)
@@ -234,6 +325,24 @@ class TransformedMoments(Moments):
 
     def basis_struct(self, size=None):
         return self.base_moments().basis_struct()
+
+    def product_table(self):
+        """``(L phi)_i (L phi)_j = sum_ab L_ia L_jb phi_a phi_b``: the base family's table with ``L`` applied on both
+        sides (same extended base moments object)."""
+        hit = getattr(self, "_product_table", None)
+        if hit is None:
+            base = self.base_moments()
+            base_table = base.product_table()
+            if base_table is None:
+                return None
+            ext_fn, c_t = base_table
+            r0, l_mat = base.size, self.transform_matrix()
+            c = c_t.T.reshape(r0, r0, -1)
+            c = np.einsum("ia,abk->ibk", l_mat, c)
+            c = np.einsum("jb,ibk->ijk", l_mat, c)
+            hit = (ext_fn, np.ascontiguousarray(c.reshape(self.size * self.size, -1).T))
+            self._product_table = hit
+        return hit
 
     def _matrix_on(self, device):
         if self._matrix_dev is None or self._matrix_dev.device != device:

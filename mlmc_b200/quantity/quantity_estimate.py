@@ -11,6 +11,10 @@ quantity                               kernels
 ``moments(q, TransformedMoments)``     moments sums of the base functions + DMMA Gram of the differences,
                                        then mean' = L s, sum d'^2 = diag(L G L^T)   (scalar q)
 ``covariance(q, basis)`` (scalar q)    ``mlmcb200_gram_accumulate`` (DMMA), sums and sums of squares
+``covariance(q, basis)``, means only   ``estimate_mean(..., variance=False)``: products of basis functions are linear
+                                       combinations of a longer basis of the same family, so the level sums are
+                                       ``C . (moment sums of 2R-1 functions)``: ``mlmcb200_moments_accumulate`` +
+                                       ``mlmcb200_level_sums_transform`` (any M, also TransformedMoments)
 anything else                          generic: chunk evaluated by device ops, reduced by the RAW kernel
 =====================================  ======================================================================
 
@@ -97,9 +101,10 @@ def covariance(quantity, moments_fn, cov_at_bottom=True):
 class _Plan:
     """How one ``estimate_mean`` call is executed on the device."""
 
-    def __init__(self, quantity):
+    def __init__(self, quantity, variance=True):
         self.quantity = quantity
         self.kind = "raw"
+        self.ext_fn = self.table = None
         self.inner = quantity
         self.fn = None
         self.at_bottom = True
@@ -116,10 +121,31 @@ class _Plan:
             elif quantity._fused_kind == "moments" and base_ok and transformed and scalar \
                     and fn.base_moments().size <= 104:
                 self.kind = "transformed"
+            elif quantity._fused_kind == "covariance" and not variance and self._linearise(fn, scalar):
+                self.kind = "cov_linear"
             elif quantity._fused_kind == "covariance" and scalar and not transformed and fn.size <= 104:
                 self.kind = "covariance"
             if self.kind != "raw":
                 self.inner, self.fn, self.at_bottom = inner, fn, quantity._at_bottom
+
+
+    def _linearise(self, fn, scalar):
+        """Covariance MEANS from the moment sums of the extended basis (``Moments.product_table``) if that basis fits
+        the fused moments kernel."""
+        table = fn.product_table()
+        if table is None or table[0].size > (226 if scalar else 113):
+            return False
+        self.ext_fn, self.table = table
+        return True
+
+
+def _product_table_on(fn, device):
+    """``C_t [E, R*R]`` of ``fn.product_table()`` as a CUDA tensor, cached on the moments object."""
+    hit = getattr(fn, "_product_table_dev", None)
+    if hit is None or hit.device != device:
+        hit = torch.from_numpy(fn.product_table()[1]).to(device)
+        fn._product_table_dev = hit
+    return hit
 
 
 def _level_row_ranges(storage, level_ids):
@@ -147,15 +173,19 @@ def _row_slices(chunks, plan):
                 yield level_id, rows[start:start + step]
 
 
-def estimate_mean(quantity):
-    """MLMC mean estimator (quantity_estimate.py:22-80) -> ``QuantityMean``."""
+def estimate_mean(quantity, variance=True):
+    """MLMC mean estimator (quantity_estimate.py:22-80) -> ``QuantityMean``.
+
+    ``variance=False`` (extension): the caller needs ``mean`` / ``l_means`` only.  For a ``covariance`` quantity this
+    selects the linearised path (table above) -- the reference's own ``construct_density`` reads nothing but the
+    covariance means (estimator.py:311-312); ``l_vars`` / ``var`` of the result are then NaN."""
     cache_clear()
     storage_q = quantity.get_quantity_storage()
     storage = storage_q._storage
     level_ids = storage_q.level_ids()
     n_levels = int(np.max(level_ids)) + 1
     device = q_mod._device()
-    plan = _Plan(quantity)
+    plan = _Plan(quantity, variance)
     multi = _dist.world_size() > 1
     sharded = multi and not getattr(storage, "rows_are_local_shard", False)
     ranges = _level_row_ranges(storage, level_ids) if sharded else None
@@ -186,6 +216,11 @@ def estimate_mean(quantity):
                 _native.gram_accumulate(base_basis, x, gram.level(level_id), mode=1, want_var=False)
             else:
                 _native.gram_accumulate(base_basis, x, gram.level(level_id), mode=0, want_var=False)
+        elif plan.kind == "cov_linear":
+            basis = plan.ext_fn.basis_struct()
+            if acc is None:
+                acc = _native.LevelAccumulator(n_levels, x.shape[0] * basis.size, device)
+            _native.moments_accumulate(basis, x, acc.level(level_id))
         elif plan.kind == "covariance":
             basis = plan.fn.basis_struct()
             if acc is None:
@@ -208,6 +243,8 @@ def estimate_mean(quantity):
             r0 = plan.fn.base_moments().size
             width = r0
             gram = _native.LevelAccumulator(n_levels, r0 * r0, device)
+        elif plan.kind == "cov_linear":
+            width = plan.inner.size() * plan.ext_fn.size
         elif plan.kind == "covariance":
             width = plan.fn.size * plan.fn.size
         else:
@@ -219,7 +256,7 @@ def estimate_mean(quantity):
     if multi:
         # scalar-sized accumulators: the sum over the ranks rides in the finalize launch (NVLink peer memory);
         # anything else: one NCCL all-reduce
-        peer = _dist.peer_state(acc.acc.numel()) if plan.kind != "transformed" else None
+        peer = _dist.peer_state(acc.acc.numel()) if plan.kind not in ("transformed", "cov_linear") else None
         if peer is None:
             _dist.all_reduce_sum(acc.acc)
             if gram is not None:
@@ -227,9 +264,23 @@ def estimate_mean(quantity):
 
     if plan.kind == "transformed":
         acc = _transform_sums(acc, gram, plan.fn, device)
+    elif plan.kind == "cov_linear":
+        acc = _native.level_sums_transform(acc, plan.inner.size(), _product_table_on(plan.fn, device))
     out = acc.finalize(peer=peer)
-    packed_dev = torch.cat([out["packed"].reshape(-1), acc.acc[:, :2].reshape(-1)])
-    packed = _to_host(packed_dev)                                                    # single D2H copy
+    parts = [out["packed"].reshape(-1), acc.acc[:, :2].reshape(-1)]
+    if peer is not None:
+        parts.append(out["status"])                      # rides in the same copy
+    packed = _to_host(torch.cat(parts))                                              # single D2H copy
+    if peer is not None:
+        if packed[-1] != 0.0:
+            # The fused reduce gave up waiting for a peer (skewed ranks).  A rank that gives up poisons the epoch for
+            # the others, so every rank lands here; the local sums are intact: reduce them with NCCL and finalize.
+            _dist.note_peer_fallback()
+            _dist.all_reduce_sum(acc.acc)
+            out = acc.finalize()
+            packed = _to_host(torch.cat([out["packed"].reshape(-1), acc.acc[:, :2].reshape(-1)]))
+        else:
+            packed = packed[:-1]
     L, K = acc.n_levels, acc.K
     l_means = packed[:L * K].reshape(L, K)
     l_vars = packed[L * K:2 * L * K].reshape(L, K)
@@ -245,6 +296,12 @@ def estimate_mean(quantity):
         l_vars = l_vars.reshape(L, -1, r).transpose(0, 2, 1).reshape(L, K)
         mean = mean.reshape(-1, r).T.reshape(K)
         var = var.reshape(-1, r).T.reshape(K)
+    elif plan.kind == "cov_linear" and not plan.at_bottom:
+        rr = plan.fn.size ** 2
+        l_means = l_means.reshape(L, -1, rr).transpose(0, 2, 1).reshape(L, K)
+        l_vars = l_vars.reshape(L, -1, rr).transpose(0, 2, 1).reshape(L, K)
+        mean = mean.reshape(-1, rr).T.reshape(K)
+        var = var.reshape(-1, rr).T.reshape(K)
     elif plan.kind == "covariance" and not plan.at_bottom:
         pass        # scalar input quantity: both layouts coincide
     return q_mod.QuantityMean(quantity.qtype, l_means=l_means, l_vars=l_vars, n_samples=n_samples,
@@ -283,8 +340,12 @@ def bootstrap_moments(quantity, moments_fn, sample_vector, n_subsamples, seed=No
     b_lo, b_hi = _dist.shard_range(n_total) if shard_replicates else (0, n_total)
     B = b_hi - b_lo
     seed = int(seed) if seed is not None else int(np.random.SeedSequence().entropy % (1 << 62))
-    host_rng = np.random.default_rng([seed, b_lo])
-    seed_dev = seed + b_lo                                          # replicate b draws with key (seed + b, ...)
+    # Every random choice is keyed by (seed, GLOBAL replicate number): the host draws (hypergeometric chunk sizes,
+    # multinomial block counts) by one generator per replicate, the row numbers by Philox with the replicate number in
+    # the counter -- so the replicates do not depend on the world size or on how they are grouped into launches.
+    host_rngs = [np.random.default_rng([seed, b_lo + b]) for b in range(B)]
+    if sum(n_collected[l] for l in level_ids) == 0:                  # the same on every rank: no rank is left behind
+        raise Exception("All samples were masked")
 
     width = 2 + 2 * quantity.size() * basis.size
     acc = torch.zeros((B, n_levels, width), dtype=torch.float64, device=device)
@@ -305,8 +366,8 @@ def bootstrap_moments(quantity, moments_fn, sample_vector, n_subsamples, seed=No
         if n_chunk >= n_left:                                          # last (or only) chunk takes what is left
             sizes = k_left.copy()
         else:
-            sizes = np.array([scipy.stats.hypergeom(n_left, int(k), n_chunk).rvs(random_state=host_rng) if k > 0
-                              else 0 for k in k_left], dtype=np.int64)
+            sizes = np.array([scipy.stats.hypergeom(n_left, int(k), n_chunk).rvs(random_state=host_rngs[b]) if k > 0
+                              else 0 for b, k in enumerate(k_left)], dtype=np.int64)
         remaining[level_id] = (k_left - sizes, n_left - n_chunk)
         valid = _native.sample_mask(basis, x) if x.shape[0] > 1 else None
         level_acc = acc[:, level_id]
@@ -320,11 +381,13 @@ def bootstrap_moments(quantity, moments_fn, sample_vector, n_subsamples, seed=No
             cum = None
             if n_blocks > 1 and k >= 4096 * n_blocks:
                 edges = (np.arange(n_blocks + 1, dtype=np.int64) * n_chunk) // n_blocks
-                counts = host_rng.multinomial(k, np.diff(edges) / n_chunk, size=b1 - b0)
+                p_block = np.diff(edges) / n_chunk
+                counts = np.stack([host_rngs[b].multinomial(k, p_block) for b in range(b0, b1)])
                 cum_h = np.zeros((b1 - b0, n_blocks + 1), dtype=np.int64)
                 np.cumsum(counts, axis=1, out=cum_h[:, 1:])
                 cum = torch.from_numpy(cum_h).to(device)
-            return _native.resample_indices(seed_dev + b0, stream_id, n_chunk, k, b1 - b0, device, block_cum=cum)
+            return _native.resample_indices(seed, stream_id, n_chunk, k, b1 - b0, device, block_cum=cum,
+                                            rep_offset=b_lo + b0)
 
         if np.all(sizes == sizes[0]):
             k = int(sizes[0])
@@ -346,8 +409,6 @@ def bootstrap_moments(quantity, moments_fn, sample_vector, n_subsamples, seed=No
                 if return_indices:
                     indices[level_id].append((offsets[level_id], b_lo + b, idx))
         offsets[level_id] += n_chunk
-    if B > 0 and not seen_rows:
-        raise Exception("All samples were masked")
 
     L, K = n_levels, (width - 2) // 2
     packed = torch.cat([_native.finalize_levels_batched(acc), acc[:, :, 0].reshape(B, L)], dim=1) if B > 0 else \

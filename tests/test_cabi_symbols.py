@@ -21,7 +21,7 @@ def test_header_symbols_exported():
     for name in names:
         assert hasattr(lib, name), name
     assert set(names) == set(_native.EXPORTED_SYMBOLS)
-    assert lib.mlmcb200_abi_version() == 1
+    assert lib.mlmcb200_abi_version() == 2
 
 
 def test_struct_layout_matches_header():

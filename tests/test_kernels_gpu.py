@@ -27,13 +27,22 @@ def to_struct(b: orc.Basis):
     return native().make_basis(KINDS[b.kind], b.size, b.domain, b.ref_domain, b.log, b.safe_eval)
 
 
-def rel_close(got, want, rtol, atol_scale=1e-15):
+def rel_close(got, want, rtol, atol_scale=1e-15, per_level=False):
+    """|got - want| <= rtol |want| + atol_scale * scale.  ``scale`` is the largest finite |want| -- of the whole array,
+    or, with ``per_level`` (arrays ``[L, K]``: one row per level), of each row separately: the variances of the fine
+    levels are orders of magnitude below level 0's and must not hide behind its scale."""
     got, want = np.asarray(got, dtype=float), np.asarray(want, dtype=float)
     assert got.shape == want.shape, (got.shape, want.shape)
-    scale = np.max(np.abs(want[np.isfinite(want)])) if np.isfinite(want).any() else 1.0
-    ok = np.isclose(got, want, rtol=rtol, atol=atol_scale * max(scale, 1e-300), equal_nan=True)
-    assert ok.all(), "max abs err %.3e (scale %.3e) at %s" % (
-        np.nanmax(np.abs(got - want)[~ok]), scale, np.argwhere(~ok)[:5].tolist())
+    finite = np.where(np.isfinite(want), np.abs(want), 0.0)
+    if per_level and want.ndim >= 2:
+        scale = finite.reshape(want.shape[0], -1).max(axis=1).reshape((-1,) + (1,) * (want.ndim - 1))
+    else:
+        scale = finite.max() if finite.size else 1.0
+    tol = rtol * np.abs(want) + atol_scale * np.maximum(scale, 1e-300)
+    with np.errstate(invalid="ignore"):
+        ok = (np.abs(got - want) <= tol) | (got == want) | (np.isnan(got) & np.isnan(want))
+    assert ok.all(), "max abs err %.3e (scale %s) at %s" % (
+        np.nanmax(np.abs(got - want)[~ok]), np.ravel(scale)[:8], np.argwhere(~ok)[:5].tolist())
 
 
 def run_moments(basis, levels, chunk_rows=None):
@@ -59,7 +68,7 @@ def run_moments(basis, levels, chunk_rows=None):
 # ------------------------------------------------------------------------------------------------------
 def test_library_loads_on_gpu():
     nat = native()
-    assert nat.load().mlmcb200_abi_version() == 1
+    assert nat.load().mlmcb200_abi_version() == nat.ABI_VERSION == 2
     assert nat.sm_count() > 0
 
 
@@ -533,6 +542,10 @@ def test_resample_indices_blocks_and_uniformity():
     other = nat.resample_indices(6, 1, n_rows, k, n_rep, dev())
     assert torch.equal(plain, again) and not torch.equal(plain, other)
     assert not torch.equal(plain[0], plain[1])                         # replicates differ
+    # a replicate's rows depend on (seed, its GLOBAL number) only, not on the grouping into calls
+    tail = nat.resample_indices(5, 1, n_rows, k, 2, dev(), rep_offset=1)
+    assert torch.equal(tail, plain[1:])
+    assert not torch.equal(nat.resample_indices(6, 1, n_rows, k, 1, dev()), plain[1:2])     # seed+1 != replicate+1
     h = plain.cpu().numpy()
     assert h.min() >= 0 and h.max() < n_rows
     # uniform draws: mean n/2 +- 5 sigma, decile counts within 5 sigma of k/10

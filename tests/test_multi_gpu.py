@@ -22,7 +22,7 @@ def _free_port():
 def _worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      LOCAL_RANK=str(rank))
+                      LOCAL_RANK=str(rank), MLMCB200_PEER_TIMEOUT_MS="300")
     import torch
     from mlmc_b200 import dist
     from mlmc_b200.moments import Legendre
@@ -53,7 +53,22 @@ def _worker(rank, world, port, out_dir):
             qm2 = qe.estimate_mean(qe.moments(value, Legendre(12, tuple(g["A_domain"]))))
             cm2 = qe.estimate_mean(qe.covariance(value, Legendre(8, tuple(g["A_domain"]))))
         peer = dict(p_l_means=qm2.l_means, p_l_vars=qm2.l_vars, p_n=qm2.n_samples, p_cov=cm2.mean, p_cov_var=cm2.var,
-                    p_err=int(dist.peer_error()))
+                    p_err=int(dist.peer_error()), p_fallbacks=dist.peer_fallbacks())
+        # skewed ranks: rank 1 reaches the fused reduce 1.5 s after rank 0 gave up on it (the time-out is 300 ms here):
+        # both must notice, repeat the reduction with NCCL and return the right numbers
+        import time
+        torch.cuda.synchronize()
+        import torch.distributed as td_
+        td_.barrier()
+        if rank == 1:
+            time.sleep(1.5)
+        qm3 = qe.estimate_mean(qe.moments(value, Legendre(12, tuple(g["A_domain"]))))
+        qm4 = qe.estimate_mean(qe.moments(value, Legendre(12, tuple(g["A_domain"]))))       # next epoch works again
+        peer.update(s_l_means=qm3.l_means, s_l_vars=qm3.l_vars, s_n=qm3.n_samples, s_fallbacks=dist.peer_fallbacks(),
+                    s2_l_means=qm4.l_means, s2_fallbacks=dist.peer_fallbacks())
+    # linearised covariance means (moment sums of the 2R-1 basis, all-reduce, C applied once)
+    lin = qe.estimate_mean(qe.covariance(value, Legendre(8, tuple(g["A_domain"]))), variance=False)
+    peer["lin_cov"] = lin.mean
     np.savez(os.path.join(out_dir, "r%d.npz" % rank), l_means=qm.l_means, l_vars=qm.l_vars, n=qm.n_samples,
              n_rm=qm.n_rm_samples, cov=cm.mean, cov_var=cm.var, bs_l_means=bs["l_means"], bs_n=bs["n_samples"],
              bs1_l_means=bs1["l_means"] if bs1 is not None else np.zeros(0), peer_ok=int(peer_ok), **peer)
@@ -78,11 +93,12 @@ def test_two_gpu_sharded_estimate(tmp_path, golden):
         assert np.allclose(out["l_vars"], g["A_leg_l_vars"], rtol=1e-10, atol=1e-15)
         assert np.allclose(out["cov"], g["A_cov_mean"], rtol=1e-8, atol=1e-14)
         assert np.allclose(out["cov_var"], g["A_cov_var"], rtol=1e-8, atol=1e-16)
+        assert np.allclose(out["lin_cov"], g["A_cov_mean"], rtol=1e-8, atol=1e-14)
     a, b = (np.load(os.path.join(str(tmp_path), "r%d.npz" % r)) for r in range(2))
     assert a["bs_l_means"].shape == (5, 3, 6) and np.array_equal(a["bs_l_means"], b["bs_l_means"])
     assert np.array_equal(a["bs_n"], b["bs_n"]) and np.all(a["bs_n"].sum(axis=1) > 0)
-    # replicates 0..1 live on rank 0 in both runs (same keys): identical; the rest are valid but differently seeded
-    assert np.array_equal(a["bs_l_means"][:2], a["bs1_l_means"][:2])
+    # replicates are keyed by (seed, global replicate number): sharded over two ranks or not, the same five replicates
+    assert np.array_equal(a["bs_l_means"], a["bs1_l_means"])
     assert np.all(np.abs(a["bs_l_means"][:, :, 0].sum(axis=1) - 1.0) < 1e-12)
     # fused peer-memory reduce: same numbers as the NCCL route (two ranks: a + b either way), no time-out
     assert int(a["peer_ok"]) == int(b["peer_ok"])
@@ -92,5 +108,10 @@ def test_two_gpu_sharded_estimate(tmp_path, golden):
             assert np.array_equal(out["p_n"], out["n"])
             assert np.array_equal(out["p_l_means"], out["l_means"]) and np.array_equal(out["p_l_vars"], out["l_vars"])
             assert np.array_equal(out["p_cov"], out["cov"]) and np.array_equal(out["p_cov_var"], out["cov_var"])
+            # the skewed call: timed out on rank 0, poisoned for rank 1, both redone with NCCL -> same numbers
+            assert int(out["p_fallbacks"]) == 0 and int(out["s_fallbacks"]) == 1 and int(out["s2_fallbacks"]) == 1
+            assert np.array_equal(out["s_n"], out["n"])
+            assert np.array_equal(out["s_l_means"], out["l_means"]) and np.array_equal(out["s_l_vars"], out["l_vars"])
+            assert np.array_equal(out["s2_l_means"], out["l_means"])
     else:
         print("peer-memory reduce not available on this box (cudaIpc); NCCL route tested only")
