@@ -9,12 +9,17 @@ Metric: level sample.moments / s = sum_l N_l * M * R / time.
   python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (CUDA kernels through the C ABI)
   python bench.py --impl reference [...]                        the reference's CPU algorithm (oracle port) on host cores
 
-``value``  : inputs resident in HBM, all launches of one step captured in a CUDA graph, timed with CUDA events.
+``value``  : inputs resident in HBM, all launches of one step captured in a CUDA graph, timed with CUDA events; the
+             D2H of the result and the host regression / allocation of every step are inside the timed region.
 ``e2e``    : the same estimate through the public API (``Estimate.estimate_diff_vars_regression`` + allocation)
              on a pinned-host ``Memory`` storage: H2D copies of every level and the D2H of the result are inside
              the timed region, every step.
-Weak scaling under torchrun: every rank holds 1e7 samples per level (global N = world * 1e7 per level), level sums
-are combined by one NCCL all-reduce per step.
+``configs``: the other BASELINE.json configs in the same JSON line -- cfg3 (covariance, Legendre 100, 1e9 samples in
+             total = STRONG scaling over the ranks, DMMA roofline), and at N = 1 cfg4 (max-ent fit ms), cfg1, cfg5.
+Weak scaling of the headline under torchrun: every rank holds 1e7 samples per level (global N = world * 1e7 per level),
+level sums are combined inside the finalize launch over NVLink peer memory (NCCL all-reduce as the fallback).
+Before anything is timed the golden case of the unmodified reference (tests/golden/estimates.npz) is estimated, sharded
+over the ranks, and compared with the stored reference outputs; a mismatch aborts the run.
 """
 import argparse
 import json
@@ -187,22 +192,193 @@ def make_levels_on_device(torch, device, n_rows, seed_base):
     return levels
 
 
-def run_gpu_arm(args):
-    import torch
-    import torch.distributed as td
-    from mlmc_b200 import _native as nat, dist as mdist
-    from mlmc_b200.moments import Legendre
+def synth_pairs_on_device(torch, device, n_rows, h_fine, h_coarse, seed, piece=25_000_000, lognormal=False):
+    """One level of (fine, coarse) rows [n, 2, 1] generated piecewise on the device (bounded temporaries)."""
+    rows = torch.empty((n_rows, 2, 1), dtype=torch.float64, device=device)
+    gen = torch.Generator(device=device).manual_seed(seed)
+    for lo in range(0, n_rows, piece):
+        hi = min(n_rows, lo + piece)
+        x = torch.randn(hi - lo, generator=gen, device=device, dtype=torch.float64)
+        if lognormal:
+            x = torch.exp(x)
+        root = torch.sqrt(1e-4 + x.abs())
+        rows[lo:hi, 0, 0] = x + h_fine * root
+        if h_coarse is None:
+            rows[lo:hi, 1, 0] = 0.0
+        else:
+            rows[lo:hi, 1, 0] = x + h_coarse * root
+        del x, root
+    return rows
+
+
+class Ctx:
+    """What the legs share: torch / native modules, rank layout, helpers for device timing over all ranks."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as td
+        from mlmc_b200 import _native as nat, dist as mdist
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+        self.torch, self.td, self.nat, self.mdist, self.args = torch, td, nat, mdist, args
+        self.rank, self.world, self.local = mdist.init_from_env()
+        torch.cuda.set_device(self.local)
+        self.device = torch.device("cuda", self.local)
+        nat.load()
+        self.peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                self.peaks = json.load(f)
+        except OSError:
+            pass
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.td.barrier()
+
+    def max_over_ranks(self, value):
+        t = self.torch.tensor([float(value)], dtype=self.torch.float64, device=self.device)
+        if self.world > 1:
+            self.td.all_reduce(t, op=self.td.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, reps, warmup=1):
+        """ms per call of ``fn`` (enqueues work on the current stream): CUDA events around ``reps`` calls, barrier +
+        synchronize on both sides, max over ranks."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / reps
+
+    def timed_wall(self, fn, reps, warmup=1):
+        """The same for calls that end with their own device -> host copy (public API): wall clock, max over ranks."""
+        res = None
+        for _ in range(warmup):
+            res = fn()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            res = fn()
+        self.torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+        return self.max_over_ranks(ms), res
+
+
+def scalar_quantity(levels, steps, n_ops=None):
     from mlmc_b200.sample_storage import Memory
     from mlmc_b200.quantity.quantity import make_root_quantity
     from mlmc_b200.quantity.quantity_spec import QuantitySpec
-    from mlmc_b200.estimator import Estimate, estimate_n_samples_for_target_variance
+    spec = [QuantitySpec(name="v", unit="", shape=(1, 1), times=[0.0], locations=["0"])]
+    storage = Memory.from_arrays(levels, level_parameters=[[h] for h in steps], n_ops=n_ops, result_format=spec)
+    return storage, make_root_quantity(storage, spec)["v"][0.0]["0"][0, 0]
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
-    rank, world, local = mdist.init_from_env()
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    nat.load()
+
+def max_rel(got, want):
+    got, want = np.asarray(got, dtype=float), np.asarray(want, dtype=float)
+    scale = float(np.max(np.abs(want))) + 1e-300
+    return float(np.max(np.abs(got - want) / (np.abs(want) + 1e-12 * scale)))
+
+
+def startup_parity_check(ctx):
+    """Before anything is timed: the golden 3-level case of tests/golden/estimates.npz (inputs + outputs of the UNMODIFIED
+    reference) estimated through the public API, rows sharded over the ranks when N > 1, against the stored reference
+    results: level means / variances rel <= 1e-10 (scaled per level), covariance <= 1e-8, counts exact."""
+    from mlmc_b200.moments import Legendre
+    from mlmc_b200.quantity import quantity_estimate as qe
+    g = np.load(os.path.join(ROOT, "tests", "golden", "estimates.npz"))
+    levels = [g["A_rows%d" % l] for l in range(3)]
+    _storage, value = scalar_quantity(levels, [float(h) for h in g["A_steps"]])
+    domain = tuple(g["A_domain"])
+    qm = qe.estimate_mean(qe.moments(value, Legendre(12, domain)))
+    cm = qe.estimate_mean(qe.covariance(value, Legendre(8, domain)))
+    lin = qe.estimate_mean(qe.covariance(value, Legendre(8, domain)), variance=False)
+
+    def per_level(got, want):
+        scale = np.max(np.abs(want), axis=1, keepdims=True)
+        return float(np.max(np.abs(got - want) / (np.abs(want) + 1e-3 * scale)))
+    out = {"l_means": per_level(qm.l_means, g["A_leg_l_means"]), "l_vars": per_level(qm.l_vars, g["A_leg_l_vars"]),
+           "cov_mean": per_level(cm.mean, g["A_cov_mean"]), "cov_var": per_level(cm.var, g["A_cov_var"]),
+           "cov_mean_linearised": per_level(lin.mean, g["A_cov_mean"]),
+           "counts_exact": bool(np.array_equal(qm.n_samples, g["A_leg_n"]) and
+                                np.array_equal(qm.n_rm_samples, g["A_leg_n_rm"]) and
+                                np.array_equal(cm.n_samples, g["A_leg_n"]))}
+    ok = (out["counts_exact"] and out["l_means"] <= 1e-10 and out["l_vars"] <= 1e-10 and out["cov_mean"] <= 1e-8 and
+          out["cov_var"] <= 1e-8 and out["cov_mean_linearised"] <= 1e-8 and qm.mean[0] == 1.0 and qm.var[0] == 0.0)
+    if not ok:
+        raise SystemExit("bench.py: start-up parity check against the reference's golden outputs FAILED on rank %d: %s"
+                         % (ctx.rank, out))
+    out["against"] = "tests/golden/estimates.npz (outputs of the unmodified reference), rows sharded over %d rank(s)" \
+        % ctx.world
+    return out
+
+
+def strict_peer_check(ctx, basis, views, acc):
+    """The fused peer-memory reduce must reproduce, BIT FOR BIT, the rank-ordered fp64 sum of the per-rank accumulators
+    (gathered with NCCL) and the finalize of that sum.  All ranks must agree, else the bench stays on NCCL."""
+    torch, td, nat, mdist = ctx.torch, ctx.td, ctx.nat, ctx.mdist
+    acc.acc.zero_()
+    for l in range(N_LEVELS):
+        nat.moments_accumulate(basis, views[l], acc.level(l))
+    local = acc.acc.clone()
+    gathered = [torch.empty_like(local) for _ in range(ctx.world)]
+    td.all_gather(gathered, local)
+    want = torch.zeros_like(local)
+    for part in gathered:                                    # rank order, like the kernel
+        want = want + part
+    ref = nat.LevelAccumulator(N_LEVELS, N_MOMENTS, ctx.device)
+    ref.acc.copy_(want)
+    want_out = ref.finalize()["packed"].clone()
+    got = acc.finalize(peer=mdist.peer_state(acc.acc.numel()))
+    torch.cuda.synchronize()
+    good = (torch.equal(acc.acc, want) and torch.equal(got["packed"], want_out) and float(got["status"].item()) == 0.0
+            and not mdist.peer_error())
+    flag = torch.tensor([int(good)], device=ctx.device)
+    td.all_reduce(flag, op=td.ReduceOp.MIN)
+    return bool(flag.item())
+
+
+def host_topology(ctx):
+    """NUMA placement of this rank and a host-memory copy bandwidth (all ranks copying at once): what the pinned
+    host -> device stream of e2e competes for."""
+    torch = ctx.torch
+    info = {"numa_nodes_online": None, "gpu_numa_node": None, "cpus_allowed": len(os.sched_getaffinity(0))}
+    try:
+        with open("/sys/devices/system/node/online") as f:
+            info["numa_nodes_online"] = f.read().strip()
+        props = torch.cuda.get_device_properties(ctx.local)
+        bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            info["gpu_numa_node"] = int(f.read().strip())
+    except (OSError, ValueError, AttributeError):
+        pass
+    src = torch.empty(32 << 20, dtype=torch.float64).pin_memory()                 # 256 MB
+    dst = torch.empty_like(src)
+    src.fill_(1.0)
+    dst.copy_(src)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        dst.copy_(src)
+    gbs = 3 * 2 * src.numel() * 8 / (time.perf_counter() - t0) / 1e9            # read + write
+    info["host_copy_gbs_per_rank_all_ranks_copying"] = -ctx.max_over_ranks(-gbs)   # the slowest rank's
+    info["host_copy_threads"] = torch.get_num_threads()
+    return info
+
+
+# ------------------------------------------------------------------------------------------------ cfg2 (headline)
+def bench_cfg2(ctx, line_out):
+    torch, td, nat, mdist, args = ctx.torch, ctx.td, ctx.nat, ctx.mdist, ctx.args
+    from mlmc_b200.moments import Legendre
+    from mlmc_b200.estimator import Estimate, estimate_n_samples_for_target_variance
+    rank, world, local, device = ctx.rank, ctx.world, ctx.local, ctx.device
     n_rows = args.samples_per_level
     steps = level_steps()
     n_ops = [n_ops_of(h) for h in steps]
@@ -214,18 +390,14 @@ def run_gpu_arm(args):
 
     # ---------------- device-resident step: one CUDA graph = zero, 3 x (moments + reduce), finalize ----------
     acc = nat.LevelAccumulator(N_LEVELS, N_MOMENTS, device)
-    views = []
-    for l, rows in enumerate(levels):
-        views.append(rows.permute(2, 0, 1))
+    views = [rows.permute(2, 0, 1) for rows in levels]
     result = {}
-
     # the levels are independent until the finalize: each runs on its own stream (a fork / join inside the graph), so
     # the ramp and tail of one level's one-wave launch overlap the next level's kernel
     level_streams = [torch.cuda.Stream(device) for _ in range(N_LEVELS - 1)]
     concurrent_levels = os.environ.get("BENCH_CONCURRENT_LEVELS", "1") != "0"
-
     # N > 1: the sum of the level accumulators over the ranks rides in the finalize launch (NVLink peer memory,
-    # mlmcb200_allreduce_finalize_levels); checked against the NCCL all-reduce once, NCCL stays the fallback
+    # mlmcb200_allreduce_finalize_levels) once it has passed the strict check; NCCL stays the fallback
     use_peer = [False]
 
     def enqueue_step():
@@ -254,19 +426,10 @@ def run_gpu_arm(args):
             td.all_reduce(acc.acc)
         result.update(acc.finalize(peer=mdist.peer_state(acc.acc.numel()) if use_peer[0] else None))
 
+    peer_checked = None
     if world > 1 and os.environ.get("BENCH_PEER_REDUCE", "1") != "0" and mdist.enable_peer_reduce():
-        enqueue_step()
-        torch.cuda.synchronize()
-        want = result["packed"].clone()
-        use_peer[0] = True
-        enqueue_step()
-        torch.cuda.synchronize()
-        # (more than two ranks: NCCL adds in its own order, the peer kernel in rank order -- rounding-level differences
-        # in the sums, amplified by the cancellation in the variances)
-        good = torch.tensor([int(torch.allclose(result["packed"], want, rtol=1e-8, atol=1e-14, equal_nan=False)
-                                 and not mdist.peer_error())], device=device)
-        td.all_reduce(good, op=td.ReduceOp.MIN)
-        use_peer[0] = bool(good.item())
+        peer_checked = strict_peer_check(ctx, basis, views, acc) and strict_peer_check(ctx, basis, views, acc)
+        use_peer[0] = peer_checked
         if not use_peer[0]:
             mdist.disable_peer_reduce()                  # the public API (e2e pass) stays on NCCL as well
     side = torch.cuda.Stream(device)
@@ -274,9 +437,8 @@ def run_gpu_arm(args):
         enqueue_step()                                   # warm up allocations outside the capture
         torch.cuda.synchronize()
         graph = None
-        # N > 1: plain stream launches by default; BENCH_GRAPH_MULTI=1 captures the all-reduce with the kernels (NCCL
-        # supports stream capture; measured 0.653 vs 0.659 ms per step at N = 2 -- not worth a capture failure mode)
-        # (with the peer-memory reduce the step holds no NCCL call at all and is captured like the single-GPU step)
+        # N > 1 on NCCL: plain stream launches by default (BENCH_GRAPH_MULTI=1 captures the all-reduce with the kernels);
+        # with the peer-memory reduce the step holds no NCCL call at all and is captured like the single-GPU step
         if world == 1 or use_peer[0] or os.environ.get("BENCH_GRAPH_MULTI", "0") == "1":
             if world > 1:
                 enqueue_step()                           # a second eager step: NCCL sets up its channels lazily
@@ -294,19 +456,35 @@ def run_gpu_arm(args):
         else:
             enqueue_step()
 
-    def host_tail():
-        """level-variance regression + allocation on the [L, R] result (tiny host math, as in the reference)."""
-        packed = result["packed"].cpu().numpy()
-        l_vars = packed[N_LEVELS:2 * N_LEVELS]
-        reg = Estimate(None, None)._all_moments_variance_regression(l_vars, np.array(steps))
-        return estimate_n_samples_for_target_variance(TARGET_VAR, reg, n_ops, N_LEVELS)
+    # The tail of the workload -- device -> host copy of the [2L+2, R] result, level-variance regression and n_samples
+    # allocation (tiny host math, as in the reference) -- is INSIDE the timed region: the copy of step k is enqueued
+    # behind its kernels and its host math runs while the kernels of step k + 1 execute.
+    packed_shape = (2 * N_LEVELS + 2, N_MOMENTS)
+    tail_host = [torch.empty(packed_shape, dtype=torch.float64).pin_memory() for _ in range(2)]
+    tail_done = [torch.cuda.Event() for _ in range(2)]
+    regress = Estimate(None, None)._all_moments_variance_regression
+    steps_arr = np.array(steps)
 
-    for _ in range(max(args.warmup, 3)):
-        device_step()
-    n_estimated = host_tail()
-    torch.cuda.synchronize()
-    if world > 1:
-        td.barrier()
+    def enqueue_tail(k):
+        tail_host[k % 2].copy_(result["packed"], non_blocking=True)
+        tail_done[k % 2].record()
+
+    def host_tail(k):
+        tail_done[k % 2].synchronize()
+        l_vars = tail_host[k % 2].numpy()[N_LEVELS:2 * N_LEVELS]
+        return estimate_n_samples_for_target_variance(TARGET_VAR, regress(l_vars, steps_arr), n_ops, N_LEVELS)
+
+    def run_steps(n):
+        n_est = None
+        for k in range(n):
+            device_step()
+            enqueue_tail(k)
+            if k > 0:
+                n_est = host_tail(k - 1)
+        return host_tail(n - 1) if n > 0 else n_est
+
+    n_estimated = run_steps(max(args.warmup, 3))
+    ctx.barrier()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -327,31 +505,22 @@ def run_gpu_arm(args):
     kernel_ms = float(np.min(kernel_ms))
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
-        td.barrier()
-    torch.cuda.synchronize()
+    ctx.barrier()
     e0.record()
-    for _ in range(args.steps):
-        device_step()
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        td.barrier()
-    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-    if world > 1:
-        td.all_reduce(ms_total, op=td.ReduceOp.MAX)
-    ms_per_step = float(ms_total.item()) / args.steps
+    n_estimated = run_steps(args.steps)
+    e1.record()                                            # after the last step's host tail has finished
+    ctx.barrier()
+    ms_per_step = ctx.max_over_ranks(e0.elapsed_time(e1)) / args.steps
     value = units_per_rank * world / (ms_per_step * 1e-3)
+    peer_errors = bool(use_peer[0] and mdist.peer_error())
 
     # ---------------- end to end through the public API, host buffers ----------------
     host_levels = [lv.cpu() for lv in levels]
-    spec = [QuantitySpec(name="v", unit="", shape=(1, 1), times=[0.0], locations=["0"])]
-    storage = Memory.from_arrays(host_levels, level_parameters=[[h] for h in steps], n_ops=n_ops, result_format=spec)
+    storage, value_q = scalar_quantity(host_levels, steps, n_ops)
     storage.rows_are_local_shard = True      # weak scaling: every rank owns n_rows samples per level
     storage.resident_fraction = 0.0          # never keep a device copy: every step streams host -> HBM
     storage.device_chunk_bytes = 32 << 20    # 32 MB chunks, copy stream overlapped with the kernels
     del host_levels
-    value_q = make_root_quantity(storage, spec)["v"][0.0]["0"][0, 0]
     estimator = Estimate(value_q, storage, moments_fn)
     d2h_bytes = (2 * N_LEVELS + 2) * N_MOMENTS * 8 + N_LEVELS * 16
 
@@ -360,20 +529,9 @@ def run_gpu_arm(args):
         variances, ops = estimator.estimate_diff_vars_regression(None)
         return estimate_n_samples_for_target_variance(TARGET_VAR, variances, ops, N_LEVELS)
 
-    for _ in range(2):
-        n_est_e2e = e2e_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        td.barrier()
-    t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        n_est_e2e = e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
-    if world > 1:
-        td.all_reduce(e2e_s, op=td.ReduceOp.MAX)
-    e2e_value = units_per_rank * world / (float(e2e_s.item()) / e2e_steps)
+    e2e_ms, n_est_e2e = ctx.timed_wall(e2e_step, e2e_steps, warmup=2)
+    e2e_value = units_per_rank * world / (e2e_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
 
     # What bounds e2e: the pinned host -> device copy of the step's inputs, measured with ALL ranks copying at once
@@ -382,56 +540,63 @@ def run_gpu_arm(args):
     segments = [(l, storage._host_tensor(l)) for l in range(N_LEVELS)]
     h2d_ms = []
     for rep in range(3):
-        torch.cuda.synchronize()
-        if world > 1:
-            td.barrier()
+        ctx.barrier()
         t0 = time.perf_counter()
         for _level, _rows in stream_levels(segments, device, storage.device_chunk_bytes):
             pass                                   # the same double-buffered chunk copies, no kernels
         torch.cuda.synchronize()
         h2d_ms.append((time.perf_counter() - t0) * 1e3)
-    h2d_t = torch.tensor([min(h2d_ms[1:])], dtype=torch.float64, device=device)
+    h2d_t = ctx.max_over_ranks(min(h2d_ms[1:]))
+    h2d_gbs_slowest = bytes_per_rank / (h2d_t * 1e-3) / 1e9
+    topo = host_topology(ctx)
+    gathered_nodes = [None] * world
     if world > 1:
-        td.all_reduce(h2d_t, op=td.ReduceOp.MAX)
-    h2d_gbs_slowest = bytes_per_rank / (float(h2d_t.item()) * 1e-3) / 1e9
+        td.all_gather_object(gathered_nodes, topo["gpu_numa_node"])
+    else:
+        gathered_nodes = [topo["gpu_numa_node"]]
+    topo["gpu_numa_node_per_rank"] = gathered_nodes
 
+    # keep the resident levels for the data-driven density leg (cfg4)
+    line_out["_levels"] = levels
+    line_out["_steps"] = steps
     if rank != 0:
-        if world > 1:
-            td.barrier()
         return
 
     # ---------------- roofline of the dominant kernel + CPU baseline (rank 0, N = 1 only for the CPU) ----------
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except OSError:
-        pass
+    peaks = ctx.peaks
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     dfma_peak = nat.fp64_peak(0) / 1e12
-    # algorithmic work of one launch over a level with a coarse part: 16 B per sample and 7 FP64 instructions per
-    # sample-moment (2 x (DMUL + DFMA) recurrence, f - c, sum, FMA square), counted as 14 flop -- one FMA-equivalent
-    # per instruction slot, the way the DFMA peak is counted
+    # Algorithmic work of one launch over a level with a coarse part:
+    # 16 B per sample and, per sample-moment, 12 flop by SURVEY's count (FMA = 2: recurrence 2 x 4, difference, sum,
+    # FMA square).  The kernel issues 7 FP64 instructions per sample-moment (monic two-instruction recurrence), so the
+    # issue-slot utilisation (7 slots x 2 / DFMA peak) is reported beside it.
     alg_bytes = n_rows * 16.0
-    alg_flop = n_rows * N_MOMENTS * 14.0
+    alg_flop = n_rows * N_MOMENTS * 12.0
     achieved_tflops = alg_flop / (kernel_ms * 1e-3) / 1e12
     traffic = None
-    try:                                   # dram__bytes_read + dram__bytes_write of this kernel, one ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")) as f:
-            cap = json.load(f)["moments_acc_kernel_coarse_R50"]
-        if cap["samples"] == n_rows:
-            traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
-    except (OSError, KeyError, ValueError):
-        pass
+    for name in ("r2_roofline_traffic.json", "r1_roofline_traffic.json"):
+        try:                               # dram__bytes_read + dram__bytes_write of this kernel, one ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                cap = json.load(f)["moments_acc_kernel_coarse_R50"]
+            if cap["samples"] == n_rows:
+                traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+                break
+        except (OSError, KeyError, ValueError):
+            pass
     roofline = {"kernel": "moments_acc_kernel<LEGENDRE, coarse> (level with fine+coarse, R=50)",
                 "bound": "fp64", "achieved": achieved_tflops, "peak": dfma_peak, "unit": "TFLOP/s",
-                "frac": achieved_tflops / dfma_peak, "peak_source": "DFMA micro-benchmark measured in this run",
+                "frac": achieved_tflops / dfma_peak, "flop_per_sample_moment": 12,
+                "peak_source": "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "issue_slot_frac": n_rows * N_MOMENTS * 14.0 / (kernel_ms * 1e-3) / 1e12 / dfma_peak,
                 "traffic": traffic, "algorithmic_bytes": alg_bytes, "kernel_ms": kernel_ms,
                 "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
-                "note": "R=50 in fp64 is FP64-pipe bound (0.75*R flop/B >> ridge 5.6 flop/B); both terms reported"}
-    cpu_baseline = None
+                "note": "R=50 in fp64 is FP64-pipe bound (0.75*R flop/B >> ridge 5.6 flop/B); both terms reported; "
+                        "frac counts SURVEY 8d's 12 flop per sample-moment, issue_slot_frac the 7 issued FP64 "
+                        "instructions x 2"}
+    cpu_baseline = {"value": None, "unit": UNIT, "kind": "port",
+                    "sample": "not timed at N > 1: see the reference arm (bench.py --impl reference) of this run"}
     if world == 1 and not args.no_cpu_baseline:
         n_procs = max(1, min(os.cpu_count() or 1, 64))
         rows_cpu = 1_000_000                 # ~5 s of NumPy per process; ~10-20 s wall with all cores busy
@@ -441,30 +606,335 @@ def run_gpu_arm(args):
                         "sample": "%d processes x %d rows/level x %d levels (oracle port of the reference's NumPy "
                                   "algorithm, 65536-row chunks)" % (n_procs, rows_cpu, N_LEVELS),
                         "single_process_value": v1, "seconds": inner}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(n_rows), "levels": N_LEVELS, "samples_per_level_per_gpu": n_rows,
-                       "n_moments": N_MOMENTS, "l2_policy": "inputs (%.0f MB per step per GPU) exceed the 126 MB L2"
-                       % (bytes_per_rank / 1e6), "parallelism": "sample-sharded x%d, one all-reduce of level sums" % world,
-                       "reduce": ("none" if world == 1 else "NVLink peer memory, fused with the finalize launch"
-                                  if use_peer[0] else "NCCL all-reduce"),
-                       "launch": "CUDA graph" if graph is not None else "stream"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(bytes_per_rank * world),
-                    "d2h_bytes_per_step": int(d2h_bytes * world), "steps": e2e_steps,
-                    "api": "Estimate.estimate_diff_vars_regression + estimate_n_samples_for_target_variance on a "
-                           "pinned-host Memory storage",
-                    "ms_per_step": float(e2e_s.item()) / e2e_steps * 1e3,
-                    "h2d_only_ms": float(h2d_t.item()),
-                    "h2d_gbs_per_gpu_all_ranks_copying": h2d_gbs_slowest,
-                    "bound": "PCIe / host memory: the bare pinned copy of the same bytes, all ranks at once"},
-            "gpu_launches": launches_per_step * args.steps,
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "n_estimated": [int(v) for v in n_estimated], "n_estimated_e2e": [int(v) for v in n_est_e2e],
-            "launch_count_native": nat.launch_count - launches_before}
-    emit(line)
-    if world > 1:
-        td.barrier()
+    line_out.update({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(n_rows), "levels": N_LEVELS, "samples_per_level_per_gpu": n_rows,
+                   "n_moments": N_MOMENTS, "l2_policy": "inputs (%.0f MB per step per GPU) exceed the 126 MB L2"
+                   % (bytes_per_rank / 1e6), "parallelism": "sample-sharded x%d, one all-reduce of level sums" % world,
+                   "reduce": ("none" if world == 1 else "NVLink peer memory, fused with the finalize launch"
+                              if use_peer[0] else "NCCL all-reduce"),
+                   "peer_reduce_bitwise_check": peer_checked, "peer_reduce_errors": peer_errors,
+                   "launch": "CUDA graph" if graph is not None else "stream",
+                   "timed_region": "kernels + D2H of the result + level-variance regression + n_samples allocation "
+                                   "(the host tail of step k overlaps the kernels of step k+1)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(bytes_per_rank * world),
+                "d2h_bytes_per_step": int(d2h_bytes * world), "steps": e2e_steps,
+                "api": "Estimate.estimate_diff_vars_regression + estimate_n_samples_for_target_variance on a "
+                       "pinned-host Memory storage",
+                "ms_per_step": e2e_ms, "h2d_only_ms": h2d_t,
+                "h2d_gbs_per_gpu_all_ranks_copying": h2d_gbs_slowest, "host": topo,
+                "bound": "PCIe / host memory: the bare pinned copy of the same bytes, all ranks at once"},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "n_estimated": [int(v) for v in n_estimated], "n_estimated_e2e": [int(v) for v in n_est_e2e],
+        "launch_count_native": nat.launch_count - launches_before})
+
+
+# ------------------------------------------------------------------------------------------------ cfg3
+def bench_cfg3(ctx):
+    """BASELINE configs[2]: moment covariance, Legendre R = 100, 1e9 samples in total (STRONG scaling: 1e9 / N per rank),
+    per-rank partial sums combined by one all-reduce inside the timed region.  Three device-resident variants:
+    DMMA contraction (means), DMMA (means + entry variances), linearised means (199 moment sums, C applied once)."""
+    torch, td, nat = ctx.torch, ctx.td, ctx.nat
+    from mlmc_b200.moments import Legendre
+    from mlmc_b200.estimator import Estimate
+    R = 100
+    n_total = ctx.args.cfg3_samples
+    lo, hi = (ctx.rank * n_total) // ctx.world, ((ctx.rank + 1) * n_total) // ctx.world
+    n_rank = hi - lo
+    fn = Legendre(R, domain())
+    basis = fn.basis_struct()
+    rows = synth_pairs_on_device(torch, ctx.device, n_rank, 0.05, 0.5, 77 + ctx.rank)
+    x = rows.permute(2, 0, 1)
+    acc = nat.LevelAccumulator(1, R * R, ctx.device)
+    ext_fn, c_t = fn.product_table()
+    ext_basis = ext_fn.basis_struct()
+    c_dev = torch.from_numpy(c_t).to(ctx.device)
+    acc_m = nat.LevelAccumulator(1, ext_fn.size, ctx.device)
+    out = {}
+
+    def reduce(a):
+        if ctx.world > 1:
+            td.all_reduce(a.acc)
+
+    def run_dmma(want_var):
+        acc.acc.zero_()
+        nat.gram_accumulate(basis, x, acc.level(0), want_var=want_var)
+        reduce(acc)
+        out["dmma"] = acc.finalize()
+
+    def run_linear():
+        acc_m.acc.zero_()
+        nat.moments_accumulate(ext_basis, x, acc_m.level(0))
+        reduce(acc_m)
+        out["lin"] = nat.level_sums_transform(acc_m, 1, c_dev).finalize()
+
+    reps = max(1, min(ctx.args.steps, 3))
+    ms_mean = ctx.timed(lambda: run_dmma(False), reps)
+    dmma_mean = out["dmma"]["mean"].clone()
+    ms_mean_var = ctx.timed(lambda: run_dmma(True), reps)
+    ms_linear = ctx.timed(run_linear, max(reps, 3))
+    # the two routes to the covariance means agree (the parity tests hold both to the oracle)
+    scale = float(dmma_mean.abs().max())
+    lin_vs_dmma = float((out["lin"]["mean"] - dmma_mean).abs().max()) / scale
+    # kernel alone (no reduce / finalize), for the roofline
+    ms_kernel = ctx.timed(lambda: nat.gram_accumulate(basis, x, acc.level(0), want_var=False), 1, warmup=0)
+
+    # end to end through the public API from pinned host rows (a bounded share of the rank's rows when N = 1)
+    n_e2e = min(n_rank, 125_000_000)
+    # (level 0 of a storage has no coarse part: a token level 0 keeps the cfg3 rows a fine - coarse level)
+    storage, value = scalar_quantity([rows[:1000].cpu(), rows[:n_e2e].cpu()], [0.5, 0.05])
+    storage.rows_are_local_shard = True
+    storage.resident_fraction = 0.0
+    est = Estimate(value, storage, fn)
+
+    def e2e(variance):
+        storage.drop_device_copies()
+        return est.estimate_covariance(variance=variance)
+    e2e_lin_ms, _ = ctx.timed_wall(lambda: e2e(False), 2)
+    e2e_var_ms, _ = ctx.timed_wall(lambda: e2e(True), 1)
+    del storage, est, value
+    if ctx.rank != 0:
+        return None
+    nb = (R + 7) // 8
+    dmma_peak = nat.fp64_peak(1) / 1e12
+    useful = 2.0 * R * R                                   # flop per sample: R(R+1)/2 products x 2 sides x FMA
+    executed = nb * (nb + 1) / 2 * 2 * 128.0               # 8x8 blocks on/above the diagonal x 2 sides x 512 / 4 samples
+    ach = n_rank * useful / (ms_kernel * 1e-3) / 1e12
+    units = float(n_total) * R
+    return {
+        "workload": "cfg3: moment covariance, Legendre R=100, %.0e samples in total, %d per rank (strong scaling), "
+                    "all-reduce of the partial sums inside the timed region" % (n_total, n_rank),
+        "scaling": "strong", "n_gpus": ctx.world, "samples_total": n_total, "samples_per_rank": n_rank, "reps": reps,
+        "cov_mean_dmma_ms": ms_mean, "cov_mean_var_dmma_ms": ms_mean_var, "cov_mean_linearised_ms": ms_linear,
+        "sample_moments_per_s": {"cov_mean_dmma": units / (ms_mean * 1e-3),
+                                 "cov_mean_var_dmma": units / (ms_mean_var * 1e-3),
+                                 "cov_mean_linearised": units / (ms_linear * 1e-3)},
+        "linearised_vs_dmma_max_rel": lin_vs_dmma,
+        "reduce": "none" if ctx.world == 1 else "NCCL all-reduce of [2 + 2 R^2] doubles (160 kB) / [2 + 2 * 199]",
+        "roofline": {"kernel": "gram_kernel<coarse, sums> (DMMA m8n8k4), R=100", "bound": "fp64-tensor",
+                     "achieved": ach, "peak": dmma_peak, "unit": "TFLOP/s", "frac": ach / dmma_peak,
+                     "useful_flop_per_sample": useful, "executed_flop_per_sample": executed,
+                     "executed_tflops": n_rank * executed / (ms_kernel * 1e-3) / 1e12,
+                     "executed_frac": n_rank * executed / (ms_kernel * 1e-3) / 1e12 / dmma_peak,
+                     "kernel_ms": ms_kernel, "algorithmic_bytes": n_rank * 16.0,
+                     "hbm_gbs": n_rank * 16.0 / (ms_kernel * 1e-3) / 1e9,
+                     "peak_source": "DMMA m8n8k4 micro-benchmark measured in this run"},
+        "e2e": {"api": "Estimate.estimate_covariance on a pinned-host Memory storage (H2D of the rows + D2H of the "
+                       "result inside the timed region)", "rows_per_rank": n_e2e,
+                "h2d_bytes_per_step": (n_e2e * 16 + 8000) * ctx.world, "d2h_bytes_per_step": (4 * R * R * 2 + 64) * 8,
+                "variance_false_ms": e2e_lin_ms, "variance_true_ms": e2e_var_ms,
+                "sample_moments_per_s_variance_false": float(n_e2e) * ctx.world * R / (e2e_lin_ms * 1e-3),
+                "sample_moments_per_s_variance_true": float(n_e2e) * ctx.world * R / (e2e_var_ms * 1e-3)}}
+
+
+def cpu_cfg3(n=20_000):
+    from oracle import mlmc_oracle as orc
+    rng = np.random.default_rng(77)
+    rows = orc.synth_level_rows(rng.normal(size=n), 0.05, 0.5)
+    t0 = time.perf_counter()
+    orc.estimate_covariance([np.zeros((1, 2, 1)), rows], orc.Basis("legendre", 100, domain()), chunk_rows=2048)
+    dt = time.perf_counter() - t0
+    return {"kind": "port", "cores": 1, "sample": "%d samples, Legendre 100 covariance (oracle port, 2048-row chunks)" % n,
+            "samples_per_s": n / dt, "sample_moments_per_s": n * 100 / dt}
+
+
+# ------------------------------------------------------------------------------------------------ cfg4
+def bench_cfg4(ctx, levels, steps):
+    """BASELINE configs[3]: max-ent fit, 50 moments, 4762 x 21 = 100 002 Gauss nodes (constructor -> normalised
+    multipliers); plus the data-driven Estimate.construct_density on cfg2's resident samples."""
+    import scipy.stats as stats
+    from oracle import mlmc_oracle as orc
+    from mlmc_b200.moments import Legendre
+    from mlmc_b200.estimator import Estimate
+    from mlmc_b200.tool.simple_distribution import (SimpleDistribution, construct_ortogonal_moments,
+                                                    compute_semiexact_cov, compute_semiexact_moments)
+    distr = stats.norm(loc=1, scale=2)
+    dom = tuple(float(v) for v in distr.ppf([0.01, 0.99]))
+    n_panels = 4762
+    base = Legendre(50, dom, safe_eval=False)
+    cov = compute_semiexact_cov(base, distr.pdf, n_panels=n_panels)
+    orth, info = construct_ortogonal_moments(base, cov, tol=1e-4)
+    mu = compute_semiexact_moments(orth, distr.pdf, n_panels=n_panels)
+    data = np.stack([mu, np.ones_like(mu)], axis=1)
+
+    def fit():
+        sd = SimpleDistribution(orth, data, domain=dom, quad_panels=n_panels)
+        return sd, sd.estimate_density_minimize(tol=1e-8, reg_param=0.0)
+    times = []
+    fit()
+    for _ in range(7):
+        ctx.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sd, res = fit()
+        ctx.torch.cuda.synchronize()
+        times.append((time.perf_counter() - t0) * 1e3)
+    before = ctx.nat.launch_count
+    ms_eval = ctx.timed(lambda: ctx.nat.maxent_fgh(sd._quad_moments_dev, sd._weights_dev, sd._lam_dev, 7, sd._out_dev), 20)
+    xs = np.linspace(dom[0], dom[1], 201)
+    ob = orc.Basis("legendre", 50, dom, safe_eval=False, matrix=info[2])
+    t0 = time.perf_counter()
+    ofit = orc.maxent_fit(ob, data, dom, tol=1e-8, n_panels=n_panels)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    r = int(orth.size)
+    q = n_panels * 21
+    flop = 2.0 * q * r + 2.0 * q * r + 2.0 * q * r * r       # exponent, gradient, Hessian (SURVEY.md section 8d)
+    out = {"workload": "cfg4: max-ent fit, %d moments (orthogonalised Legendre 50), %d Gauss nodes, trust-ncg" % (r, q),
+           "fit_ms": float(np.median(times)), "fit_ms_min": float(np.min(times)), "nit": int(res.nit),
+           "success": bool(res.success), "device_evals": int(sd.n_device_evals), "fgh_eval_ms": ms_eval,
+           "fgh_eval_tflops": flop / (ms_eval * 1e-3) / 1e12, "launches_per_eval": (ctx.nat.launch_count - before) // 21,
+           "cpu": {"kind": "port", "cores": "numpy/BLAS default threads", "fit_ms": cpu_ms,
+                   "sample": "the same fit by the oracle (NumPy + scipy trust-ncg on the same fixed rule)"},
+           "max_abs_multiplier_diff_vs_oracle": float(np.max(np.abs(sd.multipliers - ofit.multipliers))),
+           "max_rel_pdf_vs_oracle": max_rel(sd.density(xs), orc.maxent_density(ob, ofit.multipliers, np.ones(r), xs)),
+           "target_ms": 50.0}
+    # data-driven variant on the cfg2 samples (3 x samples_per_level, resident in HBM)
+    storage, value = scalar_quantity([lv.cpu() for lv in levels], steps)
+    dom2 = tuple(float(v) for v in stats.norm.ppf([0.001, 0.999]))
+    est = Estimate(value, storage, Legendre(25, dom2))
+    est.construct_density(tol=1e-8, orth_moments_tol=1e-4)
+    times = []
+    for _ in range(5):
+        ctx.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dobj, _info, res_d, mom_d = est.construct_density(tol=1e-8, orth_moments_tol=1e-4)
+        ctx.torch.cuda.synchronize()
+        times.append((time.perf_counter() - t0) * 1e3)
+    xs2 = np.linspace(dom2[0], dom2[1], 201)[10:-10]
+    out["construct_density"] = {"samples": int(sum(len(lv) for lv in levels)), "base": "Legendre 25",
+                                "ms": float(np.median(times)), "orthogonal_moments": int(mom_d.size),
+                                "nit": int(res_d.nit), "fun_norm": float(res_d.fun_norm),
+                                "max_abs_pdf_err_vs_normal_interior": float(np.max(np.abs(dobj.density(xs2)
+                                                                                         - stats.norm.pdf(xs2)))),
+                                "data_passes": 1}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ cfg1
+def bench_cfg1(ctx):
+    """BASELINE configs[0]: 1 level, 1e5 lognormal samples, Legendre 25 on the estimated log domain, estimate_moments."""
+    from oracle import mlmc_oracle as orc
+    from mlmc_b200.moments import Legendre
+    from mlmc_b200.estimator import Estimate
+    n = 100_000
+    rows = synth_pairs_on_device(ctx.torch, ctx.device, n, 0.1, None, 1234, lognormal=True).cpu().numpy()
+    storage, value = scalar_quantity([rows], [0.1])
+    dom = Estimate.estimate_domain(value, storage, quantile=0.001)
+    fn = Legendre(25, dom, log=True, safe_eval=True)
+    est = Estimate(value, storage, fn)
+    ms_res, (means, variances) = ctx.timed_wall(est.estimate_moments, 50, warmup=3)
+    storage.resident_fraction = 0.0
+
+    def staged():
+        storage.drop_device_copies()
+        return est.estimate_moments()
+    ms_e2e, _ = ctx.timed_wall(staged, 50, warmup=3)
+    t0 = time.perf_counter()
+    o = orc.estimate_moments([rows], orc.Basis("legendre", 25, tuple(dom), log=True))
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    return {"workload": "cfg1: 1 level, 1e5 lognormal samples, Legendre R=25 (log domain), estimate_moments",
+            "resident_ms": ms_res, "e2e_ms": ms_e2e, "h2d_bytes_per_step": n * 8,
+            "sample_moments_per_s_resident": n * 25 / (ms_res * 1e-3), "sample_moments_per_s_e2e": n * 25 / (ms_e2e * 1e-3),
+            "cpu": {"kind": "port", "cores": 1, "ms": cpu_ms, "sample_moments_per_s": n * 25 / (cpu_ms * 1e-3),
+                    "sample": "the full config by the oracle port"},
+            "max_rel_mean_vs_oracle": max_rel(means, o.mean), "max_rel_var_vs_oracle": max_rel(variances, o.var),
+            "n_rm_samples": int(o.n_rm_samples[0])}
+
+
+# ------------------------------------------------------------------------------------------------ cfg5
+def bench_cfg5(ctx):
+    """BASELINE configs[4]: vector quantity, 1e4 locations x 5 levels, Fourier R = 32, per-location mean / variance."""
+    torch = ctx.torch
+    from oracle import mlmc_oracle as orc
+    from mlmc_b200.moments import Fourier
+    from mlmc_b200.sample_storage import Memory
+    from mlmc_b200.quantity.quantity import make_root_quantity
+    from mlmc_b200.quantity.quantity_spec import QuantitySpec
+    from mlmc_b200.quantity import quantity_estimate as qe
+    M = 10_000
+    n_levels = [4096, 2048, 1024, 512, 256]
+    steps = orc.level_steps(5, (0.5, 0.005))
+    offs = torch.arange(M, dtype=torch.float64, device=ctx.device) * 1e-4
+    levels = []
+    for l, n in enumerate(n_levels):
+        base = synth_pairs_on_device(torch, ctx.device, n, steps[l], steps[l - 1] if l else None, 500 + l)   # [n, 2, 1]
+        rows = base + offs[None, None, :]
+        if l == 0:
+            rows[:, 1, :] = 0
+        levels.append(rows.cpu())
+        del rows
+    spec = [QuantitySpec(name="field", unit="", shape=(1, 1), times=[0.0], locations=[str(i) for i in range(M)])]
+    storage = Memory.from_arrays(levels, level_parameters=[[h] for h in steps], result_format=spec)
+    field = make_root_quantity(storage, spec)["field"][0.0]
+    dom = (-4.2, 5.4)
+    fn = Fourier(32, dom)
+    ms_res, qm = ctx.timed_wall(lambda: qe.estimate_mean(qe.moments(field, fn)), 5, warmup=2)
+    storage.resident_fraction = 0.0
+
+    def staged():
+        storage.drop_device_copies()
+        return qe.estimate_mean(qe.moments(field, fn))
+    ms_e2e, _ = ctx.timed_wall(staged, 3, warmup=1)
+    # oracle on 50 locations spread over the field (sample mask of all locations applied first)
+    ob = orc.Basis("fourier", 32, dom)
+    pick = np.arange(0, M, 200)
+    sl = []
+    for l, lv in enumerate(levels):
+        lv = lv.numpy()
+        t = orc.to_ref_domain(ob, lv[:, :1, :] if l == 0 else lv)
+        keep = ~np.isnan(t).any(axis=(1, 2))
+        sl.append(np.ascontiguousarray(lv[keep][:, :, pick]))
+    t0 = time.perf_counter()
+    o = orc.estimate_moments(sl, ob, chunk_rows=512)
+    cpu_s = time.perf_counter() - t0
+    units = float(sum(n_levels)) * M * 32
+    n_bytes = sum(n_levels[1:]) * M * 16 + n_levels[0] * M * 8
+    got_means = qm.l_means.reshape(5, M, 32)[:, pick].reshape(5, -1)
+    got_vars = qm.l_vars.reshape(5, M, 32)[:, pick].reshape(5, -1)
+    return {"workload": "cfg5: field of 1e4 locations x 5 levels (4096..256 samples), Fourier R=32, per-location mean/var",
+            "resident_ms": ms_res, "e2e_ms": ms_e2e, "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": (2 * 5 + 2) * M * 32 * 8,
+            "sample_moments_per_s_resident": units / (ms_res * 1e-3), "sample_moments_per_s_e2e": units / (ms_e2e * 1e-3),
+            "hbm_gbs_resident": n_bytes / (ms_res * 1e-3) / 1e9,
+            "cpu": {"kind": "port", "cores": 1, "sample_moments_per_s": sum(len(s) for s in sl) * len(pick) * 32 / cpu_s,
+                    "sample": "50 of the 1e4 locations, all samples (oracle port, 512-row chunks)"},
+            "n_samples": [int(v) for v in qm.n_samples], "n_rm_samples": [int(v) for v in qm.n_rm_samples],
+            "max_rel_l_means_vs_oracle": max_rel(got_means, o.l_means), "max_rel_l_vars_vs_oracle": max_rel(got_vars, o.l_vars)}
+
+
+def run_gpu_arm(args):
+    ctx = Ctx(args)
+    parity = startup_parity_check(ctx)
+    line = {}
+    bench_cfg2(ctx, line)
+    levels, steps = line.pop("_levels"), line.pop("_steps")
+    wanted = [c for c in args.configs.split(",") if c]
+    configs = {}
+    if "cfg3" in wanted:
+        res = bench_cfg3(ctx)
+        if ctx.rank == 0:
+            configs["cfg3"] = res
+            if ctx.world == 1 and not args.no_cpu_baseline:
+                configs["cfg3"]["cpu"] = cpu_cfg3()
+    ctx.barrier()
+    # cfg1 / cfg4 / cfg5 are single-GPU configurations (max-ent: replicas only, SURVEY.md section 8e): timed at N = 1
+    if ctx.world == 1:
+        if "cfg4" in wanted:
+            configs["cfg4"] = bench_cfg4(ctx, levels, steps)
+        if "cfg1" in wanted:
+            configs["cfg1"] = bench_cfg1(ctx)
+        if "cfg5" in wanted:
+            del levels
+            ctx.torch.cuda.empty_cache()
+            configs["cfg5"] = bench_cfg5(ctx)
+    elif ctx.rank == 0:
+        configs["note"] = "cfg1 / cfg4 / cfg5 are single-GPU configurations: reported by the N = 1 run"
+    if ctx.rank == 0:
+        line["parity_check"] = parity
+        line["configs"] = configs
+        emit(line)
+    ctx.barrier()
 
 
 _JSON_OUT = None
@@ -491,6 +961,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples-per-level", type=int, default=N_PER_LEVEL)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="cfg1,cfg3,cfg4,cfg5",
+                    help="further BASELINE configs reported under `configs` in the same JSON line ('' = none)")
+    ap.add_argument("--cfg3-samples", type=int, default=1_000_000_000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -27,10 +27,11 @@ def to_struct(b: orc.Basis):
     return native().make_basis(KINDS[b.kind], b.size, b.domain, b.ref_domain, b.log, b.safe_eval)
 
 
-def rel_close(got, want, rtol, atol_scale=1e-15, per_level=False):
+def rel_close(got, want, rtol, atol_scale=1e-15, per_level=False, extra_atol=None):
     """|got - want| <= rtol |want| + atol_scale * scale.  ``scale`` is the largest finite |want| -- of the whole array,
     or, with ``per_level`` (arrays ``[L, K]``: one row per level), of each row separately: the variances of the fine
-    levels are orders of magnitude below level 0's and must not hide behind its scale."""
+    levels are orders of magnitude below level 0's and must not hide behind its scale.  ``extra_atol`` (array like
+    ``want``) adds an entry-wise absolute allowance."""
     got, want = np.asarray(got, dtype=float), np.asarray(want, dtype=float)
     assert got.shape == want.shape, (got.shape, want.shape)
     finite = np.where(np.isfinite(want), np.abs(want), 0.0)
@@ -39,6 +40,8 @@ def rel_close(got, want, rtol, atol_scale=1e-15, per_level=False):
     else:
         scale = finite.max() if finite.size else 1.0
     tol = rtol * np.abs(want) + atol_scale * np.maximum(scale, 1e-300)
+    if extra_atol is not None:
+        tol = tol + np.where(np.isfinite(extra_atol), np.abs(extra_atol), 0.0)
     with np.errstate(invalid="ignore"):
         ok = (np.abs(got - want) <= tol) | (got == want) | (np.isnan(got) & np.isnan(want))
     assert ok.all(), "max abs err %.3e (scale %s) at %s" % (
