@@ -818,14 +818,18 @@ int launch_moments(const MomentsArgs& a, Plan p, cudaStream_t st) {
     if (STAGES > 0) p.smem += (size_t)STAGES * ((size_t)S * kThreads * 16 + 8);
     // resident CTAs per SM for this variant and shared-memory size (registers may bind before shared memory);
     // the sample-partition dimension of the grid is sized to exactly one resident wave
+    // (both are per-device properties of the function: the cache is keyed by the current device as well)
     static thread_local size_t cached_smem = 0;
-    static thread_local int cached_ctas = 0;
-    if (cached_smem != p.smem || cached_ctas == 0) {
+    static thread_local int cached_ctas = 0, cached_dev = -1;
+    int cur_dev = 0;
+    MB_CUDA_OK(cudaGetDevice(&cur_dev));
+    if (cached_smem != p.smem || cached_ctas == 0 || cached_dev != cur_dev) {
         MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
         int ctas = 0;
         MB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern, kThreads, p.smem));
         cached_ctas = ctas > 0 ? ctas : 1;
         cached_smem = p.smem;
+        cached_dev = cur_dev;
     }
     const unsigned slots = (unsigned)(sm_count() * cached_ctas);
     const int TN = a.n_comp >= kThreads ? 1 : kThreads / a.n_comp;

@@ -96,7 +96,7 @@ class SampleStorage(metaclass=ABCMeta):
         return len(self.get_level_ids())
 
     def get_n_collected(self):
-        return [len(self.level_rows(l)) for l in self.get_level_ids()]
+        return [self.level_n_rows(l) for l in self.get_level_ids()]
 
     def n_finished(self):
         return np.array(self.get_n_collected(), dtype=float)
@@ -110,7 +110,7 @@ class SampleStorage(metaclass=ABCMeta):
         return itertools.chain(*[self._level_chunks(l, n_samples) for l in level_ids])
 
     def _level_chunks(self, level_id, n_samples=None):
-        n = len(self.level_rows(level_id))
+        n = self.level_n_rows(level_id)
         if n_samples is not None:
             n = min(n, n_samples)
         yield ChunkSpec(chunk_id=0, chunk_slice=slice(0, n, 1), level_id=level_id)
@@ -138,27 +138,38 @@ class SampleStorage(metaclass=ABCMeta):
         self._resident().clear()
 
     def _host_tensor(self, level_id):
-        """Rows as a (preferably pinned) torch CPU tensor; subclasses with pinned storage override."""
-        return torch.from_numpy(np.ascontiguousarray(self.level_rows(level_id)))
+        """Where the streaming feed reads a level from: a pinned torch CPU tensor (``Memory``) or a ``RowSource`` over
+        file-backed rows (level 0 without its zero coarse row)."""
+        return RowSource(self.level_rows(level_id), drop_coarse=int(level_id) == 0)
+
+    def level_n_rows(self, level_id):
+        """Number of collected rows of a level, WITHOUT reading them (array / memmap / HDF5 dataset shape)."""
+        return int(self.level_rows(level_id).shape[0])
 
     def device_rows(self, level_id, device, keep_resident=True, free_bytes=None):
         """Whole level as one CUDA tensor ``[N, 2, M]`` (uploaded once, cached) or None if it should be streamed."""
         key = (level_id, str(device))
         cache = self._resident()
         rows = cache.get(key)
-        n_now = len(self.level_rows(level_id))
+        n_now = self.level_n_rows(level_id)
         if rows is not None and rows.shape[0] == n_now:
             return rows
         if self.resident_fraction <= 0:
             return None
         host = self._host_tensor(level_id)
-        n_bytes = host.numel() * 8
+        n_bytes = 8 * int(np.prod(host.shape))
         if free_bytes is None:
             free_bytes, _total = torch.cuda.mem_get_info(device)
         if n_bytes > self.resident_fraction * free_bytes:
             return None
-        rows = torch.empty(host.shape, dtype=torch.float64, device=device)
-        rows.copy_(host, non_blocking=True)
+        rows = torch.empty(tuple(host.shape), dtype=torch.float64, device=device)
+        if isinstance(host, torch.Tensor):
+            rows.copy_(host, non_blocking=True)
+        else:                                   # file-backed: through the staged pipeline, piece by piece
+            at = 0
+            for _level, piece in stream_levels([(level_id, host)], device, self.device_chunk_bytes):
+                rows[at:at + piece.shape[0]].copy_(piece)
+                at += piece.shape[0]
         if keep_resident:
             cache[key] = rows
         return rows
@@ -190,22 +201,75 @@ class SampleStorage(metaclass=ABCMeta):
                 yield level_id, (rows if rng is None else rows[rng[0]:rng[1]])
             else:
                 host = self._host_tensor(level_id)
-                pending.append((level_id, host if rng is None else host[rng[0]:rng[1]]))
+                if rng is not None:
+                    host = host[rng[0]:rng[1]] if isinstance(host, torch.Tensor) else host.slice_rows(rng[0], rng[1])
+                pending.append((level_id, host))
         if pending:
             yield from stream_levels(pending, device, self.device_chunk_bytes)
 
 
+class RowSource:
+    """Rows ``float64[N, S, M]`` of one level that live in a file (memory map, HDF5 dataset): ``read_into(lo, hi, out)``
+    fills a C-contiguous NumPy buffer ``[hi - lo, S, M]`` -- a pinned staging buffer on the streaming path.  Level 0
+    drops the auxiliary zero coarse row HERE (``S = 1``), so it is neither staged nor copied to the GPU."""
+
+    def __init__(self, rows, drop_coarse=False, lo=0, hi=None):
+        self._rows = rows                       # NumPy array / memmap [N, 2, M] or an object with read_rows(lo, hi, out)
+        n, sides, m = rows.shape
+        self._lo = lo
+        self._hi = n if hi is None else hi
+        self._drop = bool(drop_coarse) and sides == 2
+        self.shape = (self._hi - self._lo, 1 if self._drop else sides, m)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def slice_rows(self, lo, hi):
+        lo, hi = max(0, min(lo, len(self))), max(0, min(hi, len(self)))
+        return RowSource(self._rows, self._drop, self._lo + lo, self._lo + max(lo, hi))
+
+    def read_into(self, lo, hi, out):
+        lo, hi = self._lo + lo, self._lo + hi
+        if hasattr(self._rows, "read_rows"):
+            if self._drop:
+                out[...] = self._rows.read_rows(lo, hi)[:, :1, :]
+            else:
+                self._rows.read_rows(lo, hi, out=out)
+        else:
+            out[...] = self._rows[lo:hi, :1, :] if self._drop else self._rows[lo:hi]
+
+
+_staging = {}
+
+
+def _staging_buffers(n_bytes):
+    """Two fixed pinned staging buffers (reused by every staged stream of this process)."""
+    bufs = _staging.get("bufs")
+    if bufs is None or bufs[0].numel() * 8 < n_bytes:
+        n = max((int(n_bytes) + 7) // 8, 1 << 20)
+        bufs = _staging["bufs"] = [_pinned_empty((n,)) for _ in range(2)]
+    return bufs
+
+
 def stream_levels(segments, device, chunk_bytes=32 << 20):
-    """Double-buffered H2D streaming of ``[(level_id, host rows [N, 2, M]), ...]`` (pinned => truly asynchronous).
-    Yields ``(level_id, device rows)``; a yielded tensor stays valid until the second next ``next()``."""
+    """Double-buffered H2D streaming of ``[(level_id, host rows [N, S, M]), ...]``.
+    Yields ``(level_id, device rows)``; a yielded tensor stays valid until the second next ``next()``.
+
+    ``host rows`` is a torch CPU tensor (pinned => truly asynchronous copies straight from it: ``Memory``) or a
+    ``RowSource`` (file-backed levels).  The latter go through a THREE-stage pipeline: file -> one of two fixed pinned
+    staging buffers (CPU copy out of the page cache / HDF5 chunks) -> one of two device buffers (copy stream) -> the
+    consumer's kernels (compute stream); while the kernels of piece k run, piece k + 1 is on the copy engine and the
+    CPU reads piece k + 2.  No buffer of the size of a level is ever pinned."""
     pieces = []
     max_elems = 0
+    staged = False
     for level_id, host in segments:
         n = host.shape[0]
         if n == 0:
             continue
-        row_elems = host[0].numel()
+        row_elems = int(host.shape[1]) * int(host.shape[2])
         chunk_rows = max(1, min(n, chunk_bytes // (8 * row_elems)))
+        staged = staged or not isinstance(host, torch.Tensor)
         for lo in range(0, n, chunk_rows):
             hi = min(lo + chunk_rows, n)
             pieces.append((level_id, host, lo, hi))
@@ -215,6 +279,12 @@ def stream_levels(segments, device, chunk_bytes=32 << 20):
     compute = torch.cuda.current_stream(device)
     copy_stream = _copy_stream(device)
     bufs = [torch.empty(max_elems, dtype=torch.float64, device=device) for _ in range(2)]
+    for buf in bufs:
+        # allocated on the compute stream, written on the copy stream: tell the caching allocator NOW, so that a consumer
+        # that raises mid-iteration (the generator is then closed at the `yield`) cannot hand the memory out again while
+        # a prefetch is still in flight
+        buf.record_stream(copy_stream)
+    stage = _staging_buffers(max_elems * 8) if staged else None
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     copy_stream.wait_stream(compute)          # the buffers may be recycled memory still in use on the compute stream
@@ -222,25 +292,36 @@ def stream_levels(segments, device, chunk_bytes=32 << 20):
     def issue(k):
         b = k % 2
         level_id, host, lo, hi = pieces[k]
-        view = bufs[b][: (hi - lo) * host[0].numel()].view((hi - lo,) + tuple(host.shape[1:]))
+        shape = (hi - lo,) + tuple(int(d) for d in host.shape[1:])
+        n_elems = shape[0] * shape[1] * shape[2]
+        view = bufs[b][:n_elems].view(shape)
+        if isinstance(host, torch.Tensor):
+            src = host[lo:hi]
+        else:
+            if k >= 2:
+                copied[b].synchronize()       # the copy that last read this staging buffer has finished
+            src = stage[b][:n_elems].view(shape)
+            host.read_into(lo, hi, src.numpy())
         with torch.cuda.stream(copy_stream):
             if k >= 2:
                 copy_stream.wait_event(consumed[b])
-            view.copy_(host[lo:hi], non_blocking=True)
+            view.copy_(src, non_blocking=True)
             copied[b].record(copy_stream)
         return level_id, view
 
     nxt = issue(0)
-    for k in range(len(pieces)):
-        cur = nxt
-        if k + 1 < len(pieces):
-            nxt = issue(k + 1)
-        b = k % 2
-        compute.wait_event(copied[b])
-        yield cur
-        consumed[b].record(compute)
-    for buf in bufs:                           # allocated on the compute stream, written on the copy stream
-        buf.record_stream(copy_stream)
+    try:
+        for k in range(len(pieces)):
+            cur = nxt
+            if k + 1 < len(pieces):
+                nxt = issue(k + 1)
+            b = k % 2
+            compute.wait_event(copied[b])
+            yield cur
+            consumed[b].record(compute)
+    finally:
+        if staged:                            # the staging buffers are shared: nothing may still be reading them
+            copy_stream.synchronize()
 
 
 _copy_streams = {}
@@ -309,7 +390,9 @@ class Memory(SampleStorage):
             self._rows[level_id] = buf = grown
         buf[n_old:n_old + len(new)].copy_(new)
         self._n[level_id] = n_old + len(new)
-        self._resident().pop((level_id, None), None)
+        cache = self._resident()
+        for key in [k for k in cache if k[0] == level_id]:       # resident copies (any device) of this level are stale
+            del cache[key]
 
     # ---- write side
     def save_samples(self, successful_samples, failed_samples):
@@ -355,6 +438,9 @@ class Memory(SampleStorage):
         level_id = int(level_id)
         return self._rows[level_id][: self._n[level_id]]
 
+    def level_n_rows(self, level_id):
+        return self._n[int(level_id)]
+
     def n_finished(self):
         out = np.zeros(max(self._n_finished) + 1 if self._n_finished else 0)
         for level_id, n in self._n_finished.items():
@@ -378,7 +464,8 @@ class NpyStorage(SampleStorage):
     """File-backed read side in the reference's on-disk row order: one ``level_<l>.npy`` of shape ``[N, 2, M]``
     per level plus ``meta.npz`` (level parameters, n_ops).  It stands in for ``SampleStorageHDF``'s
     ``Levels/<l>/collected_values`` datasets (h5py / libhdf5 are not part of this image); levels are
-    memory-mapped and streamed to the GPU through pinned staging buffers."""
+    memory-mapped (row counts come from the ``.npy`` header) and streamed to the GPU through two fixed pinned staging
+    buffers (``stream_levels``): file read, H2D copy and kernels overlap, no level-sized pinned allocation."""
 
     def __init__(self, directory):
         self._dir = directory
@@ -402,12 +489,6 @@ class NpyStorage(SampleStorage):
         if level_id not in self._maps:
             self._maps[level_id] = np.load(os.path.join(self._dir, "level_%d.npy" % level_id), mmap_mode="r")
         return self._maps[level_id]
-
-    def _host_tensor(self, level_id):
-        rows = self.level_rows(level_id)
-        staged = _pinned_empty(rows.shape)
-        staged.numpy()[...] = rows          # disk -> pinned host buffer
-        return staged
 
     def get_level_ids(self):
         return list(range(len(self._level_parameters)))
@@ -440,27 +521,118 @@ class NpyStorage(SampleStorage):
         raise NotImplementedError("NpyStorage is a read-side adapter")
 
 
-class SampleStorageHDF(SampleStorage):
-    """Read-side adapter for the reference's HDF5 files (``mlmc/sample_storage_hdf.py:169-184``,
-    ``mlmc/tool/hdf5.py:365-376``): dataset ``Levels/<l>/collected_values`` of array dtype ``(2, M) f8``.
-    Needs ``h5py``, which this image does not ship -- constructing it without h5py raises ImportError."""
+class _H5pyRows:
+    """``read_rows`` over an h5py dataset of one level (the file is opened per read, like the reference does)."""
 
-    def __init__(self, file_path):
-        try:
-            import h5py  # noqa: F401
-        except ImportError as exc:
-            raise ImportError("SampleStorageHDF needs h5py (not installed in this image); "
-                              "use NpyStorage or Memory for the same row layout") from exc
+    def __init__(self, h5py, path, name, shape):
+        self._h5py, self._path, self._name, self.shape = h5py, path, name, shape
+
+    def read_rows(self, lo=0, hi=None, out=None):
+        hi = self.shape[0] if hi is None else hi
+        with self._h5py.File(self._path, "r") as f:
+            dset = f[self._name]
+            if out is None:
+                return np.asarray(dset[lo:hi], dtype=np.float64)
+            dset.read_direct(out, np.s_[lo:hi])
+            return out
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, key):
+        if isinstance(key, slice):
+            lo, hi, step = key.indices(self.shape[0])
+            rows = self.read_rows(lo, hi)
+            return rows if step == 1 else rows[::step]
+        return self.read_rows()[key]
+
+    def __array__(self, dtype=None, copy=None):
+        return self.read_rows()
+
+
+class _MinRows(_H5pyRows):
+    """The same over ``mlmc_b200.tool.hdf5_min`` (memory-mapped file, no h5py)."""
+
+    def __init__(self, dataset, shape):
+        self._dset, self.shape = dataset, shape
+
+    def read_rows(self, lo=0, hi=None, out=None):
+        return self._dset.read_rows(lo, hi, out=out)
+
+
+class SampleStorageHDF(SampleStorage):
+    """Read side of the reference's HDF5 sample files (``mlmc/sample_storage_hdf.py:144-184``,
+    ``mlmc/tool/hdf5.py:311-320, 353-376``): dataset ``Levels/<l>/collected_values`` -- 1-D, chunked, element type
+    ``(2, M)`` float64 -- root attribute ``level_parameters``, level attribute ``n_ops_estimate``.
+
+    Opens with h5py when it is importable, otherwise with the built-in minimal reader
+    (``mlmc_b200.tool.hdf5_min``; h5py / libhdf5 are not part of this image).  Nothing is read at construction but
+    the metadata: row counts come from the dataset shapes (the reference's ``collected_n_items`` loads the whole
+    dataset, ``hdf5.py:378-389``).  Rows reach the GPU through the staged pipeline of ``stream_levels`` (HDF5 chunks ->
+    two pinned staging buffers -> device), level 0 without its stored zero coarse row."""
+
+    def __init__(self, file_path, backend=None):
         self._path = file_path
-        self._h5py = h5py
-        with h5py.File(file_path, "r") as f:
-            self._level_parameters = np.array(f.attrs["level_parameters"]).tolist()
-            self._levels = sorted(int(k) for k in f["Levels"].keys())
         self._format = []
+        if backend not in (None, "h5py", "min"):
+            raise ValueError("backend must be None, 'h5py' or 'min'")
+        h5py = None
+        if backend != "min":
+            try:
+                import h5py
+            except ImportError:
+                if backend == "h5py":
+                    raise
+        self._rows = {}
+        self._n_ops = {}
+        if h5py is not None:
+            self.backend = "h5py"
+            with h5py.File(file_path, "r") as f:
+                self._level_parameters = np.array(f.attrs["level_parameters"]).tolist()
+                for key in f["Levels"].keys():
+                    group = f["Levels"][key]
+                    if "collected_values" not in group:
+                        continue
+                    dset = group["collected_values"]
+                    shape = (int(dset.shape[0]),) + tuple(int(d) for d in dset.dtype.shape)
+                    self._rows[int(key)] = _H5pyRows(h5py, file_path, "Levels/%s/collected_values" % key, shape)
+                    self._n_ops[int(key)] = np.array(group.attrs.get("n_ops_estimate", [0.0, 0.0]), dtype=float)
+        else:
+            from .tool import hdf5_min
+            self.backend = "min"
+            self._file = hdf5_min.File(file_path)
+            params = self._file.attrs.get("level_parameters")
+            if params is None:
+                raise Exception("'level_parameters' aren't store in HDF file, so unable to create level groups")
+            self._level_parameters = np.asarray(params).tolist()
+            levels = self._file["Levels"]
+            for key in levels.keys():
+                group = levels[key]
+                if "collected_values" not in group:
+                    continue
+                dset = group["collected_values"]
+                sub = dset.dtype.shape if dset.dtype.subdtype else ()
+                if len(dset.shape) != 1 or len(sub) != 2 or dset.dtype.base != np.dtype("<f8"):
+                    raise ValueError("Levels/%s/collected_values: expected a 1-D dataset of (2, M) float64 elements" % key)
+                self._rows[int(key)] = _MinRows(dset, (int(dset.shape[0]),) + tuple(int(d) for d in sub))
+                ops = group.attrs.get("n_ops_estimate")
+                self._n_ops[int(key)] = np.asarray(ops if ops is not None else [0.0, 0.0], dtype=float).reshape(-1)
+        self._levels = sorted(self._rows)
 
     def level_rows(self, level_id):
-        with self._h5py.File(self._path, "r") as f:
-            return np.asarray(f["Levels"][str(int(level_id))]["collected_values"][()], dtype=np.float64)
+        """Lazy rows ``[N, 2, M]`` of a level: ``len()``, ``.shape``, slicing and ``np.asarray`` read from the file."""
+        return self._rows[int(level_id)]
+
+    def level_n_rows(self, level_id):
+        return self._rows[int(level_id)].shape[0]
+
+    def sample_pairs_level(self, chunk_spec):
+        level_id = 0 if chunk_spec.level_id is None else int(chunk_spec.level_id)
+        sl = chunk_spec.chunk_slice if chunk_spec.chunk_slice is not None else slice(None)
+        rows = self._rows[level_id][sl]
+        if level_id == 0:
+            rows = rows[:, :1, :]
+        return rows.transpose((2, 0, 1))
 
     def get_level_ids(self):
         return self._levels
@@ -469,15 +641,16 @@ class SampleStorageHDF(SampleStorage):
         return self._level_parameters
 
     def get_n_ops(self):
+        """``n_ops_estimate`` = (accumulated time, number of samples) per level -> time per sample
+        (``sample_storage_hdf.py:225-241``)."""
         out = []
-        with self._h5py.File(self._path, "r") as f:
-            for l in self._levels:
-                est = f["Levels"][str(l)].attrs.get("n_ops_estimate", [0.0, 0.0])
-                out.append(est[0] / est[1] if est[1] > 0 else 0)
+        for l in self._levels:
+            est = self._n_ops.get(l, np.zeros(2))
+            out.append(float(est[0] / est[1]) if len(est) > 1 and est[1] > 0 else 0)
         return out
 
     def save_samples(self, successful_samples, failed_samples):
-        raise NotImplementedError("read-side adapter")
+        raise NotImplementedError("read-side adapter (write with the reference, or hdf5_min.write_mlmc_file)")
 
     def save_result_format(self, res_spec):
         self._format = res_spec

@@ -249,6 +249,50 @@ def test_npy_storage_streaming(tmp_path, golden):
     rel_close(variances, g["A_leg_var"], rtol=1e-10)
 
 
+def test_hdf_storage_streaming(tmp_path, golden):
+    """The reference's HDF5 layout (Levels/<l>/collected_values, chunked, (2, M) float64 elements) read by the built-in
+    reader and streamed through the two pinned staging buffers in many small pieces; also the resident path and a
+    vector quantity; same estimates as the golden reference outputs."""
+    from mlmc_b200.sample_storage import SampleStorageHDF
+    from mlmc_b200.tool.hdf5_min import write_mlmc_file
+    from mlmc_b200.quantity.quantity import make_root_quantity
+    from mlmc_b200.quantity.quantity_spec import QuantitySpec
+    from mlmc_b200.quantity import quantity_estimate as qe
+    from mlmc_b200.moments import Legendre
+    from mlmc_b200.estimator import Estimate
+    g = golden("estimates")
+    levels = [g["A_rows%d" % l] for l in range(3)]
+    path = write_mlmc_file(str(tmp_path / "mlmc.hdf5"), levels, [[h] for h in g["A_steps"]], g["A_n_ops"], chunk_rows=500)
+    spec = [QuantitySpec(name="v", unit="", shape=(1, 1), times=[0.0], locations=["0"])]
+    for resident in (0.0, 0.6):
+        storage = SampleStorageHDF(path, backend="min")
+        storage.device_chunk_bytes = 16 * 300      # ~14 pieces on level 0, each crossing HDF5 chunk boundaries
+        storage.resident_fraction = resident
+        value = make_root_quantity(storage, spec)["v"][0.0]["0"][0, 0]
+        est = Estimate(value, storage, Legendre(12, tuple(g["A_domain"])))
+        for _ in range(2):                         # second call: resident copy (or a fresh stream)
+            means, variances = est.estimate_moments()
+            rel_close(means, g["A_leg_mean"], rtol=1e-10)
+            rel_close(variances, g["A_leg_var"], rtol=1e-10)
+        reg_vars, n_ops = est.estimate_diff_vars_regression(g["A_leg_n"])
+        rel_close(reg_vars, g["A_leg_reg_vars"], rtol=1e-9)
+        assert np.allclose(n_ops, g["A_n_ops"])
+        dom = Estimate.estimate_domain(value, storage, quantile=0.01)
+        assert np.array_equal(np.array(dom), g["A_est_domain"])
+    # vector quantity from a second file
+    levels_c = [g["C_rows%d" % l] for l in range(4)]
+    path_c = write_mlmc_file(str(tmp_path / "vec.hdf5"), levels_c, [[0.1]] * 4, chunk_rows=37)
+    storage = SampleStorageHDF(path_c, backend="min")
+    storage.resident_fraction = 0.0
+    storage.device_chunk_bytes = 6 * 16 * 50
+    spec_c = [QuantitySpec(name="v", unit="", shape=(6, 1), times=[0.0], locations=["0"])]
+    vec = make_root_quantity(storage, spec_c)["v"][0.0]["0"]
+    qm = qe.estimate_mean(qe.moments(vec, Legendre(5, tuple(g["C_domain"]))))
+    rel_close(qm.mean, g["C_bottom_mean"], rtol=1e-10)
+    rel_close(qm.var, g["C_bottom_var"], rtol=1e-10)
+    assert np.array_equal(qm.n_samples, g["C_bottom_n"])
+
+
 # ---------------------------------------------------------------- test/test_distribution.py
 @pytest.mark.parametrize("size", [5, 15, 25])
 def test_simple_distribution_matches_reference(golden, size):

@@ -57,6 +57,12 @@ def test_memory_storage_contract(golden):
     assert st2.n_finished().tolist() == [2.0, 3.0]
     st2.save_n_ops([(0, (10.0, 2)), (1, (30.0, 2))])
     assert st2.get_n_ops() == [5.0, 15.0]
+    # appending rows drops the resident device copies of THAT level (keys are (level, device))
+    st2._resident()[(1, "cuda:0")] = "stale"
+    st2._resident()[(1, "cuda:1")] = "stale"
+    st2._resident()[(0, "cuda:0")] = "kept"
+    st2.save_samples({1: [("L01_S0000003", (6 * np.ones(3), 7 * np.ones(3)))]}, {})
+    assert list(st2._resident()) == [(0, "cuda:0")] and st2.get_n_collected() == [2, 3]
 
 
 def test_npy_storage_roundtrip(tmp_path, golden):
@@ -69,13 +75,16 @@ def test_npy_storage_roundtrip(tmp_path, golden):
     assert st.get_level_parameters() == [[0.3], [0.1], [0.03], [0.003]]
 
 
-def test_hdf_adapter_needs_h5py():
+def test_hdf_adapter_backends():
+    """h5py is optional: without it the built-in reader is used; asking for h5py explicitly fails loudly if absent."""
     from mlmc_b200.sample_storage import SampleStorageHDF
+    with pytest.raises(FileNotFoundError):
+        SampleStorageHDF("/nonexistent.hdf5")
     try:
         import h5py  # noqa: F401
     except ImportError:
         with pytest.raises(ImportError, match="h5py"):
-            SampleStorageHDF("/nonexistent.hdf5")
+            SampleStorageHDF("/nonexistent.hdf5", backend="h5py")
 
 
 def test_allocation_and_regression_follow_reference(golden):
