@@ -185,3 +185,35 @@ def test_replicate_shards_cover_all_replicates():
             assert ranges[0][0] == 0 and ranges[-1][1] == n_rep
             assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
     assert dist.peer_state() is None and dist.peer_error() is False       # nothing set up in a plain process
+
+
+def test_product_tables_linearise_the_outer_products():
+    """phi_i phi_j = sum_k C[ij, k] phi^E_k for every family (Adams' formula for Legendre, exponent addition for the
+    monomials, product-to-sum for the trigonometric basis, L (x) L on top for a transformed basis), checked against the
+    oracle's basis tables; Legendre rows are convex combinations."""
+    from mlmc_b200.moments import Legendre, Monomial, Fourier, TransformedMoments
+    for fn, table, t in ((Legendre(12, (-1, 1)), orc.legendre_table, np.linspace(-1, 1, 41)),
+                         (Legendre(100, (-1, 1)), orc.legendre_table, np.linspace(-1, 1, 41)),
+                         (Monomial(7, (0, 1)), orc.monomial_table, np.linspace(0, 1, 41)),
+                         (Fourier(7), orc.fourier_table, np.linspace(0, 2 * np.pi, 57)),
+                         (Fourier(8), orc.fourier_table, np.linspace(0, 2 * np.pi, 57)),
+                         (Fourier(1), orc.fourier_table, np.linspace(0, 2 * np.pi, 5))):
+        r = fn.size
+        ext_fn, c_t = fn.product_table()
+        assert type(ext_fn) is type(fn) and c_t.shape == (ext_fn.size, r * r)
+        phi = table(t, ext_fn.size)
+        want = (phi[:, :r, None] * phi[:, None, :r]).reshape(len(t), -1)
+        assert np.abs(phi @ c_t - want).max() < 2e-14
+        assert fn.product_table()[1] is c_t                                   # memoised
+    leg = Legendre(30, (-1, 1))
+    c_t = leg.product_table()[1]
+    assert leg.product_table()[0].size == 59 and c_t.min() >= 0.0 and np.abs(c_t.sum(axis=0) - 1.0).max() < 1e-14
+    rng = np.random.default_rng(0)
+    l_mat = rng.normal(size=(4, 6))
+    tm = TransformedMoments(Legendre(6, (-1, 1)), l_mat)
+    ext_fn, c_t = tm.product_table()
+    t = np.linspace(-1, 1, 23)
+    phi_e = orc.legendre_table(t, ext_fn.size)
+    psi = orc.legendre_table(t, 6) @ l_mat.T
+    want = (psi[:, :, None] * psi[:, None, :]).reshape(len(t), -1)
+    assert c_t.shape == (11, 16) and np.abs(phi_e @ c_t - want).max() < 1e-12
