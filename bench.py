@@ -667,7 +667,7 @@ def bench_cfg3(ctx):
 
     def run_linear():
         acc_m.acc.zero_()
-        nat.moments_accumulate(ext_basis, x, acc_m.level(0))
+        nat.moments_accumulate(ext_basis, x, acc_m.level(0), sums_only=True)
         reduce(acc_m)
         out["lin"] = nat.level_sums_transform(acc_m, 1, c_dev).finalize()
 

@@ -38,6 +38,8 @@ _SIGNATURES = {
     "mlmcb200_moments_workspace_bytes": (_c_i64, [_c_i32, _c_i32]),
     "mlmcb200_moments_accumulate": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_i32, _c_i64,
                                                    _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
+    "mlmcb200_moments_accumulate_sums": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_i32, _c_i64,
+                                                        _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
     "mlmcb200_resample_indices": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, _c_i64, _c_i64, _c_i32, _c_i32,
                                                  _c_i32, _c_vp, _c_vp, _c_vp]),
     "mlmcb200_moments_resampled_workspace_bytes": (_c_i64, [_c_i32, _c_i32, _c_i32]),
@@ -248,8 +250,9 @@ class _on_device:
             self._ctx.__exit__(*exc)
 
 
-def moments_accumulate(basis, x, acc_row, valid=None):
-    """Add the chunk x [M, n, S] to ``acc_row`` ([2 + 2*M*R] float64, contiguous)."""
+def moments_accumulate(basis, x, acc_row, valid=None, sums_only=False):
+    """Add the chunk x [M, n, S] to ``acc_row`` ([2 + 2*M*R] float64, contiguous).  ``sums_only``: the caller does not
+    read the sums of squares (they are then unspecified) -- ``mlmcb200_moments_accumulate_sums``."""
     global launch_count
     M, n, has_coarse, sn, ss, sm = _chunk_layout(x)
     _require_cuda(acc_row, "acc")
@@ -270,9 +273,9 @@ def moments_accumulate(basis, x, acc_row, valid=None):
                 raise NativeError("moments workspace: %s" % lib.mlmcb200_last_error().decode())
             _ws_bytes_cache[key] = ws_bytes
         ws = _workspace(x.device, ws_bytes)
-        _check(lib.mlmcb200_moments_accumulate(ctypes.byref(basis), _ptr(x), n, M, sn, ss, sm, has_coarse,
-                                               _ptr(valid), _ptr(acc_row), _ptr(ws), ws.numel(), _stream()),
-               "moments_accumulate")
+        fn = lib.mlmcb200_moments_accumulate_sums if sums_only else lib.mlmcb200_moments_accumulate
+        _check(fn(ctypes.byref(basis), _ptr(x), n, M, sn, ss, sm, has_coarse, _ptr(valid), _ptr(acc_row), _ptr(ws),
+                  ws.numel(), _stream()), "moments_accumulate")
     launch_count += 2
 
 

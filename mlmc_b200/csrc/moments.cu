@@ -49,7 +49,9 @@ struct MomentsArgs {
 // PAIR (scalar quantity): lanes 2j and 2j+1 share ONE pair of columns -- the even lane keeps the sum of both, the odd
 // lane the sum of squares of both (one 64-bit shuffle) -- which halves the shared memory per thread and so doubles
 // the number of resident warps for a given number of moments.
-template <bool COARSE, int S, bool PAIR>
+// NOSQ (sums only: the caller needs no sums of squares, e.g. the moment sums behind the linearised covariance means):
+// one private column per thread, 6 instead of 7.25 FP64 instructions per sample-moment, half the shared memory.
+template <bool COARSE, int S, bool PAIR, bool NOSQ = false>
 __device__ __forceinline__ void accumulate(double* __restrict__ col, int sq_off, bool odd,
                                            const double (&vf)[S], const double (&vc)[S]) {
     // col = this thread's column entry of the moment (sm + k*T + tid); the squares live sq_off doubles further (private
@@ -58,6 +60,15 @@ __device__ __forceinline__ void accumulate(double* __restrict__ col, int sq_off,
     double d[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) d[s] = COARSE ? vf[s] - vc[s] : vf[s];
+    if (NOSQ) {
+#pragma unroll
+        for (int w = 1; w < S; w <<= 1) {
+#pragma unroll
+            for (int s = 0; s + w < S; s += 2 * w) d[s] += d[s + w];
+        }
+        *col += d[0];
+        return;
+    }
     double qa = d[0] * d[0], qb = d[1] * d[1];
 #pragma unroll
     for (int s = 2; s < S; s += 2) {
@@ -109,7 +120,7 @@ __device__ __forceinline__ void load_tile(const MomentsArgs& a, const double* ba
 // copies (cp.async.bulk + mbarrier, one elected thread), STAGES - 1 tiles ahead of the compute -- the variant for few
 // moments, where the kernel is HBM-bound and the two register-prefetched tiles per warp do not cover the DRAM latency.
 // GATHER (FAST, STAGES == 0 only): bootstrap re-sampling, sample i of replicate blockIdx.z is the row idx[z * n + i].
-template <int KIND, bool COARSE, bool LOG, int S, bool PAIR, bool FAST, int STAGES, bool GATHER>
+template <int KIND, bool COARSE, bool LOG, int S, bool PAIR, bool FAST, int STAGES, bool GATHER, bool NOSQ>
 __global__ void __launch_bounds__(kThreads)
 moments_acc_kernel(const MomentsArgs a) {
     extern __shared__ __align__(128) double sm[];
@@ -117,7 +128,8 @@ moments_acc_kernel(const MomentsArgs a) {
     const int tid = threadIdx.x;
     const int R = a.basis.size;
     const int M = a.n_comp;
-    const int n_cols = PAIR ? R : 2 * R;
+    static_assert(!(NOSQ && PAIR), "sums-only columns are private");
+    const int n_cols = (PAIR || NOSQ) ? R : 2 * R;
     for (int r = 0; r < n_cols; ++r) sm[r * T + tid] = 0.0;         // own column(s) only: no barrier needed
 
     // thread -> (component, sample lane)
@@ -152,7 +164,7 @@ moments_acc_kernel(const MomentsArgs a) {
     // moments are reduced strictly in increasing order: a running column pointer replaces the index arithmetic
 #define MB_ACC(K, VF, VC)                                                       \
     {                                                                            \
-        accumulate<COARSE, S, PAIR>(col, sq_off, odd_lane, VF, VC);              \
+        accumulate<COARSE, S, PAIR, NOSQ>(col, sq_off, odd_lane, VF, VC);        \
         col += T;                                                                \
     }
 
@@ -259,24 +271,51 @@ moments_acc_kernel(const MomentsArgs a) {
                 __syncthreads();                                   // every thread has read the stage: refill it
                 if (tid == 0 && k_tile + STAGES < my_tiles) issue_stage(k_tile + STAGES);
             }
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-                tf[s] = KIND == MLMCB200_RAW ? xf[s] : map_to_ref_t<LOG>(a.basis, xf[s]);
-                tc[s] = !COARSE ? 0.0 : (KIND == MLMCB200_RAW ? xc[s] : map_to_ref_t<LOG>(a.basis, xc[s]));
-                bool good;
-                if (a.basis.is_clip) {            // map_to_ref_t returns NaN outside [ref_lo, ref_hi]
-                    good = (tf[s] == tf[s]) && (!COARSE || tc[s] == tc[s]);
-                    if (KIND == MLMCB200_FOURIER && R == 1) good = true;
+            // Per-sample preamble.  The common case -- a clipped domain (safe_eval) -- is kept free of branches and of
+            // 64-bit index arithmetic on full tiles: affine map (3 FP64 ops per value, as the reference), closed-interval
+            // test (NaN fails it), select.  Unclipped bases take the generic validity test (rare NaN replay for Legendre).
+            if (KIND != MLMCB200_RAW && a.basis.is_clip) {
+                const double lo = a.basis.ref_lo, hi = a.basis.ref_hi;
+                const bool always = KIND == MLMCB200_FOURIER && R == 1;          // column 0 is the literal 1
+#define MB_CLASSIFY(IN_EXPR)                                                                             \
+    _Pragma("unroll") for (int s = 0; s < S; ++s) {                                                      \
+        const double vf = LOG ? log(xf[s]) : xf[s];                                                      \
+        const double t_f = __dadd_rn(__dmul_rn(__dsub_rn(vf, a.basis.shift), a.basis.scale), lo);        \
+        bool good = (t_f >= lo) && (t_f <= hi);                                                          \
+        double t_c = 0.0;                                                                                \
+        if (COARSE) {                                                                                    \
+            const double vc = LOG ? log(xc[s]) : xc[s];                                                  \
+            t_c = __dadd_rn(__dmul_rn(__dsub_rn(vc, a.basis.shift), a.basis.scale), lo);                 \
+            good = good && (t_c >= lo) && (t_c <= hi);                                                   \
+        }                                                                                                \
+        const bool in = (IN_EXPR);                                                                       \
+        good = (good || always) && in;                                                                   \
+        cnt_ok += good ? 1u : 0u;                                                                        \
+        cnt_rm += (in && !good) ? 1u : 0u;                                                               \
+        tf[s] = good ? t_f : 0.0;                                                                        \
+        tc[s] = good ? t_c : 0.0;                                                                        \
+        ok[s] = good;                                                                                    \
+    }
+                if (full) {
+                    MB_CLASSIFY(true)
                 } else {
-                    good = moments_finite(a.basis, tf[s]) && (!COARSE || moments_finite(a.basis, tc[s]));
+                    MB_CLASSIFY(first + s * T < a.n)
                 }
-                const bool in = full || first + s * T < a.n;
-                good = good && in;
-                cnt_ok += good ? 1u : 0u;
-                cnt_rm += (in && !good) ? 1u : 0u;
-                tf[s] = good ? tf[s] : 0.0;
-                tc[s] = good ? tc[s] : 0.0;
-                ok[s] = good;
+#undef MB_CLASSIFY
+            } else {
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    tf[s] = KIND == MLMCB200_RAW ? xf[s] : map_to_ref_t<LOG>(a.basis, xf[s]);
+                    tc[s] = !COARSE ? 0.0 : (KIND == MLMCB200_RAW ? xc[s] : map_to_ref_t<LOG>(a.basis, xc[s]));
+                    bool good = moments_finite(a.basis, tf[s]) && (!COARSE || moments_finite(a.basis, tc[s]));
+                    const bool in = full || first + s * T < a.n;
+                    good = good && in;
+                    cnt_ok += good ? 1u : 0u;
+                    cnt_rm += (in && !good) ? 1u : 0u;
+                    tf[s] = good ? tf[s] : 0.0;
+                    tc[s] = good ? tc[s] : 0.0;
+                    ok[s] = good;
+                }
             }
             if (STAGES == 0 && tile + gridDim.y < n_tiles) load_fast(tile + gridDim.y);
         } else {
@@ -471,7 +510,7 @@ moments_acc_kernel(const MomentsArgs a) {
             for (int r = 0; r < R; ++r) {
                 const double al = (KIND == MLMCB200_LEGENDRE) ? kLegAlpha[r] : 1.0;
                 out[2 + (int64_t)m * R + r] = sm[r * T + tid] * al;
-                out[2 + K + (int64_t)m * R + r] = sm[(R + r) * T + tid] * (al * al);
+                out[2 + K + (int64_t)m * R + r] = NOSQ ? 0.0 : sm[(R + r) * T + tid] * (al * al);
             }
         }
     } else if (!PAIR && TN <= 16) {
@@ -483,7 +522,7 @@ moments_acc_kernel(const MomentsArgs a) {
             double s1 = 0.0, s2 = 0.0;
             for (int j = 0; j < TN; ++j) {
                 s1 += sm[r * T + j * M + mm];
-                s2 += sm[(R + r) * T + j * M + mm];
+                if (!NOSQ) s2 += sm[(R + r) * T + j * M + mm];
             }
             const double al = (KIND == MLMCB200_LEGENDRE) ? kLegAlpha[r] : 1.0;
             out[2 + (int64_t)mm * R + r] = s1 * al;
@@ -502,7 +541,7 @@ moments_acc_kernel(const MomentsArgs a) {
             } else {
                 for (int j = lane; j < TN; j += 32) {
                     s1 += sm[r * T + j * M + mm];
-                    s2 += sm[(R + r) * T + j * M + mm];
+                    if (!NOSQ) s2 += sm[(R + r) * T + j * M + mm];
                 }
             }
             s1 = warp_sum(s1);
@@ -741,6 +780,7 @@ struct Plan {
     bool fast;    // scalar quantity in storage order: specialised addressing
     bool stream;  // few moments (HBM-bound): tiles staged through a TMA-fed shared-memory ring
     bool gather;  // re-sampled rows (bootstrap replicates in grid.z)
+    bool nosq;    // sums only (no sums of squares): scalar FAST variant, private columns of half the size
 };
 
 constexpr int kStages = 4;
@@ -753,8 +793,9 @@ int choose_S(int kind, bool coarse, bool scalar, bool stream) {
     return (!coarse && scalar && kind != MLMCB200_RAW && !stream) ? 16 : 8;
 }
 
-int plan_moments(int kind, int size, int n_comp, int64_t n, bool coarse, bool stream, Plan* p) {
+int plan_moments(int kind, int size, int n_comp, int64_t n, bool coarse, bool stream, Plan* p, bool nosq = false) {
     p->S = choose_S(kind, coarse, n_comp == 1, stream);
+    p->nosq = nosq;
     // Lane-pair columns halve the shared memory per thread at the price of a shuffle in every moment's reduction tail:
     // worth it only where private columns would cap the CTAs per SM below what the registers allow (2 for the
     // fine+coarse kernels), i.e. above ~56 moments.  MLMCB200_PAIR=0|1 overrides (experiments).
@@ -765,10 +806,11 @@ int plan_moments(int kind, int size, int n_comp, int64_t n, bool coarse, bool st
     }
     p->pair = n_comp == 1 && (size_t)2 * size * kThreads * sizeof(double) > 113u * 1024u;
     if (forced >= 0 && n_comp == 1) p->pair = forced != 0;
+    if (nosq) p->pair = false;
     p->fast = false;
     p->gather = false;
     p->stream = stream;
-    const size_t smem = (size_t)(p->pair ? 1 : 2) * size * kThreads * sizeof(double);
+    const size_t smem = (size_t)((p->pair || nosq) ? 1 : 2) * size * kThreads * sizeof(double);
     if (smem + 64 > 227u * 1024u) {        // 64 B: static shared memory of the kernel (sample counters)
         set_error("moments: size %d needs %zu B of shared memory per CTA (max %u)", size, smem, 227u * 1024u);
         return -1;
@@ -812,9 +854,10 @@ unsigned choose_partitions(unsigned slots, unsigned columns, int64_t tiles, unsi
     return best;
 }
 
-template <int KIND, bool COARSE, bool LOG, int S, bool PAIR, bool FAST, int STAGES = 0, bool GATHER = false>
+template <int KIND, bool COARSE, bool LOG, int S, bool PAIR, bool FAST, int STAGES = 0, bool GATHER = false,
+          bool NOSQ = false>
 int launch_moments(const MomentsArgs& a, Plan p, cudaStream_t st) {
-    auto kern = moments_acc_kernel<KIND, COARSE, LOG, S, PAIR, FAST, STAGES, GATHER>;
+    auto kern = moments_acc_kernel<KIND, COARSE, LOG, S, PAIR, FAST, STAGES, GATHER, NOSQ>;
     if (STAGES > 0) p.smem += (size_t)STAGES * ((size_t)S * kThreads * 16 + 8);
     // resident CTAs per SM for this variant and shared-memory size (registers may bind before shared memory);
     // the sample-partition dimension of the grid is sized to exactly one resident wave
@@ -859,6 +902,7 @@ int launch_moments_pair(const MomentsArgs& a, const Plan& p, cudaStream_t st) {
                           : launch_moments<KIND, COARSE, LOG, S, false, true, 0, true>(a, p, st);
     }
     if constexpr (KIND != MLMCB200_RAW) {
+        if (p.fast && p.nosq) return launch_moments<KIND, COARSE, LOG, S, false, true, 0, false, true>(a, p, st);
         if (p.fast)
             return p.pair ? launch_moments<KIND, COARSE, LOG, S, true, true>(a, p, st)
                           : launch_moments<KIND, COARSE, LOG, S, false, true>(a, p, st);
@@ -899,6 +943,8 @@ extern "C" int64_t mlmcb200_moments_workspace_bytes(int32_t size, int32_t n_comp
     Plan p;
     if (size < 1 || n_comp < 1) return -1;
     if (plan_moments(MLMCB200_LEGENDRE, size, n_comp, -1, true, false, &p) != 0) return -1;
+    Plan q;                                             // the sums-only variant may keep more CTAs per SM resident
+    if (plan_moments(MLMCB200_LEGENDRE, size, n_comp, -1, true, false, &q, true) == 0 && q.grid.y > p.grid.y) p = q;
     return (int64_t)p.grid.y * (2 + 2 * (int64_t)size * n_comp) * (int64_t)sizeof(double);
 }
 
@@ -909,7 +955,7 @@ int moments_accumulate_impl(const mlmcb200_basis_t* basis, const double* pairs, 
                             int64_t stride_n, int64_t stride_side, int64_t stride_m, int32_t has_coarse,
                             const uint8_t* valid, const int32_t* idx, int32_t n_rep, double* acc,
                             int64_t acc_rep_stride, void* workspace, int64_t workspace_bytes, cudaStream_t st,
-                            const char* who) {
+                            const char* who, bool sums_only = false) {
     if (check_basis(basis) != 0) return -1;
     MB_REQUIRE(n >= 0 && n_comp >= 1, "%s: bad n=%lld n_comp=%d", who, (long long)n, n_comp);
     MB_REQUIRE(acc != nullptr && workspace != nullptr, "%s: null acc/workspace", who);
@@ -926,7 +972,9 @@ int moments_accumulate_impl(const mlmcb200_basis_t* basis, const double* pairs, 
     const bool use_ring = fast && !gather && basis->size <= kStreamMaxMoments && basis->kind != MLMCB200_FOURIER &&
                           (stride_n == 2 || (!has_coarse && stride_n == 1)) &&
                           (reinterpret_cast<uintptr_t>(pairs) & 15) == 0 && n >= (int64_t)8 * kThreads * 8;
-    if (plan_moments(basis->kind, basis->size, n_comp, n, has_coarse != 0, use_ring, &p) != 0) return -1;
+    // sums only: the scalar FAST kernels have a variant without the sums of squares; everything else computes them anyway
+    const bool nosq = sums_only && fast && !gather && !use_ring && basis->kind != MLMCB200_RAW;
+    if (plan_moments(basis->kind, basis->size, n_comp, n, has_coarse != 0, use_ring, &p, nosq) != 0) return -1;
     const int64_t K = (int64_t)basis->size * n_comp;
     const int64_t stride = 2 + 2 * K;
     if (gather) {
@@ -983,6 +1031,15 @@ extern "C" int mlmcb200_moments_accumulate(const mlmcb200_basis_t* basis, const 
     return moments_accumulate_impl(basis, pairs, n, n_comp, stride_n, stride_side, stride_m, has_coarse, valid,
                                    nullptr, 1, acc, 0, workspace, workspace_bytes, (cudaStream_t)stream,
                                    "moments_accumulate");
+}
+
+extern "C" int mlmcb200_moments_accumulate_sums(const mlmcb200_basis_t* basis, const double* pairs, int64_t n,
+                                                int32_t n_comp, int64_t stride_n, int64_t stride_side,
+                                                int64_t stride_m, int32_t has_coarse, const uint8_t* valid,
+                                                double* acc, void* workspace, int64_t workspace_bytes, void* stream) {
+    return moments_accumulate_impl(basis, pairs, n, n_comp, stride_n, stride_side, stride_m, has_coarse, valid,
+                                   nullptr, 1, acc, 0, workspace, workspace_bytes, (cudaStream_t)stream,
+                                   "moments_accumulate_sums", true);
 }
 
 extern "C" int64_t mlmcb200_moments_resampled_workspace_bytes(int32_t size, int32_t n_comp, int32_t n_rep) {

@@ -220,7 +220,7 @@ def estimate_mean(quantity, variance=True):
             basis = plan.ext_fn.basis_struct()
             if acc is None:
                 acc = _native.LevelAccumulator(n_levels, x.shape[0] * basis.size, device)
-            _native.moments_accumulate(basis, x, acc.level(level_id))
+            _native.moments_accumulate(basis, x, acc.level(level_id), sums_only=True)
         elif plan.kind == "covariance":
             basis = plan.fn.basis_struct()
             if acc is None:

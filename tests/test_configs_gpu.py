@@ -85,7 +85,7 @@ def test_cfg3_full_size_linearised_equals_dmma():
     ext_fn, c_t = fn.product_table()
     assert ext_fn.size == 2 * R - 1
     mom = nat.LevelAccumulator(1, ext_fn.size, dev())
-    nat.moments_accumulate(ext_fn.basis_struct(), x, mom.level(0))
+    nat.moments_accumulate(ext_fn.basis_struct(), x, mom.level(0), sums_only=True)
     lin = nat.level_sums_transform(mom, 1, torch.from_numpy(c_t).to(dev()))
     cov = nat.LevelAccumulator(1, R * R, dev())
     nat.gram_accumulate(fn.basis_struct(), x, cov.level(0), mode=0, want_var=False)
