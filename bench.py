@@ -361,6 +361,8 @@ def host_topology(ctx):
         pass
     src = torch.empty(32 << 20, dtype=torch.float64).pin_memory()                 # 256 MB
     dst = torch.empty_like(src)
+    threads_before = torch.get_num_threads()
+    torch.set_num_threads(max(1, info["cpus_allowed"] // ctx.world))              # torchrun sets OMP_NUM_THREADS=1
     src.fill_(1.0)
     dst.copy_(src)
     ctx.barrier()
@@ -370,6 +372,7 @@ def host_topology(ctx):
     gbs = 3 * 2 * src.numel() * 8 / (time.perf_counter() - t0) / 1e9            # read + write
     info["host_copy_gbs_per_rank_all_ranks_copying"] = -ctx.max_over_ranks(-gbs)   # the slowest rank's
     info["host_copy_threads"] = torch.get_num_threads()
+    torch.set_num_threads(threads_before)
     return info
 
 
@@ -772,7 +775,8 @@ def bench_cfg4(ctx, levels, steps):
         ctx.torch.cuda.synchronize()
         times.append((time.perf_counter() - t0) * 1e3)
     before = ctx.nat.launch_count
-    ms_eval = ctx.timed(lambda: ctx.nat.maxent_fgh(sd._quad_moments_dev, sd._weights_dev, sd._lam_dev, 7, sd._out_dev), 20)
+    buf = sd._buffers
+    ms_eval = ctx.timed(lambda: ctx.nat.maxent_fgh(buf.phi, buf.w, buf.lam, 7, buf.out, workspace=buf.workspace), 20)
     xs = np.linspace(dom[0], dom[1], 201)
     ob = orc.Basis("legendre", 50, dom, safe_eval=False, matrix=info[2])
     t0 = time.perf_counter()
@@ -784,7 +788,7 @@ def bench_cfg4(ctx, levels, steps):
     out = {"workload": "cfg4: max-ent fit, %d moments (orthogonalised Legendre 50), %d Gauss nodes, trust-ncg" % (r, q),
            "fit_ms": float(np.median(times)), "fit_ms_min": float(np.min(times)), "nit": int(res.nit),
            "success": bool(res.success), "device_evals": int(sd.n_device_evals), "fgh_eval_ms": ms_eval,
-           "fgh_eval_tflops": flop / (ms_eval * 1e-3) / 1e12, "launches_per_eval": (ctx.nat.launch_count - before) // 21,
+           "fgh_eval_tflops": flop / (ms_eval * 1e-3) / 1e12, "launches_per_eval": (ctx.nat.launch_count - before) // 21, "cuda_graph": buf.graph is not None,
            "cpu": {"kind": "port", "cores": "numpy/BLAS default threads", "fit_ms": cpu_ms,
                    "sample": "the same fit by the oracle (NumPy + scipy trust-ncg on the same fixed rule)"},
            "max_abs_multiplier_diff_vs_oracle": float(np.max(np.abs(sd.multipliers - ofit.multipliers))),

@@ -135,12 +135,15 @@ def sm_count():
 
 
 # ---------------------------------------------------------------------------------------------------------
-def basis_eval(basis, x, n_out, matrix=None):
-    """x: flat CUDA float64 tensor [n] -> Phi [n, n_out]."""
+def basis_eval(basis, x, n_out, matrix=None, out=None):
+    """x: flat CUDA float64 tensor [n] -> Phi [n, n_out] (written into ``out`` if given: contiguous, that shape)."""
     global launch_count
     _require_cuda(x, "x")
     x = x.contiguous()
-    out = torch.empty((x.numel(), n_out), dtype=torch.float64, device=x.device)
+    if out is None:
+        out = torch.empty((x.numel(), n_out), dtype=torch.float64, device=x.device)
+    elif tuple(out.shape) != (x.numel(), n_out) or not out.is_contiguous() or out.dtype != torch.float64:
+        raise NativeError("basis_eval: out must be a contiguous float64 tensor of shape (%d, %d)" % (x.numel(), n_out))
     n_rows = 0
     if matrix is not None:
         _require_cuda(matrix, "matrix")
@@ -420,7 +423,15 @@ def gram_accumulate(basis, x, acc_row, mode=0, want_var=True):
     launch_count += 2
 
 
-def maxent_fgh(phi, w, lam_scaled, what=7, out=None):
+def maxent_workspace(phi, n_moments):
+    """A private scratch tensor for ``maxent_fgh`` on ``phi`` (callers that capture the evaluation in a CUDA graph)."""
+    n_bytes = load().mlmcb200_maxent_workspace_bytes(phi.shape[0], n_moments)
+    if n_bytes < 0:
+        raise NativeError("maxent workspace: %s" % load().mlmcb200_last_error().decode())
+    return torch.empty(max(int(n_bytes), 8), dtype=torch.uint8, device=phi.device)
+
+
+def maxent_fgh(phi, w, lam_scaled, what=7, out=None, workspace=None):
     """phi [Q, ld] (R = len(lam_scaled) <= ld), w [Q] -> out [1 + R + R*R] (F, g, H integral terms)."""
     global launch_count
     _require_cuda(phi, "phi")
@@ -433,12 +444,15 @@ def maxent_fgh(phi, w, lam_scaled, what=7, out=None):
     if out is None:
         out = torch.zeros(1 + R + R * R, dtype=torch.float64, device=phi.device)
     lib = load()
-    with torch.cuda.device(phi.device):
-        ws_bytes = lib.mlmcb200_maxent_workspace_bytes(Q, R)
-        ws = _workspace(phi.device, ws_bytes)
+    with _on_device(phi.device):
+        if workspace is not None:
+            ws = workspace
+        else:
+            ws_bytes = lib.mlmcb200_maxent_workspace_bytes(Q, R)
+            ws = _workspace(phi.device, ws_bytes)
         _check(lib.mlmcb200_maxent_fgh(_ptr(phi), ld, _ptr(w), _ptr(lam_scaled), Q, R, what, _ptr(out), _ptr(ws),
                                        ws.numel(), _stream()), "maxent_fgh")
-    launch_count += 2
+    launch_count += 3
     return out
 
 

@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 SRC_DIR = os.path.join(PKG_DIR, "csrc")
 OUT_DIR = os.path.join(PKG_DIR, "_lib")
 LIB_PATH = os.path.join(OUT_DIR, "libmlmcb200.so")
-SOURCES = ["api.cu", "moments.cu", "basis_eval.cu", "gram.cu", "select.cu", "peer.cu"]
+SOURCES = ["api.cu", "moments.cu", "basis_eval.cu", "gram.cu", "maxent.cu", "select.cu", "peer.cu"]
 HEADERS = ["common.cuh", "legendre_tables.inc", os.path.join("..", "..", "include", "mlmcb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

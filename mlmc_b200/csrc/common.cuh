@@ -41,6 +41,11 @@ static __constant__ double kLegAlpha[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_ALPHA_
 int launch_reduce_partials(const double* partial, int n_partials, int64_t stride, int64_t len, double* acc,
                            cudaStream_t st);
 
+// defined in maxent.cu: the max-ent F / g / H kernels for up to 104 moments; returns 1 when the size is not covered
+int64_t maxent_fast_workspace_bytes(int64_t n_nodes, int R);
+int maxent_fast_launch(const double* phi, int64_t ld_g, const double* w, const double* lam, int64_t n_nodes, int R,
+                       int want_h, double* out, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+
 // ---------------------------------------------------------------------------------------------
 // Moments.transform (mlmc/moments.py:28-39, 58-73).  The affine map is evaluated with the same three
 // IEEE operations as the reference ((v - shift) * scale + ref_lo, no FMA contraction) so that the

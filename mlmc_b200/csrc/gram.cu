@@ -371,8 +371,8 @@ __global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a)
 
 int popcount4(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1); }
 
-// n_warps / n_slots: warps that contract and task slots per warp; two_tiles: room for a second tile (unused now)
-int make_plan(int R, int n_warps, int n_slots, bool two_tiles, GramPlan* pl, size_t* smem, int fixed_ld = 0) {
+// n_warps / n_slots: warps that contract and task slots per warp
+int make_plan(int R, int n_warps, int n_slots, GramPlan* pl, size_t* smem, int fixed_ld = 0) {
     const int nb = (R + 7) / 8;
     if (fixed_ld && R > kGramMaxMoments) {
         set_error("gram: %d moments do not fit the shared-memory tile (max %d)", R, kGramMaxMoments);
@@ -440,19 +440,17 @@ int make_plan(int R, int n_warps, int n_slots, bool two_tiles, GramPlan* pl, siz
     while (ld % 8 != 4) ++ld;
     if (fixed_ld) ld = fixed_ld;
     pl->ld = ld;
-    // tile(s) of Phi_f + Phi_c rows; NS a multiple of 4
+    // tile of Phi_f + Phi_c rows; NS a multiple of 4
     const size_t budget = 216u * 1024u;
-    const int n_tiles = two_tiles ? 2 : 1;
-    int ns = (int)(budget / ((size_t)2 * n_tiles * ld * sizeof(double)));
+    int ns = (int)(budget / ((size_t)2 * ld * sizeof(double)));
     ns = fixed_ld ? (ns / 16) * 16 : (ns / 4) * 4;      // covariance tiles: whole 4-k-step unrolled bodies
-    const int cap = two_tiles ? 64 : 128;
-    if (ns > cap) ns = cap;
+    if (ns > 128) ns = 128;
     if (ns < 8) {
         set_error("gram: %d moments do not fit the shared-memory tile", R);
         return -1;
     }
     pl->ns = ns;
-    *smem = (size_t)2 * n_tiles * ns * ld * sizeof(double);
+    *smem = (size_t)2 * ns * ld * sizeof(double);
     return 0;
 }
 
@@ -660,7 +658,7 @@ extern "C" int mlmcb200_gram_accumulate(const mlmcb200_basis_t* basis, const dou
     a.stride_n = stride_n;
     a.stride_side = stride_side;
     size_t smem = 0;
-    if (make_plan(basis->size, kWarps, 2, false, &a.plan, &smem, kLD) != 0) return -1;
+    if (make_plan(basis->size, kWarps, 2, &a.plan, &smem, kLD) != 0) return -1;
     const int64_t R2 = (int64_t)basis->size * basis->size;
     const int64_t stride = 2 + 2 * R2;
     const int64_t tiles = (n + a.plan.ns - 1) / a.plan.ns;
@@ -685,7 +683,9 @@ extern "C" int mlmcb200_gram_accumulate(const mlmcb200_basis_t* basis, const dou
 
 extern "C" int64_t mlmcb200_maxent_workspace_bytes(int64_t n_nodes, int32_t size) {
     if (size < 1 || size > MLMCB200_MAX_MOMENTS || n_nodes < 0) return -1;
-    return (int64_t)sm_count() * (1 + (int64_t)size + (int64_t)size * size) * (int64_t)sizeof(double);
+    const int64_t v1 = (int64_t)sm_count() * (1 + (int64_t)size + (int64_t)size * size) * (int64_t)sizeof(double);
+    const int64_t v2 = maxent_fast_workspace_bytes(n_nodes, size);
+    return v1 > v2 ? v1 : v2;
 }
 
 extern "C" int mlmcb200_maxent_fgh(const double* phi, int64_t ld, const double* w, const double* lam_scaled,
@@ -694,31 +694,39 @@ extern "C" int mlmcb200_maxent_fgh(const double* phi, int64_t ld, const double* 
     MB_REQUIRE(phi && w && lam_scaled && out && workspace, "maxent_fgh: null pointer");
     MB_REQUIRE(size >= 1 && size <= MLMCB200_MAX_MOMENTS && ld >= size && n_nodes >= 1, "maxent_fgh: bad sizes");
     MB_REQUIRE((what & 7) != 0, "maxent_fgh: nothing requested");
-    MaxentArgs a;
-    a.phi = phi;
-    a.ld_g = ld;
-    a.w = w;
-    a.lam = lam_scaled;
-    a.n_nodes = n_nodes;
-    a.R = size;
-    a.want_h = (what & 4) ? 1 : 0;
-    size_t smem = 0;
-    if (make_plan(size, kWarps, 2, false, &a.plan, &smem) != 0) return -1;
-    // single table + weights + multipliers instead of two tables + flags
-    const int ns = a.plan.ns;
-    smem = ((size_t)ns * a.plan.ld + ns + 8 * a.plan.nb) * sizeof(double);
-    const size_t red_bytes = (size_t)kWarps * (1 + MLMCB200_MAX_MOMENTS) * sizeof(double);   // F / g partials per warp
-    if (smem < red_bytes) smem = red_bytes;
-    const int grid = maxent_grid(n_nodes, ns);
-    const int64_t stride = 1 + (int64_t)size + (int64_t)size * size;
-    MB_REQUIRE(workspace_bytes >= (int64_t)grid * stride * 8, "maxent_fgh: workspace too small");
-    a.partial = static_cast<double*>(workspace);
-    a.partial_stride = stride;
     cudaStream_t st = (cudaStream_t)stream;
-    auto kern = a.plan.gs == 1 ? maxent_kernel<1> : maxent_kernel<2>;
-    MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreadsGram, smem, st>>>(a);
-    MB_CUDA_OK(cudaGetLastError());
+    const int64_t stride = 1 + (int64_t)size + (int64_t)size * size;
+    const int want_h = (what & 4) ? 1 : 0;
+    int grid = 0;
+    // up to 104 moments: the kernels of maxent.cu; beyond: the first version below
+    int rc = (getenv("MLMCB200_MAXENT_V1") != nullptr) ? 1 : maxent_fast_launch(
+        phi, ld, w, lam_scaled, n_nodes, size, want_h, out, workspace, workspace_bytes, st);
+    if (rc <= 0) return rc;
+    MB_REQUIRE(workspace_bytes >= (int64_t)sm_count() * stride * 8, "maxent_fgh: workspace too small");
+    MaxentArgs a;
+    a.want_h = want_h;
+    a.partial = static_cast<double*>(workspace);
+    {
+        a.phi = phi;
+        a.ld_g = ld;
+        a.w = w;
+        a.lam = lam_scaled;
+        a.n_nodes = n_nodes;
+        a.R = size;
+        size_t smem = 0;
+        if (make_plan(size, kWarps, 2, &a.plan, &smem) != 0) return -1;
+        // single table + weights + multipliers instead of two tables + flags
+        const int ns = a.plan.ns;
+        smem = ((size_t)ns * a.plan.ld + ns + 8 * a.plan.nb) * sizeof(double);
+        const size_t red_bytes = (size_t)kWarps * (1 + MLMCB200_MAX_MOMENTS) * sizeof(double);   // F / g partials per warp
+        if (smem < red_bytes) smem = red_bytes;
+        grid = maxent_grid(n_nodes, ns);
+        a.partial_stride = stride;
+        auto kern = a.plan.gs == 1 ? maxent_kernel<1> : maxent_kernel<2>;
+        MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kThreadsGram, smem, st>>>(a);
+        MB_CUDA_OK(cudaGetLastError());
+    }
     const int64_t len = a.want_h ? stride : 1 + size;
     const int threads = 256;
     sum_partials_kernel<<<(unsigned)((len + threads - 1) / threads), threads, 0, st>>>(a.partial, grid, stride, len, out);

@@ -117,10 +117,11 @@ class Moments:
             self._product_table = hit
         return hit
 
-    def _eval_device(self, value, size):
-        """value: CUDA float64 tensor of any shape -> CUDA tensor ``value.shape + (size,)``."""
+    def _eval_device(self, value, size, out=None):
+        """value: CUDA float64 tensor of any shape -> CUDA tensor ``value.shape + (size,)`` (``out``: optional
+        contiguous ``[value.numel(), size]`` tensor to write into)."""
         flat = value.reshape(-1)
-        out = _native.basis_eval(self.basis_struct(size), flat, size)
+        out = _native.basis_eval(self.basis_struct(size), flat, size, out=out)
         return out.reshape(tuple(value.shape) + (size,))
 
     def _eval_all(self, value, size):
@@ -349,9 +350,9 @@ class TransformedMoments(Moments):
             self._matrix_dev = torch.from_numpy(np.ascontiguousarray(self.transform_matrix())).to(device)
         return self._matrix_dev
 
-    def _eval_device(self, value, size):
+    def _eval_device(self, value, size, out=None):
         flat = value.reshape(-1)
-        out = _native.basis_eval(self.basis_struct(), flat, size, self._matrix_on(value.device))
+        out = _native.basis_eval(self.basis_struct(), flat, size, self._matrix_on(value.device), out=out)
         return out.reshape(tuple(value.shape) + (size,))
 
     def _derived(self, fn_name, value, size, **kw):

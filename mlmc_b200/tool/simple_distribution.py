@@ -74,6 +74,62 @@ def _pinned_vectors(size):
     return hit
 
 
+class _FitBuffers:
+    """Device / pinned buffers of one (device, n_nodes, n_moments) fit shape, kept across fits, and the CUDA graph of
+    one functional evaluation on them: H2D of the scaled multipliers -> rho / H / sum kernels -> D2H of [F | g | H].
+    A fit then costs one graph launch + one stream synchronisation per evaluation instead of ~10 host calls."""
+
+    def __init__(self, device, n_nodes, size):
+        self.phi = torch.empty((n_nodes, size), dtype=torch.float64, device=device)
+        self.w = torch.empty(n_nodes, dtype=torch.float64, device=device)
+        self.lam = torch.zeros(size, dtype=torch.float64, device=device)
+        self.out = torch.zeros(1 + size + size * size, dtype=torch.float64, device=device)
+        self.out_host, self.lam_host = _pinned_vectors(size)
+        self.out_np, self.lam_np = self.out_host.numpy(), self.lam_host.numpy()
+        self.workspace = _native.maxent_workspace(self.phi, size)
+        self.owner = None
+        self.graph = None
+        self.n_evals = 0
+
+    def _enqueue(self):
+        self.lam.copy_(self.lam_host, non_blocking=True)
+        _native.maxent_fgh(self.phi, self.w, self.lam, 7, self.out, workspace=self.workspace)
+        self.out_host.copy_(self.out, non_blocking=True)
+
+    def evaluate(self):
+        """``lam_np`` holds the scaled multipliers -> ``out_np`` = [F | g | H] (valid until the next call)."""
+        self.n_evals += 1
+        if self.graph is None and self.n_evals > 2 and _USE_GRAPH:
+            # third evaluation on these buffers: worth a capture (the first two ran eagerly and warmed the workspace)
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream(self.phi.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    self._enqueue()
+            self.graph = graph
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
+        torch.cuda.current_stream().synchronize()
+        return self.out_np
+
+
+_USE_GRAPH = True
+_fit_buffers = {}
+
+
+def _fit_buffers_for(device, n_nodes, size):
+    key = (str(device), int(n_nodes), int(size))
+    hit = _fit_buffers.get(key)
+    if hit is None:
+        if len(_fit_buffers) >= 8:
+            _fit_buffers.clear()
+        hit = _fit_buffers[key] = _FitBuffers(device, n_nodes, size)
+    return hit
+
+
 class SimpleDistribution:
     """Calculation of the distribution (``simple_distribution.py:9-327``)."""
 
@@ -156,16 +212,20 @@ class SimpleDistribution:
         self._quad_points = nodes
         self._quad_weights = weights
         self._nodes_dev, self._weights_dev = _gauss_panels_on(dev, self.domain, self._n_panels, self._gauss_degree)
-        self._quad_moments_dev = self.moments_fn.eval_all(self._nodes_dev, self.approx_size).contiguous()
-        self._sigma_dev = torch.from_numpy(np.ascontiguousarray(self._moment_errs)).to(dev)
-        self._lam_dev = torch.empty(self.approx_size, dtype=torch.float64, device=dev)
-        self._out_dev = torch.zeros(1 + self.approx_size + self.approx_size ** 2, dtype=torch.float64, device=dev)
-        self._out_host, self._lam_host = _pinned_vectors(self.approx_size)
+        # the moment table and the weights go into buffers that persist across fits of this shape (and with them the
+        # CUDA graph of one evaluation); this fit owns them until another fit of the same shape starts
+        buf = self._buffers = _fit_buffers_for(dev, len(nodes), self.approx_size)
+        buf.owner = self
+        self.moments_fn._eval_device(self._nodes_dev, self.approx_size, out=buf.phi)
+        buf.w.copy_(self._weights_dev)
+        self._quad_moments_dev = buf.phi
         self._cache_key = None
 
     @property
     def _quad_moments(self):
         """Moment table of the nodes as a NumPy array (reference attribute name)."""
+        if self._buffers.owner is not self:
+            self._update_quadrature(self.multipliers, force=True)
         return self._quad_moments_dev.cpu().numpy()
 
     def _integrals(self, multipliers):
@@ -175,18 +235,20 @@ class SimpleDistribution:
         key = multipliers.tobytes()
         if key != self._cache_key:
             r = self.approx_size
-            self._lam_host.copy_(torch.from_numpy(multipliers / self._moment_errs))
-            self._lam_dev.copy_(self._lam_host, non_blocking=True)
-            _native.maxent_fgh(self._quad_moments_dev, self._weights_dev, self._lam_dev, 7, self._out_dev)
-            self._out_host.copy_(self._out_dev, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            out = self._out_host.numpy()
+            buf = self._buffers
+            if buf.owner is not self:                      # another fit of the same shape took the buffers: take them back
+                self._update_quadrature(multipliers, force=True)
+                buf = self._buffers
+            np.divide(multipliers, self._moment_errs, out=buf.lam_np)
+            out = buf.evaluate()
             self._cache = (float(out[0]), out[1:1 + r].copy(), out[1 + r:].reshape(r, r).copy())
             self._cache_key = key
             self.n_device_evals += 1
         return self._cache
 
     def _density_in_quads(self, multipliers):
+        if self._buffers.owner is not self:
+            self._update_quadrature(multipliers, force=True)
         power = -(self._quad_moments_dev @ torch.from_numpy(np.asarray(multipliers / self._moment_errs)).to(
             self._quad_moments_dev.device))
         return torch.exp(torch.clamp(power, -200, 200)).cpu().numpy()
