@@ -156,6 +156,27 @@ int mlmcb200_finalize_levels(const double* acc, int64_t acc_stride, int32_t n_le
                              double* l_means, double* l_vars, double* mean, double* var, void* stream);
 
 /*
+ * One whole estimate_mean over a `moments` quantity in ONE call (mlmc/quantity/quantity_estimate.py:22-80 with the
+ * operation of :105-110): zero the accumulators, mlmcb200_moments_accumulate of every level (levels[l]: host array of
+ * descriptors of device rows, one chunk per level), mlmcb200_finalize_levels, and -- if host_out != NULL (pinned host
+ * memory) -- the copy of the packed result to the host followed by a stream synchronisation.  For callers whose levels
+ * are resident in device memory: the ~10 separate host calls of the step-by-step route cost more than the kernels of a
+ * small estimate (cfg1: 1e5 samples).  out / host_out (doubles):
+ *     [l_means (L*K) | l_vars (L*K) | mean (K) | var (K) | n_samples, n_rm_samples per level (2 L)],  K = n_comp * size.
+ */
+typedef struct {
+    const double*  pairs;        /* device rows of the level (layout above) */
+    int64_t        n;            /* samples */
+    int64_t        stride_n, stride_side, stride_m;
+    int32_t        has_coarse;
+    int32_t        reserved;
+    const uint8_t* valid;        /* mlmcb200_sample_mask result for n_comp > 128, else NULL */
+} mlmcb200_level_t;
+int mlmcb200_estimate_moments_levels(const mlmcb200_basis_t* basis, const mlmcb200_level_t* levels, int32_t n_levels,
+                                     int32_t n_comp, double* acc, int64_t acc_stride, double* out, double* host_out,
+                                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * Covariance level sums from moment level sums.  The reference forms per-sample outer products phi_i phi_j
  * (mlmc/quantity/quantity_estimate.py:131-147) and sums them; products of Legendre / monomial / trigonometric
  * functions are exact linear combinations of a longer basis of the same family (phi_i phi_j = sum_k C[ij][k] phi_k,

@@ -25,6 +25,12 @@ class BasisStruct(ctypes.Structure):
                 ("shift", _c_dbl), ("scale", _c_dbl), ("ref_lo", _c_dbl), ("ref_hi", _c_dbl)]
 
 
+class LevelStruct(ctypes.Structure):
+    """mlmcb200_level_t"""
+    _fields_ = [("pairs", _c_vp), ("n", _c_i64), ("stride_n", _c_i64), ("stride_side", _c_i64), ("stride_m", _c_i64),
+                ("has_coarse", _c_i32), ("reserved", _c_i32), ("valid", _c_vp)]
+
+
 RAW_BASIS = BasisStruct(RAW, 1, 0, 0, 0.0, 1.0, 0.0, 0.0)
 
 _SIGNATURES = {
@@ -53,6 +59,8 @@ _SIGNATURES = {
                                                 _c_vp]),
     "mlmcb200_finalize_levels_batched": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i64, _c_i32, _c_i64, _c_vp,
                                                         _c_vp]),
+    "mlmcb200_estimate_moments_levels": (ctypes.c_int, [ctypes.POINTER(BasisStruct), ctypes.POINTER(LevelStruct), _c_i32,
+                                                        _c_i32, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp]),
     "mlmcb200_level_sums_transform": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i32, _c_i32, _c_vp, _c_i32, _c_vp,
                                                      _c_i64, _c_vp]),
     "mlmcb200_peer_buffer_bytes": (_c_i64, [_c_i32, _c_i64]),
@@ -355,6 +363,70 @@ def finalize_levels_batched(acc):
                                                        _stream()), "finalize_levels_batched")
     launch_count += 1
     return out
+
+
+class EstimatePlan:
+    """Everything ``mlmcb200_estimate_moments_levels`` needs for one (quantity, basis) on resident levels, marshalled
+    once: level descriptors, accumulator / result / pinned host buffers, workspace.  ``run()`` is ONE C call
+    (memset + kernels + finalize + D2H + synchronise) and returns the packed host result as a NumPy view."""
+
+    def __init__(self, basis, views, n_levels):
+        """views: {level_id: CUDA tensor [M, n, S]} (levels without samples may be missing)."""
+        first = next(iter(views.values()))
+        self.device = first.device
+        self.basis = basis
+        self.M = int(first.shape[0])
+        self.L = int(n_levels)
+        self.K = self.M * basis.size
+        if self.M > 128 or basis.size > 112 and self.M > 1:
+            raise NativeError("EstimatePlan covers quantities the kernel masks itself (<= 128 components)")
+        levels = (LevelStruct * self.L)()
+        self.keys = []
+        for l in range(self.L):
+            x = views.get(l)
+            if x is None:
+                levels[l] = LevelStruct(None, 0, 0, 0, 0, 0, 0, None)
+                self.keys.append(None)
+                continue
+            M, n, has_coarse, sn, ss, sm = _chunk_layout(x)
+            if M != self.M:
+                raise NativeError("EstimatePlan: levels differ in the number of components")
+            levels[l] = LevelStruct(x.data_ptr(), n, sn, ss, sm, has_coarse, 0, None)
+            self.keys.append((x.data_ptr(), tuple(x.shape), tuple(x.stride())))
+        self.levels = levels
+        self.views = views                       # keeps the rows alive
+        self.acc = torch.zeros((self.L, 2 + 2 * self.K), dtype=torch.float64, device=self.device)
+        n_out = 2 * self.L * self.K + 2 * self.K + 2 * self.L
+        self.out = torch.empty(n_out, dtype=torch.float64, device=self.device)
+        self.host = torch.empty(n_out, dtype=torch.float64).pin_memory()
+        self.host_np = self.host.numpy()
+        lib = load()
+        ws_bytes = lib.mlmcb200_moments_workspace_bytes(basis.size, self.M)
+        if ws_bytes < 0:
+            raise NativeError("moments workspace: %s" % lib.mlmcb200_last_error().decode())
+        self.ws = torch.empty(max(int(ws_bytes), 8), dtype=torch.uint8, device=self.device)
+        self._args = (ctypes.byref(self.basis), self.levels, self.L, self.M, _ptr(self.acc), self.acc.stride(0),
+                      _ptr(self.out), ctypes.c_void_p(self.host.data_ptr()), _ptr(self.ws), self.ws.numel())
+        self._fn = lib.mlmcb200_estimate_moments_levels
+        self.n_launches = 2 * sum(1 for k in self.keys if k is not None) + 1
+
+    def matches(self, views):
+        if len(views) != sum(1 for k in self.keys if k is not None):
+            return False
+        for l, key in enumerate(self.keys):
+            x = views.get(l)
+            if (x is None) != (key is None):
+                return False
+            if x is not None and key != (x.data_ptr(), tuple(x.shape), tuple(x.stride())):
+                return False
+        return True
+
+    def run(self):
+        global launch_count
+        with _on_device(self.device):
+            _check(self._fn(*self._args, _stream()), "estimate_moments_levels")
+        launch_count += self.n_launches
+        return self.host_np
 
 
 def level_sums_transform(acc_in, n_comp, mat_t):

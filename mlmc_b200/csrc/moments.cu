@@ -698,8 +698,10 @@ __global__ void sample_mask_kernel(const mlmcb200_basis_t basis, const double* _
 // [l_means (L*K) | l_vars (L*K) | mean (K) | var (K)] when out_batch_stride != 0
 __global__ void finalize_levels_kernel(const double* __restrict__ acc, int64_t acc_stride, int n_levels, int64_t K,
                                        double* l_means, double* l_vars, double* mean, double* var,
-                                       int64_t acc_batch_stride, int64_t out_batch_stride) {
+                                       int64_t acc_batch_stride, int64_t out_batch_stride, double* counts = nullptr) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (counts != nullptr && k < 2 * (int64_t)n_levels)        // [n_samples, n_rm_samples] per level, packed
+        counts[k] = acc[(k >> 1) * acc_stride + (k & 1)];
     if (k >= K) return;
     acc += (int64_t)blockIdx.y * acc_batch_stride;
     const int64_t out_off = (int64_t)blockIdx.y * out_batch_stride;
@@ -1118,6 +1120,39 @@ extern "C" int mlmcb200_finalize_levels(const double* acc, int64_t acc_stride, i
     finalize_levels_kernel<<<(unsigned)((K + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
         acc, acc_stride, n_levels, K, l_means, l_vars, mean, var, 0, 0);
     MB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mlmcb200_estimate_moments_levels(const mlmcb200_basis_t* basis, const mlmcb200_level_t* levels,
+                                                int32_t n_levels, int32_t n_comp, double* acc, int64_t acc_stride,
+                                                double* out, double* host_out, void* workspace,
+                                                int64_t workspace_bytes, void* stream) {
+    if (check_basis(basis) != 0) return -1;
+    MB_REQUIRE(levels != nullptr && n_levels >= 1 && n_comp >= 1 && acc != nullptr && out != nullptr,
+               "estimate_moments_levels: bad arguments");
+    const int64_t K = (int64_t)n_comp * basis->size;
+    MB_REQUIRE(acc_stride >= 2 + 2 * K, "estimate_moments_levels: accumulator stride too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    MB_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)n_levels * acc_stride * sizeof(double), st));
+    for (int l = 0; l < n_levels; ++l) {
+        const mlmcb200_level_t& lv = levels[l];
+        if (lv.n == 0) continue;
+        const int rc = moments_accumulate_impl(basis, lv.pairs, lv.n, n_comp, lv.stride_n, lv.stride_side, lv.stride_m,
+                                               lv.has_coarse, lv.valid, nullptr, 1, acc + (int64_t)l * acc_stride, 0,
+                                               workspace, workspace_bytes, st, "estimate_moments_levels");
+        if (rc != 0) return rc;
+    }
+    const int64_t LK = (int64_t)n_levels * K;
+    const int threads = 128;
+    const int64_t work = K > 2 * n_levels ? K : 2 * n_levels;
+    finalize_levels_kernel<<<(unsigned)((work + threads - 1) / threads), threads, 0, st>>>(
+        acc, acc_stride, n_levels, K, out, out + LK, out + 2 * LK, out + 2 * LK + K, 0, 0, out + 2 * LK + 2 * K);
+    MB_CUDA_OK(cudaGetLastError());
+    if (host_out != nullptr) {
+        MB_CUDA_OK(cudaMemcpyAsync(host_out, out, (size_t)(2 * LK + 2 * K + 2 * n_levels) * sizeof(double),
+                                   cudaMemcpyDeviceToHost, st));
+        MB_CUDA_OK(cudaStreamSynchronize(st));
+    }
     return 0;
 }
 

@@ -173,6 +173,58 @@ def _row_slices(chunks, plan):
                 yield level_id, rows[start:start + step]
 
 
+def _basis_key(basis):
+    return (basis.kind, basis.size, basis.is_log, basis.is_clip, basis.shift, basis.scale, basis.ref_lo, basis.ref_hi)
+
+
+def _resident_fast_path(quantity, plan, storage, level_ids, n_levels, device):
+    """Small-call latency: ``moments`` of a quantity that is a VIEW of storage rows (column selections of the root
+    quantity), every level resident in HBM, single process.  The whole estimate -- zeroing, one fused launch per level,
+    finalize, D2H, synchronise -- is then ONE native call on a cached ``_native.EstimatePlan``
+    (``mlmcb200_estimate_moments_levels``); without it the ~10 host calls of the generic route cost several times the
+    kernels of a small estimate (cfg1: 1e5 samples).  Returns the packed host result or None (generic route)."""
+    if plan.kind != "moments" or _dist.world_size() > 1:
+        return None
+    basis = plan.fn.basis_struct()
+    m = plan.inner.size()
+    if m > 128 or (m > 1 and basis.size > 112) or basis.size > 226:
+        return None
+    rows_of = {}
+    for level_id in level_ids:
+        if storage.level_n_rows(level_id) == 0:
+            continue
+        rows = storage.device_rows(level_id, device, True)
+        if rows is None:
+            return None                                   # does not fit / must be streamed
+        rows_of[level_id] = rows
+    if not rows_of:
+        return None
+    cache = plan.inner.__dict__.setdefault("_estimate_plans", {})
+    key = _basis_key(basis)
+    hit = cache.get(key)
+    if hit is None and key in cache:
+        return None                                       # known not to be a view of the storage rows
+    if hit is not None:
+        ep, row_keys = hit
+        if row_keys == {l: (r.data_ptr(), r.shape[0]) for l, r in rows_of.items()}:
+            return ep, ep.run()
+    views = {}
+    for level_id, rows in rows_of.items():
+        x = plan.inner.device_samples(q_mod.DeviceChunk(level_id, rows, 0))
+        if x.dtype != torch.float64 or x.untyped_storage().data_ptr() != rows.untyped_storage().data_ptr():
+            cache[key] = None                             # a computed quantity: its chunks are new tensors every time
+            return None
+        views[level_id] = x
+    try:
+        ep = _native.EstimatePlan(basis, views, n_levels)
+    except _native.NativeError:
+        return None
+    if len(cache) >= 8:
+        cache.clear()
+    cache[key] = (ep, {l: (r.data_ptr(), r.shape[0]) for l, r in rows_of.items()})
+    return ep, ep.run()
+
+
 def estimate_mean(quantity, variance=True):
     """MLMC mean estimator (quantity_estimate.py:22-80) -> ``QuantityMean``.
 
@@ -189,6 +241,12 @@ def estimate_mean(quantity, variance=True):
     multi = _dist.world_size() > 1
     sharded = multi and not getattr(storage, "rows_are_local_shard", False)
     ranges = _level_row_ranges(storage, level_ids) if sharded else None
+
+    fast = _resident_fast_path(quantity, plan, storage, level_ids, n_levels, device) \
+        if getattr(storage, "resident_fraction", 0) > 0 else None
+    if fast is not None:
+        ep, packed = fast
+        return _quantity_mean_from_packed(quantity, plan, packed, ep.L, ep.K)
 
     acc = None          # LevelAccumulator of the main statistics
     gram = None         # transformed moments: Gram of the base differences
@@ -281,7 +339,12 @@ def estimate_mean(quantity, variance=True):
             packed = _to_host(torch.cat([out["packed"].reshape(-1), acc.acc[:, :2].reshape(-1)]))
         else:
             packed = packed[:-1]
-    L, K = acc.n_levels, acc.K
+    return _quantity_mean_from_packed(quantity, plan, packed, acc.n_levels, acc.K)
+
+
+def _quantity_mean_from_packed(quantity, plan, packed, L, K):
+    """``QuantityMean`` from the packed host result [l_means | l_vars | mean | var | (n, n_rm) per level]."""
+    packed = np.array(packed)                            # own copy: the pinned staging buffers are reused
     l_means = packed[:L * K].reshape(L, K)
     l_vars = packed[L * K:2 * L * K].reshape(L, K)
     mean, var = packed[2 * L * K:(2 * L + 1) * K], packed[(2 * L + 1) * K:(2 * L + 2) * K]
