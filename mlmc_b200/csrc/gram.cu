@@ -22,7 +22,7 @@ namespace {
 
 constexpr int kWarps = 16;
 constexpr int kThreadsGram = kWarps * 32;
-constexpr int kMaxSlots = 3;     // tasks per warp (array bound; the plan uses 2 or 3)
+constexpr int kMaxSlots = 4;     // tasks per warp (array bound; the plans use 2 ... 4)
 constexpr int kMaxGroup = 2;     // blocks per task side
 // Leading dimension of the covariance tiles, a compile-time constant (4 mod 8, >= 8 * 13 + 3 for the row skew) so that
 // every fragment address of a tile is "slot base register + immediate": holds up to 13 blocks = 104 moments.
@@ -213,14 +213,15 @@ __device__ __forceinline__ void slot_tile(double (&am)[GS][GS][2], double (&av)[
 // a second tile while 12 warps contracted the first) was slower: an FP64-pipe instruction issued while DMMAs are in
 // flight costs the tensor pipe ~10 cycles (measured: contraction alone 33.5 TFLOP/s, producers alone 1/3 of that time,
 // together 26.6 TFLOP/s), so the phases do not overlap for free and the larger single tile wins (28.6 TFLOP/s).
-template <bool COARSE, int MODE, int GS>
-__global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a) {
+// WARPS / SLOTS: 16 warps x 2 task slots, one CTA per SM (128-sample tiles) -- or 8 warps x 4 slots, TWO CTAs per SM
+// (64-sample tiles): a CTA's produce phase and barrier waits then overlap the other CTA's DMMA stream.
+template <bool COARSE, int MODE, int GS, int WARPS, int SLOTS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2) gram_kernel(const GramArgs a) {
     extern __shared__ double sm[];
     const GramPlan& pl = a.plan;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int LD = kLD;
     const int NS = pl.ns, nb = pl.nb, r_pad = 8 * nb, R = a.basis.size;
-    constexpr int SLOTS = 2;
     const size_t tile_elems = (size_t)2 * NS * LD;             // Phi_f rows then Phi_c rows
     __shared__ unsigned cnt_sm[2];
     if (tid == 0) cnt_sm[0] = cnt_sm[1] = 0;
@@ -325,6 +326,7 @@ __global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a)
         __syncthreads();
     }
 
+    (void)tile_elems;
     // ---- epilogue: one partial [2 + 2 R R] per CTA, upper blocks mirrored ----
     double* const out = a.partial + (int64_t)blockIdx.x * a.partial_stride;
     double* const out_m = out + 2;
@@ -372,7 +374,8 @@ __global__ void __launch_bounds__(kThreadsGram, 1) gram_kernel(const GramArgs a)
 int popcount4(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1); }
 
 // n_warps / n_slots: warps that contract and task slots per warp
-int make_plan(int R, int n_warps, int n_slots, GramPlan* pl, size_t* smem, int fixed_ld = 0) {
+int make_plan(int R, int n_warps, int n_slots, GramPlan* pl, size_t* smem, int fixed_ld = 0, int ns_cap = 128,
+              size_t budget = 216u * 1024u) {
     const int nb = (R + 7) / 8;
     if (fixed_ld && R > kGramMaxMoments) {
         set_error("gram: %d moments do not fit the shared-memory tile (max %d)", R, kGramMaxMoments);
@@ -441,10 +444,9 @@ int make_plan(int R, int n_warps, int n_slots, GramPlan* pl, size_t* smem, int f
     if (fixed_ld) ld = fixed_ld;
     pl->ld = ld;
     // tile of Phi_f + Phi_c rows; NS a multiple of 4
-    const size_t budget = 216u * 1024u;
     int ns = (int)(budget / ((size_t)2 * ld * sizeof(double)));
     ns = fixed_ld ? (ns / 16) * 16 : (ns / 4) * 4;      // covariance tiles: whole 4-k-step unrolled bodies
-    if (ns > 128) ns = 128;
+    if (ns > ns_cap) ns = ns_cap;
     if (ns < 8) {
         set_error("gram: %d moments do not fit the shared-memory tile", R);
         return -1;
@@ -454,19 +456,26 @@ int make_plan(int R, int n_warps, int n_slots, GramPlan* pl, size_t* smem, int f
     return 0;
 }
 
-template <bool COARSE, int MODE, int GS>
+template <bool COARSE, int MODE, int GS, int WARPS, int SLOTS>
 int launch_gram(const GramArgs& a, int grid, size_t smem, cudaStream_t st) {
-    auto kern = gram_kernel<COARSE, MODE, GS>;
+    auto kern = gram_kernel<COARSE, MODE, GS, WARPS, SLOTS>;
     MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreadsGram, smem, st>>>(a);
+    kern<<<grid, WARPS * 32, smem, st>>>(a);
     MB_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
+// two_ctas: the 8-warp / 4-slot / two-CTAs-per-SM variant (sums-only modes: the sums-of-squares accumulators of mode 1
+// do not fit 128 registers per thread)
 template <bool COARSE, int MODE>
-int launch_gram_gs(const GramArgs& a, int grid, size_t smem, cudaStream_t st) {
-    return a.plan.gs == 1 ? launch_gram<COARSE, MODE, 1>(a, grid, smem, st)
-                          : launch_gram<COARSE, MODE, 2>(a, grid, smem, st);
+int launch_gram_gs(const GramArgs& a, int grid, size_t smem, cudaStream_t st, bool two_ctas) {
+    if constexpr (MODE != 1) {
+        if (two_ctas)
+            return a.plan.gs == 1 ? launch_gram<COARSE, MODE, 1, 8, 4>(a, grid, smem, st)
+                                  : launch_gram<COARSE, MODE, 2, 8, 4>(a, grid, smem, st);
+    }
+    return a.plan.gs == 1 ? launch_gram<COARSE, MODE, 1, 16, 2>(a, grid, smem, st)
+                          : launch_gram<COARSE, MODE, 2, 16, 2>(a, grid, smem, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -638,7 +647,7 @@ using namespace mlmcb200;
 
 extern "C" int64_t mlmcb200_gram_workspace_bytes(int32_t size) {
     if (size < 1 || size > MLMCB200_MAX_MOMENTS) return -1;
-    return (int64_t)sm_count() * (2 + 2 * (int64_t)size * size) * (int64_t)sizeof(double);
+    return 2 * (int64_t)sm_count() * (2 + 2 * (int64_t)size * size) * (int64_t)sizeof(double);   // up to two CTAs per SM
 }
 
 extern "C" int mlmcb200_gram_accumulate(const mlmcb200_basis_t* basis, const double* pairs, int64_t n,
@@ -658,11 +667,24 @@ extern "C" int mlmcb200_gram_accumulate(const mlmcb200_basis_t* basis, const dou
     a.stride_n = stride_n;
     a.stride_side = stride_side;
     size_t smem = 0;
-    if (make_plan(basis->size, kWarps, 2, &a.plan, &smem, kLD) != 0) return -1;
+    // sums-only modes, more than 72 moments: two 8-warp CTAs per SM on 64-sample tiles -- one CTA's produce phase and
+    // barrier waits overlap the other's DMMA stream (R = 100: 28.7 -> 29.9 TFLOP/s executed; R = 50 loses 6 %, its
+    // produce phase is short and the smaller tile costs more).  MLMCB200_GRAM_2CTA=0 / 1 forces a variant (experiments).
+    static int two_env = -2;
+    if (two_env == -2) {
+        const char* e = getenv("MLMCB200_GRAM_2CTA");
+        two_env = e ? atoi(e) : -1;
+    }
+    const bool two_ctas = (two_env >= 0 ? two_env != 0 : basis->size > 72) && (mode == 1 || !want_var);
+    if (two_ctas) {
+        if (make_plan(basis->size, 8, 4, &a.plan, &smem, kLD, 64, 111u * 1024u) != 0) return -1;
+    } else {
+        if (make_plan(basis->size, kWarps, 2, &a.plan, &smem, kLD) != 0) return -1;
+    }
     const int64_t R2 = (int64_t)basis->size * basis->size;
     const int64_t stride = 2 + 2 * R2;
     const int64_t tiles = (n + a.plan.ns - 1) / a.plan.ns;
-    int grid = sm_count();
+    int grid = sm_count() * (two_ctas ? 2 : 1);
     if (tiles < grid) grid = (int)tiles;
     MB_REQUIRE(workspace_bytes >= (int64_t)grid * stride * 8, "gram_accumulate: workspace too small");
     a.partial = static_cast<double*>(workspace);
@@ -670,11 +692,13 @@ extern "C" int mlmcb200_gram_accumulate(const mlmcb200_basis_t* basis, const dou
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (mode == 1)
-        rc = launch_gram_gs<true, 2>(a, grid, smem, st);
+        rc = launch_gram_gs<true, 2>(a, grid, smem, st, two_ctas);
     else if (want_var)
-        rc = has_coarse ? launch_gram_gs<true, 1>(a, grid, smem, st) : launch_gram_gs<false, 1>(a, grid, smem, st);
+        rc = has_coarse ? launch_gram_gs<true, 1>(a, grid, smem, st, false)
+                        : launch_gram_gs<false, 1>(a, grid, smem, st, false);
     else
-        rc = has_coarse ? launch_gram_gs<true, 0>(a, grid, smem, st) : launch_gram_gs<false, 0>(a, grid, smem, st);
+        rc = has_coarse ? launch_gram_gs<true, 0>(a, grid, smem, st, two_ctas)
+                        : launch_gram_gs<false, 0>(a, grid, smem, st, two_ctas);
     if (rc != 0) return rc;
     // sums always; sums of squares only when they were produced
     const int64_t len = want_var && mode == 0 ? stride : 2 + R2;

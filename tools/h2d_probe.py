@@ -102,6 +102,30 @@ def main():
             k *= 2
         results[name] = res
         del src
+    # the storage feed itself (mlmc_b200.sample_storage.stream_levels: double-buffered chunks on a copy stream), all ranks
+    # at once, for several chunk sizes
+    from mlmc_b200.sample_storage import stream_levels
+    src = torch.empty((50_000_000, 1, 1), dtype=torch.float64).pin_memory()      # 400 MB, like one cfg2 step
+    src.fill_(1.0)
+    chunked = {}
+    for mb in (8, 32, 128, 400):
+        best = 1e9
+        for rep in range(3):
+            torch.cuda.synchronize()
+            if world > 1:
+                td.barrier()
+            t0 = time.perf_counter()
+            for _lvl, _rows in stream_levels([(0, src)], dev, mb << 20):
+                pass
+            torch.cuda.synchronize()
+            if rep:
+                best = min(best, time.perf_counter() - t0)
+        t = torch.tensor([src.numel() * 8 / best / 1e9], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MIN)
+        chunked["chunk_%d_MB_slowest_gbs" % mb] = float(t.item())
+    results["stream_levels_all_ranks"] = chunked
+    del src
     # host memory copy bandwidth, all ranks at once (threads = allowed CPUs / world)
     threads = max(1, len(os.sched_getaffinity(0)) // world)
     torch.set_num_threads(threads)
