@@ -236,17 +236,21 @@ int launch_h(const MaxentHArgs& a, int grid, cudaStream_t st) {
 // ---- 3. out[0 .. R] = sum of the F / g partials, out[1 + R ..] = sum of the H partials (fixed order) ----
 __global__ void maxent_sum_kernel(const double* __restrict__ partial_fg, int n_fg, const double* __restrict__ partial_h,
                                   int n_h, int R, int want_h, double* __restrict__ out) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // one WARP per output: lanes stride over the partials (independent loads), then a shuffle tree -- a thread per output
+    // walking ~300 partials one after the other took longer than the two kernels before it
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     const int64_t n_fg_out = 1 + R, total = n_fg_out + (want_h ? (int64_t)R * R : 0);
     if (j >= total) return;
     double s = 0.0;
     if (j < n_fg_out) {
-        for (int b = 0; b < n_fg; ++b) s += partial_fg[(int64_t)b * n_fg_out + j];
+        for (int b = lane; b < n_fg; b += 32) s += partial_fg[(int64_t)b * n_fg_out + j];
     } else {
         const int64_t k = j - n_fg_out;
-        for (int b = 0; b < n_h; ++b) s += partial_h[(int64_t)b * R * R + k];
+        for (int b = lane; b < n_h; b += 32) s += partial_h[(int64_t)b * R * R + k];
     }
-    out[j] = s;
+    s = warp_sum(s);
+    if (lane == 0) out[j] = s;
 }
 
 int rho_grid(int64_t n_nodes) {
@@ -321,8 +325,8 @@ int maxent_fast_launch(const double* phi, int64_t ld_g, const double* w, const d
         if (rc != 0) return rc;
     }
     const int64_t total = 1 + R + (want_h ? (int64_t)R * R : 0);
-    maxent_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial_fg, grid_rho, partial_h, grid_h, R, want_h,
-                                                                        out);
+    maxent_sum_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, st>>>(partial_fg, grid_rho, partial_h, grid_h, R,
+                                                                             want_h, out);
     MB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -246,7 +246,7 @@ def estimate_mean(quantity, variance=True):
         if getattr(storage, "resident_fraction", 0) > 0 else None
     if fast is not None:
         ep, packed = fast
-        return _quantity_mean_from_packed(quantity, plan, packed, ep.L, ep.K)
+        return _quantity_mean_from_packed(quantity, plan, np.array(packed), ep.L, ep.K)   # the plan's buffer is reused
 
     acc = None          # LevelAccumulator of the main statistics
     gram = None         # transformed moments: Gram of the base differences
@@ -344,7 +344,6 @@ def estimate_mean(quantity, variance=True):
 
 def _quantity_mean_from_packed(quantity, plan, packed, L, K):
     """``QuantityMean`` from the packed host result [l_means | l_vars | mean | var | (n, n_rm) per level]."""
-    packed = np.array(packed)                            # own copy: the pinned staging buffers are reused
     l_means = packed[:L * K].reshape(L, K)
     l_vars = packed[L * K:2 * L * K].reshape(L, K)
     mean, var = packed[2 * L * K:(2 * L + 1) * K], packed[(2 * L + 1) * K:(2 * L + 2) * K]
