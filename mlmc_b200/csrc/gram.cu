@@ -624,14 +624,16 @@ __global__ void __launch_bounds__(kThreadsGram, 1) maxent_kernel(const MaxentArg
     }
 }
 
-// out[j] = sum_b partial[b][j]
+// out[j] = sum_b partial[b][j]: one warp per output, lanes stride over the partials, shuffle tree (fixed order)
 __global__ void sum_partials_kernel(const double* __restrict__ partial, int n_partials, int64_t stride, int64_t len,
                                     double* __restrict__ out) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (j >= len) return;
     double s = 0.0;
-    for (int b = 0; b < n_partials; ++b) s += partial[(int64_t)b * stride + j];
-    out[j] = s;
+    for (int b = lane; b < n_partials; b += 32) s += partial[(int64_t)b * stride + j];
+    s = warp_sum(s);
+    if (lane == 0) out[j] = s;
 }
 
 int maxent_grid(int64_t n_nodes, int ns) {
@@ -753,7 +755,8 @@ extern "C" int mlmcb200_maxent_fgh(const double* phi, int64_t ld, const double* 
     }
     const int64_t len = a.want_h ? stride : 1 + size;
     const int threads = 256;
-    sum_partials_kernel<<<(unsigned)((len + threads - 1) / threads), threads, 0, st>>>(a.partial, grid, stride, len, out);
+    sum_partials_kernel<<<(unsigned)((len * 32 + threads - 1) / threads), threads, 0, st>>>(a.partial, grid, stride, len,
+                                                                                            out);
     MB_CUDA_OK(cudaGetLastError());
     return 0;
 }
