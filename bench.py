@@ -704,7 +704,8 @@ def bench_cfg3(ctx):
     nb = (R + 7) // 8
     dmma_peak = nat.fp64_peak(1) / 1e12
     useful = 2.0 * R * R                                   # flop per sample: R(R+1)/2 products x 2 sides x FMA
-    executed = nb * (nb + 1) / 2 * 2 * 128.0               # 8x8 blocks on/above the diagonal x 2 sides x 512 / 4 samples
+    # DMMA.8x8x4 (512 flop) per 4 samples: two per off-diagonal block pair (S^T D + D^T S), one per diagonal block
+    executed = (nb * (nb - 1) / 2 * 2 + nb) * 128.0
     ach = n_rank * useful / (ms_kernel * 1e-3) / 1e12
     units = float(n_total) * R
     return {

@@ -118,16 +118,94 @@ __device__ __forceinline__ void write_row(const mlmcb200_basis_t& b, double t, b
     for (int i = R; i < r_pad; ++i) row[i] = 0.0;
 }
 
+// Fine + coarse levels: the tile holds S = phi(f) + phi(c) and D = phi(f) - phi(c) instead of phi(f), phi(c)
+// (d_ij = f_i f_j - c_i c_j = (D_i S_j + S_i D_j) / 2: no cancellation between two Gram matrices, see slot_mma).
+// One thread runs both recurrences of a sample (two independent chains; a lane-pair variant that exchanged every
+// element by shuffle was 4 % slower).  Zero rows for a dropped sample.
+__device__ __forceinline__ void write_rows_sd(const mlmcb200_basis_t& b, double tf, double tc, bool good, double* row_s,
+                                              double* row_d, int r_pad) {
+    const int R = b.size;
+    if (!good) {
+        for (int i = 0; i < r_pad; ++i) row_s[i] = row_d[i] = 0.0;
+        return;
+    }
+#define MB_PUT(I, F, C)            \
+    {                              \
+        row_s[I] = (F) + (C);      \
+        row_d[I] = (F) - (C);      \
+    }
+    if (b.kind == MLMCB200_RAW) {
+        MB_PUT(0, tf, tc)
+    } else if (b.kind == MLMCB200_FOURIER) {
+        MB_PUT(0, 1.0, 1.0)
+        if (R > 1) {
+            double sf1, cf1, sc1, cc1;
+            sincos(tf, &sf1, &cf1);
+            sincos(tc, &sc1, &cc1);
+            double cfk = cf1, sfk = sf1, cck = cc1, sck = sc1;
+            for (int i = 1; i < R; i += 2) {
+                MB_PUT(i, cfk, cck)
+                if (i + 1 < R) MB_PUT(i + 1, sfk, sck)
+                const double nf = fma(cfk, cf1, -(sfk * sf1));
+                sfk = fma(sfk, cf1, cfk * sf1);
+                cfk = nf;
+                const double nc = fma(cck, cc1, -(sck * sc1));
+                sck = fma(sck, cc1, cck * sc1);
+                cck = nc;
+            }
+        }
+    } else {
+        double f0 = 1.0, f1 = tf, c0 = 1.0, c1 = tc;
+        MB_PUT(0, f0, c0)
+        if (R > 1) MB_PUT(1, f1, c1)
+        if (b.kind == MLMCB200_LEGENDRE) {
+            // monic recurrence W_i = t W_{i-1} - e_i W_{i-2} for both values, two steps per iteration
+            int i = 2;
+            for (; i + 1 < R; i += 2) {
+                const double e0 = kLegCoef[i], e1 = kLegCoef[i + 1];
+                const double qf0 = fma(tf, f1, -(e0 * f0)), qc0 = fma(tc, c1, -(e0 * c0));
+                const double qf1 = fma(tf, qf0, -(e1 * f1)), qc1 = fma(tc, qc0, -(e1 * c1));
+                MB_PUT(i, qf0, qc0)
+                MB_PUT(i + 1, qf1, qc1)
+                f0 = qf0;
+                f1 = qf1;
+                c0 = qc0;
+                c1 = qc1;
+            }
+            if (i < R) {
+                const double qf = fma(tf, f1, -(kLegCoef[i] * f0)), qc = fma(tc, c1, -(kLegCoef[i] * c0));
+                MB_PUT(i, qf, qc)
+            }
+        } else {
+            for (int i = 2; i < R; ++i) {
+                f1 *= tf;
+                c1 *= tc;
+                MB_PUT(i, f1, c1)
+            }
+        }
+    }
+#undef MB_PUT
+    for (int i = R; i < r_pad; ++i) row_s[i] = row_d[i] = 0.0;
+}
+
 // All DMMAs of one task for one 4-sample step.  MASK = the 8x8 blocks of the GS x GS group this slot owns
 // (bit u*GS+v).  Products into the same accumulator are issued in separate passes so that consecutive DMMAs are
 // independent; only the fragments the mask needs are loaded.
-template <bool COARSE, int MODE, int GS, int MASK>
-__device__ __forceinline__ void slot_mma(double (&am)[GS][GS][2], double (&av)[GS][GS][2], const double* pf,
-                                         const double* pc, const int (&off_r)[GS], const int (&off_c)[GS]) {
-    double fr[GS], cr[GS], fcol[GS], ccol[GS];
+//
+// COARSE tiles hold S = phi(f) + phi(c) (ps) and D = phi(f) - phi(c) (pd).  With d_ij = (D_i S_j + S_i D_j) / 2:
+//   2 sum d_ij    = (S^T D + D^T S)_ij                               two DMMAs per block, ONE for a diagonal block:
+//                                                                    X = S_I^T D_I, the epilogue / reduction forms X + X^T
+//   4 sum d_ij^2  = (A^T B + B^T A + 2 E^T E)_ij,  A = D.D, B = S.S, E = D.S   three DMMAs per block, two on the diagonal
+//                                                                    (Y = A_I^T B_I + E_I^T E_I, Y + Y^T is the block)
+//   MODE 2:         (D^T D)_ij                                       one DMMA per block, no subtraction here
+// DIAG: the task lies on the block diagonal (gi == gj): its blocks (u, u) are diagonal blocks.
+template <bool COARSE, int MODE, int GS, int MASK, bool DIAG>
+__device__ __forceinline__ void slot_mma(double (&am)[GS][GS][2], double (&av)[GS][GS][2], const double* ps,
+                                         const double* pd, const int (&off_r)[GS], const int (&off_c)[GS]) {
+    double sr[GS], dr[GS], scol[GS], dcol[GS];
 #pragma unroll
     for (int u = 0; u < GS; ++u) {
-        fr[u] = cr[u] = fcol[u] = ccol[u] = 0.0;
+        sr[u] = dr[u] = scol[u] = dcol[u] = 0.0;
         bool row_used = false, col_used = false;
 #pragma unroll
         for (int v = 0; v < GS; ++v) {
@@ -135,41 +213,46 @@ __device__ __forceinline__ void slot_mma(double (&am)[GS][GS][2], double (&av)[G
             col_used = col_used || ((MASK >> (v * GS + u)) & 1);
         }
         if (row_used) {
-            fr[u] = pf[off_r[u]];
-            if (COARSE) cr[u] = pc[off_r[u]];
+            if (!(COARSE && MODE == 2)) sr[u] = ps[off_r[u]];
+            if (COARSE) dr[u] = pd[off_r[u]];
         }
         if (col_used) {
-            fcol[u] = pf[off_c[u]];
-            if (COARSE) ccol[u] = pc[off_c[u]];
+            if (!(COARSE && MODE == 2)) scol[u] = ps[off_c[u]];
+            if (COARSE) dcol[u] = pd[off_c[u]];
         }
     }
-#define MB_FOR_BLOCKS(BODY)                                                     \
+#define MB_FOR_BLOCKS(COND, BODY)                                               \
     _Pragma("unroll") for (int u = 0; u < GS; ++u) {                            \
         _Pragma("unroll") for (int v = 0; v < GS; ++v) {                        \
-            if ((MASK >> (u * GS + v)) & 1) { BODY }                            \
+            if (((MASK >> (u * GS + v)) & 1) && (COND)) { BODY }                \
         }                                                                       \
     }
-    if (MODE == 2) {
-        MB_FOR_BLOCKS(dmma(am[u][v][0], am[u][v][1], fr[u] - cr[u], fcol[v] - ccol[v]);)
+#define MB_OFFDIAG (!(DIAG && u == v))
+    if (!COARSE) {                                   // level 0: Phi^T Phi (ps holds phi(f)), symmetric
+        MB_FOR_BLOCKS(true, dmma(am[u][v][0], am[u][v][1], sr[u], scol[v]);)
+        if (MODE == 1) { MB_FOR_BLOCKS(true, dmma(av[u][v][0], av[u][v][1], sr[u] * sr[u], scol[v] * scol[v]);) }
+    } else if (MODE == 2) {
+        MB_FOR_BLOCKS(true, dmma(am[u][v][0], am[u][v][1], dr[u], dcol[v]);)
     } else {
-        MB_FOR_BLOCKS(dmma(am[u][v][0], am[u][v][1], fr[u], fcol[v]);)
-        if (COARSE) { MB_FOR_BLOCKS(dmma(am[u][v][0], am[u][v][1], -cr[u], ccol[v]);) }
+        MB_FOR_BLOCKS(true, dmma(am[u][v][0], am[u][v][1], sr[u], dcol[v]);)
+        MB_FOR_BLOCKS(MB_OFFDIAG, dmma(am[u][v][0], am[u][v][1], dr[u], scol[v]);)
         if (MODE == 1) {
-            if (COARSE) {
-                double di[GS], dj[GS];
+            double ar[GS], br[GS], er[GS], ac[GS], bc[GS], ec[GS];
 #pragma unroll
-                for (int u = 0; u < GS; ++u) {
-                    di[u] = fr[u] - cr[u];
-                    dj[u] = fcol[u] - ccol[u];
-                }
-                MB_FOR_BLOCKS(dmma(av[u][v][0], av[u][v][1], di[u] * di[u], fcol[v] * fcol[v]);)
-                MB_FOR_BLOCKS(dmma(av[u][v][0], av[u][v][1], cr[u] * cr[u], dj[v] * dj[v]);)
-                MB_FOR_BLOCKS(dmma(av[u][v][0], av[u][v][1], 2.0 * (di[u] * cr[u]), fcol[v] * dj[v]);)
-            } else {
-                MB_FOR_BLOCKS(dmma(av[u][v][0], av[u][v][1], fr[u] * fr[u], fcol[v] * fcol[v]);)
+            for (int u = 0; u < GS; ++u) {
+                ar[u] = dr[u] * dr[u];
+                br[u] = sr[u] * sr[u];
+                er[u] = dr[u] * sr[u];
+                ac[u] = dcol[u] * dcol[u];
+                bc[u] = scol[u] * scol[u];
+                ec[u] = dcol[u] * scol[u];
             }
+            MB_FOR_BLOCKS(true, dmma(av[u][v][0], av[u][v][1], ar[u], bc[v]);)
+            MB_FOR_BLOCKS(MB_OFFDIAG, dmma(av[u][v][0], av[u][v][1], br[u], ac[v]);)
+            MB_FOR_BLOCKS(true, dmma(av[u][v][0], av[u][v][1], MB_OFFDIAG ? er[u] + er[u] : er[u], ec[v]);)
         }
     }
+#undef MB_OFFDIAG
 #undef MB_FOR_BLOCKS
 }
 
@@ -177,7 +260,7 @@ __device__ __forceinline__ void slot_mma(double (&am)[GS][GS][2], double (&av)[G
 // the 4-k-step unrolled body every shared-memory address is pointer + immediate (constant kLD, the row skew has
 // period 4 k-steps), so the loop carries no address arithmetic and the loads of a k-step can be hoisted over the DMMAs
 // of the previous one.  NS is a multiple of 16.
-template <bool COARSE, int MODE, int GS, int MASK>
+template <bool COARSE, int MODE, int GS, int MASK, bool DIAG>
 __device__ __forceinline__ void slot_tile(double (&am)[GS][GS][2], double (&av)[GS][GS][2], const double* phi_f,
                                           const double* phi_c, const int (&off_r)[GS], const int (&off_c)[GS],
                                           int NS) {
@@ -188,22 +271,31 @@ __device__ __forceinline__ void slot_tile(double (&am)[GS][GS][2], double (&av)[
         for (int q = 0; q < 4; ++q) {
             const double* pfq = pf + q * 4 * kLD + q;
             const double* pcq = pc + q * 4 * kLD + q;
-            slot_mma<COARSE, MODE, GS, MASK>(am, av, pfq, pcq, off_r, off_c);       // skew of rows k0 + 4q .. : q
+            slot_mma<COARSE, MODE, GS, MASK, DIAG>(am, av, pfq, pcq, off_r, off_c);  // skew of rows k0 + 4q .. : q
         }
     }
 }
 
-// the block masks the planner can emit (make_plan): whole group, one column, one row, upper triangle, single blocks
-#define MB_SLOT_SWITCH(MASKVAR, CALL)                                           \
-    switch (MASKVAR) {                                                          \
-        case 0xF: CALL(0xF); break;                                             \
-        case 0x5: CALL(0x5); break;                                             \
-        case 0xA: CALL(0xA); break;                                             \
-        case 0xB: CALL(0xB); break;                                             \
-        case 0x3: CALL(0x3); break;                                             \
-        case 0x1: CALL(0x1); break;                                             \
-        case 0x8: CALL(0x8); break;                                             \
-        default: break;                                                         \
+// the block masks the planner can emit (make_plan).  Off the block diagonal: whole group, one column, one row (edge
+// groups), single block; on it: upper triangle, its first row, its last block, single block.
+#define MB_SLOT_SWITCH(MASKVAR, DIAGVAR, CALL)                                  \
+    if (DIAGVAR) {                                                              \
+        switch (MASKVAR) {                                                      \
+            case 0xB: CALL(0xB, true); break;                                   \
+            case 0x3: CALL(0x3, true); break;                                   \
+            case 0x8: CALL(0x8, true); break;                                   \
+            case 0x1: CALL(0x1, true); break;                                   \
+            default: break;                                                     \
+        }                                                                       \
+    } else {                                                                    \
+        switch (MASKVAR) {                                                      \
+            case 0xF: CALL(0xF, false); break;                                  \
+            case 0x5: CALL(0x5, false); break;                                  \
+            case 0xA: CALL(0xA, false); break;                                  \
+            case 0x3: CALL(0x3, false); break;                                  \
+            case 0x1: CALL(0x1, false); break;                                  \
+            default: break;                                                     \
+        }                                                                       \
     }
 
 // MODE 0: covariance sums only; 1: covariance sums + sums of squares; 2: Gram of the differences
@@ -239,7 +331,6 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2) gram_kernel(c
                 if (MODE == 1) acc_v[s][u][v][0] = acc_v[s][u][v][1] = 0.0;
             }
 
-    const int n_sides = COARSE ? 2 : 1;
     const int64_t n_tiles = (a.n + NS - 1) / NS;
     const int frag_off = (lane & 3) * LD + (lane >> 2);
     unsigned cnt_ok = 0, cnt_rm = 0;
@@ -247,9 +338,11 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2) gram_kernel(c
     // decode this warp's task list ONCE: shared-memory column offsets of its row / column fragments and the mask of
     // 8x8 blocks each slot owns (0 = empty slot)
     int off_r[SLOTS][GS], off_c[SLOTS][GS], mask[SLOTS];
+    bool diag[SLOTS];
 #pragma unroll
     for (int slot = 0; slot < SLOTS; ++slot) {
         const bool used = slot < my_tasks;
+        diag[slot] = used && pl.gi[warp][slot] == pl.gj[warp][slot];
         const int bi0 = used ? pl.gi[warp][slot] * GS : 0, bj0 = used ? pl.gj[warp][slot] * GS : 0;
 #pragma unroll
         for (int u = 0; u < GS; ++u) {
@@ -259,15 +352,14 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2) gram_kernel(c
         mask[slot] = used ? pl.mk[warp][slot] : 0;
     }
 
-    // Basis rows of one tile: item = (sample s, side), at most one item per producing thread; every item tests both sides
-    // of its sample for validity.  The raw values of an item are FETCHED one tile ahead (registers), so the DRAM latency
-    // hides behind the contraction of the current tile.
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    // Basis rows of one tile: item = sample (fine + coarse levels: both recurrences, rows S and D), at most one item per
+    // producing thread.  The raw values of an item are FETCHED one tile ahead (registers), so the DRAM latency hides
+    // behind the contraction of the current tile.
     auto fetch = [&](int64_t tile, int item, double& xf, double& xc) {
         xf = xc = qnan;
-        if (item < NS * n_sides && tile < n_tiles) {
-            const int s = item >= NS ? item - NS : item;
-            const int64_t n = tile * NS + s;
+        if (item < NS && tile < n_tiles) {
+            const int64_t n = tile * NS + item;
             if (n < a.n) {
                 xf = __ldcs(a.pairs + n * a.stride_n);
                 if (COARSE) xc = __ldcs(a.pairs + n * a.stride_n + a.stride_side);
@@ -275,29 +367,28 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2) gram_kernel(c
         }
     };
     auto generate = [&](int64_t tile, double* tile_base, int item, double xf, double xc) {
-        if (item >= NS * n_sides) return;
-        const int side = item >= NS ? 1 : 0, s = item - side * NS;
+        if (item >= NS) return;
+        const int s = item;
         const int64_t n = tile * NS + s;
         // rows are skewed by (s / 4) % 4 doubles: the 16 lanes of a half-warp then store to 16 distinct 8-byte
         // bank pairs (row stride LD = 4 mod 8 alone gives only 4), and a k-step's 4 rows share one skew
-        double* row = tile_base + ((size_t)side * NS + s) * LD + ((s >> 2) & 3);
+        double* row = tile_base + (size_t)s * LD + ((s >> 2) & 3);
         bool good = n < a.n;
-        double t = 0.0;
+        double tf = 0.0, tc = 0.0;
         if (good) {
-            const double tf = a.basis.kind == MLMCB200_RAW ? xf : map_to_ref(a.basis, xf);
+            tf = a.basis.kind == MLMCB200_RAW ? xf : map_to_ref(a.basis, xf);
             good = moments_finite(a.basis, tf);
-            t = tf;
             if (COARSE) {
-                const double tc = a.basis.kind == MLMCB200_RAW ? xc : map_to_ref(a.basis, xc);
+                tc = a.basis.kind == MLMCB200_RAW ? xc : map_to_ref(a.basis, xc);
                 good = good && moments_finite(a.basis, tc);
-                if (side == 1) t = tc;
             }
-            if (side == 0) {
-                cnt_ok += good ? 1u : 0u;
-                cnt_rm += good ? 0u : 1u;
-            }
+            cnt_ok += good ? 1u : 0u;
+            cnt_rm += good ? 0u : 1u;
         }
-        write_row(a.basis, t, good, row, r_pad);
+        if (COARSE)
+            write_rows_sd(a.basis, tf, tc, good, row, row + (size_t)NS * LD, r_pad);
+        else
+            write_row(a.basis, tf, good, row, r_pad);
     };
     auto consume = [&](const double* tile_base) {
         const double* phi_f = tile_base + frag_off;
@@ -305,12 +396,15 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2) gram_kernel(c
 #pragma unroll
         for (int slot = 0; slot < SLOTS; ++slot) {
             if (GS == 1) {
-                if (mask[slot])
-                    slot_tile<COARSE, MODE, GS, 0x1>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], phi_f, phi_c, off_r[slot],
-                                                     off_c[slot], NS);
+                if (mask[slot] && diag[slot])
+                    slot_tile<COARSE, MODE, GS, 0x1, true>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], phi_f, phi_c,
+                                                           off_r[slot], off_c[slot], NS);
+                else if (mask[slot])
+                    slot_tile<COARSE, MODE, GS, 0x1, false>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], phi_f, phi_c,
+                                                            off_r[slot], off_c[slot], NS);
             } else {
-#define MB_CALL(M) slot_tile<COARSE, MODE, GS, M>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], phi_f, phi_c, off_r[slot], off_c[slot], NS)
-                MB_SLOT_SWITCH(mask[slot], MB_CALL)               // warp-uniform, once per slot and tile
+#define MB_CALL(M, D) slot_tile<COARSE, MODE, GS, M, D>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], phi_f, phi_c, off_r[slot], off_c[slot], NS)
+                MB_SLOT_SWITCH(mask[slot], diag[slot], MB_CALL)   // warp-uniform, once per slot and tile
 #undef MB_CALL
             }
         }
@@ -344,10 +438,24 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2) gram_kernel(c
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int i = 8 * I + (lane >> 2), j = 8 * J + 2 * (lane & 3) + e;
-                            // diagonal blocks: keep the upper triangle and mirror it, so the result is exactly symmetric
-                            if (i < R && j < R && (I != J || j >= i)) {
-                                // Legendre tiles hold the monic W_i: P_i P_j = (g_i g_j) W_i W_j
-                                const double gg = a.basis.kind == MLMCB200_LEGENDRE ? kLegAlpha[i] * kLegAlpha[j] : 1.0;
+                            if (i >= R || j >= R) continue;
+                            // Legendre tiles hold the monic W_i: P_i P_j = (g_i g_j) W_i W_j
+                            const double gg = a.basis.kind == MLMCB200_LEGENDRE ? kLegAlpha[i] * kLegAlpha[j] : 1.0;
+                            if (COARSE && MODE != 2) {
+                                // accumulators hold 2 sum d_ij (4 sum d_ij^2); a DIAGONAL block holds the one-sided
+                                // X = S_I^T D_I (Y = A_I^T B_I + E_I^T E_I) and is written un-mirrored: the reduction
+                                // (reduce_partials_sym_kernel) forms (T + T^T) / 2 of the whole matrix
+                                const double hm = I == J ? 1.0 : 0.5, hv = I == J ? 0.5 : 0.25;
+                                const double vm = acc_m[slot][u][v][e] * gg * hm;
+                                out_m[(int64_t)i * R + j] = vm;
+                                if (I != J) out_m[(int64_t)j * R + i] = vm;
+                                if (MODE == 1) {
+                                    const double vv = acc_v[slot][u][v][e] * (gg * gg) * hv;
+                                    out_v[(int64_t)i * R + j] = vv;
+                                    if (I != J) out_v[(int64_t)j * R + i] = vv;
+                                }
+                            } else if (I != J || j >= i) {
+                                // symmetric products: diagonal blocks keep the upper triangle and mirror it
                                 const double vm = acc_m[slot][u][v][e] * gg;
                                 out_m[(int64_t)i * R + j] = vm;
                                 if (i != j) out_m[(int64_t)j * R + i] = vm;
@@ -369,6 +477,32 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2) gram_kernel(c
         out[0] = (double)cnt_sm[0];
         out[1] = (double)cnt_sm[1];
     }
+}
+
+// acc[0..1] += counts; acc[2 + k] += (P[k] + P[k^T]) / 2 with P = sum of the partials (fixed order) and k^T the
+// transposed index inside each R x R matrix (sums, then sums of squares).  Entries that the kernel wrote mirrored are
+// bit-identical on both sides ((a + a) / 2 = a); the one-sided diagonal blocks of the fine + coarse modes become X + X^T.
+// One warp per output: lanes stride over the partials, shuffle tree.
+__global__ void reduce_partials_sym_kernel(const double* __restrict__ partial, int n_partials, int64_t stride, int R,
+                                           int n_mats, double* __restrict__ acc) {
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t R2 = (int64_t)R * R, len = 2 + n_mats * R2;
+    if (j >= len) return;
+    int64_t jt = j;
+    if (j >= 2) {
+        const int64_t k = j - 2, mat = k / R2, e = k - mat * R2;
+        const int64_t row = e / R, col = e - row * R;
+        jt = 2 + mat * R2 + col * R + row;
+    }
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = lane; b < n_partials; b += 32) {
+        s1 += partial[(int64_t)b * stride + j];
+        s2 += partial[(int64_t)b * stride + jt];
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) acc[j] += j < 2 ? s1 : 0.5 * (s1 + s2);
 }
 
 int popcount4(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1); }
@@ -669,15 +803,16 @@ extern "C" int mlmcb200_gram_accumulate(const mlmcb200_basis_t* basis, const dou
     a.stride_n = stride_n;
     a.stride_side = stride_side;
     size_t smem = 0;
-    // sums-only modes, more than 72 moments: two 8-warp CTAs per SM on 64-sample tiles -- one CTA's produce phase and
-    // barrier waits overlap the other's DMMA stream (R = 100: 28.7 -> 29.9 TFLOP/s executed; R = 50 loses 6 %, its
-    // produce phase is short and the smaller tile costs more).  MLMCB200_GRAM_2CTA=0 / 1 forces a variant (experiments).
+    // MLMCB200_GRAM_2CTA=1: the sums-only modes as two 8-warp CTAs per SM on 64-sample tiles (one CTA's produce phase and
+    // barrier waits overlap the other's DMMA stream).  It paid at R = 100 (+4 %) while every lane computed one
+    // recurrence; with the S / D tiles (one thread, both recurrences of a sample) the 16-warp CTA on 128-sample tiles
+    // is faster at every size (R = 100: 6.14 vs 6.29 ms per 8e6 samples), so it is off by default.
     static int two_env = -2;
     if (two_env == -2) {
         const char* e = getenv("MLMCB200_GRAM_2CTA");
-        two_env = e ? atoi(e) : -1;
+        two_env = e ? atoi(e) : 0;
     }
-    const bool two_ctas = (two_env >= 0 ? two_env != 0 : basis->size > 72) && (mode == 1 || !want_var);
+    const bool two_ctas = two_env > 0 && (mode == 1 || !want_var);
     if (two_ctas) {
         if (make_plan(basis->size, 8, 4, &a.plan, &smem, kLD, 64, 111u * 1024u) != 0) return -1;
     } else {
@@ -703,8 +838,12 @@ extern "C" int mlmcb200_gram_accumulate(const mlmcb200_basis_t* basis, const dou
                         : launch_gram_gs<false, 0>(a, grid, smem, st, two_ctas);
     if (rc != 0) return rc;
     // sums always; sums of squares only when they were produced
-    const int64_t len = want_var && mode == 0 ? stride : 2 + R2;
-    return launch_reduce_partials(a.partial, grid, stride, len, acc, st);
+    const int n_mats = want_var && mode == 0 ? 2 : 1;
+    const int64_t len = 2 + n_mats * R2;
+    reduce_partials_sym_kernel<<<(unsigned)((len * 32 + 255) / 256), 256, 0, st>>>(a.partial, grid, stride, basis->size,
+                                                                                    n_mats, acc);
+    MB_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int64_t mlmcb200_maxent_workspace_bytes(int64_t n_nodes, int32_t size) {

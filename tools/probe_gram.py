@@ -37,14 +37,16 @@ for R in (25, 50, 100):
     basis = nat.make_basis(nat.LEGENDRE, R, (-3.72, 3.72), (-1.0, 1.0))
     acc = nat.LevelAccumulator(1, R * R, dev)
     nb = (R + 7) // 8
-    blocks = nb * (nb + 1) // 2
-    for name, kw, per_block, useful in (("sums", dict(mode=0, want_var=False), 2, 2.0 * R * R),
-                                        ("sums+squares", dict(mode=0, want_var=True), 5, 5.0 * R * R),
-                                        ("diff gram", dict(mode=1, want_var=False), 1, 1.0 * R * R),
-                                        ("level-0 sums", dict(mode=0, want_var=False), 1, 1.0 * R * R)):
+    off, dia = nb * (nb - 1) // 2, nb
+    # DMMAs per 4 samples (fine + coarse tiles hold S, D: two per off-diagonal block and one per diagonal block for the
+    # sums, three / two for the sums of squares)
+    for name, kw, dmmas, useful in (("sums", dict(mode=0, want_var=False), 2 * off + dia, 2.0 * R * R),
+                                    ("sums+squares", dict(mode=0, want_var=True), 5 * off + 3 * dia, 5.0 * R * R),
+                                    ("diff gram", dict(mode=1, want_var=False), off + dia, 1.0 * R * R),
+                                    ("level-0 sums", dict(mode=0, want_var=False), off + dia, 1.0 * R * R)):
         xx = x[:, :, :1] if name.startswith("level-0") else x
         ms = timed(lambda: nat.gram_accumulate(basis, xx, acc.level(0), **kw))
-        ex = n * blocks * per_block * 128.0 / (ms * 1e-3) / 1e12
+        ex = n * dmmas * 128.0 / (ms * 1e-3) / 1e12
         us = n * useful / (ms * 1e-3) / 1e12
         print("R=%3d %-13s %8.3f ms  executed %5.2f TFLOP/s (%.2f)  useful %5.2f TFLOP/s (%.2f)" % (
             R, name, ms, ex, ex / peak, us, us / peak), flush=True)
