@@ -147,6 +147,21 @@ int mlmcb200_gram_accumulate(const mlmcb200_basis_t* basis, const double* pairs,
                              void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * The same for a quantity of n_comp components (the reference's covariance quantity handles any shape,
+ * mlmc/quantity/quantity_estimate.py:131-147: outer products per component, cov_at_bottom order): component m of
+ * sample n at pairs[n * stride_n + s * stride_side + m * stride_m]; K = n_comp * R * R and
+ *     acc[2 + m*R*R + i*R + j] = sum_n d_ij (component m),   acc[2 + K + m*R*R + i*R + j] = sum_n d_ij^2.
+ * `valid` (mlmcb200_sample_mask, shared by all components: mask_nan_samples drops a sample when ANY component leaves
+ * the domain) is required for n_comp > 1, NULL for n_comp == 1.  One launch covers all components (grid.y), the SMs
+ * are shared out between them.
+ */
+int64_t mlmcb200_gram_workspace_bytes_comp(int32_t size, int32_t n_comp);
+int mlmcb200_gram_accumulate_comp(const mlmcb200_basis_t* basis, const double* pairs, int64_t n, int32_t n_comp,
+                                  int64_t stride_n, int64_t stride_side, int64_t stride_m, int32_t has_coarse,
+                                  const uint8_t* valid, int32_t mode, int32_t want_var, double* acc,
+                                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * l_means / l_vars of estimate_mean (mlmc/quantity/quantity_estimate.py:70-77) and QuantityMean.mean / .var
  * (mlmc/quantity/quantity.py:588-593) for n_levels accumulators of K sums each, laid out back to back
  * with a stride of acc_stride doubles:  mean_l = s/n,  var_l = (sq - s^2/n)/(n-1)  (n <= 1 -> +inf).

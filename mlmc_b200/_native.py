@@ -55,6 +55,10 @@ _SIGNATURES = {
     "mlmcb200_gram_workspace_bytes": (_c_i64, [_c_i32]),
     "mlmcb200_gram_accumulate": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_i64, _c_i64,
                                                 _c_i32, _c_i32, _c_i32, _c_vp, _c_vp, _c_i64, _c_vp]),
+    "mlmcb200_gram_workspace_bytes_comp": (_c_i64, [_c_i32, _c_i32]),
+    "mlmcb200_gram_accumulate_comp": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_i32, _c_i64, _c_i64,
+                                                     _c_i64, _c_i32, _c_vp, _c_i32, _c_i32, _c_vp, _c_vp, _c_i64,
+                                                     _c_vp]),
     "mlmcb200_finalize_levels": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp,
                                                 _c_vp]),
     "mlmcb200_finalize_levels_batched": (ctypes.c_int, [_c_vp, _c_i64, _c_i32, _c_i64, _c_i32, _c_i64, _c_vp,
@@ -471,26 +475,29 @@ def percentile_stats(values, fracs):
     return host[:-1].reshape(len(fracs), 2), int(host[-1])
 
 
-def gram_accumulate(basis, x, acc_row, mode=0, want_var=True):
-    """Add the chunk x [1, n, S] to the covariance accumulator ``acc_row`` ([2 + 2*R*R])."""
+def gram_accumulate(basis, x, acc_row, mode=0, want_var=True, valid=None):
+    """Add the chunk x [M, n, S] to the covariance accumulator ``acc_row`` ([2 + 2*M*R*R], flat index
+    ``m*R*R + i*R + j``).  Vector quantities (M > 1) share one sample mask (``sample_mask``, computed here unless
+    passed): a sample is dropped when any component leaves the domain."""
     global launch_count
     M, n, has_coarse, sn, ss, sm = _chunk_layout(x)
-    if M != 1:
-        raise NativeError("gram_accumulate handles scalar quantities (M == 1), got M = %d" % M)
     _require_cuda(acc_row, "acc")
     R = basis.size
-    if acc_row.numel() != 2 + 2 * R * R or not acc_row.is_contiguous():
-        raise NativeError("accumulator must be contiguous with %d entries" % (2 + 2 * R * R))
+    if acc_row.numel() != 2 + 2 * M * R * R or not acc_row.is_contiguous():
+        raise NativeError("accumulator must be contiguous with %d entries" % (2 + 2 * M * R * R))
     if n == 0:
         return
     lib = load()
-    with torch.cuda.device(x.device):
-        ws_bytes = lib.mlmcb200_gram_workspace_bytes(R)
+    if M > 1 and valid is None:
+        valid = sample_mask(basis, x)
+    with _on_device(x.device):
+        ws_bytes = lib.mlmcb200_gram_workspace_bytes_comp(R, M)
         if ws_bytes < 0:
             raise NativeError("gram workspace: %s" % lib.mlmcb200_last_error().decode())
         ws = _workspace(x.device, ws_bytes)
-        _check(lib.mlmcb200_gram_accumulate(ctypes.byref(basis), _ptr(x), n, sn, ss, has_coarse, mode,
-                                            int(bool(want_var)), _ptr(acc_row), _ptr(ws), ws.numel(), _stream()),
+        _check(lib.mlmcb200_gram_accumulate_comp(ctypes.byref(basis), _ptr(x), n, M, sn, ss, sm, has_coarse,
+                                                 _ptr(valid if M > 1 else None), mode, int(bool(want_var)),
+                                                 _ptr(acc_row), _ptr(ws), ws.numel(), _stream()),
                "gram_accumulate")
     launch_count += 2
 

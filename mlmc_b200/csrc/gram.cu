@@ -42,9 +42,10 @@ struct GramPlan {
 
 struct GramArgs {
     mlmcb200_basis_t basis;
-    const double* pairs;
-    int64_t n, stride_n, stride_side;
-    double* partial;         // [gridDim.x][2 + 2 R R]
+    const double* pairs;     // component blockIdx.y starts at pairs + blockIdx.y * stride_m
+    int64_t n, stride_n, stride_side, stride_m;
+    const uint8_t* valid;    // vector quantities: sample mask shared by the components (mlmcb200_sample_mask), or null
+    double* partial;         // [gridDim.y][gridDim.x][2 + 2 R R]
     int64_t partial_stride;
     GramPlan plan;
 };
@@ -356,13 +357,15 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2) gram_kernel(c
     // Basis rows of one tile: item = sample (fine + coarse levels: both recurrences, rows S and D), at most one item per
     // producing thread.  The raw values of an item are FETCHED one tile ahead (registers), so the DRAM latency hides
     // behind the contraction of the current tile.
+    // A sample the mask of a vector quantity drops is fetched as NaN: the domain test below then drops it here too.
+    const double* const pairs = a.pairs + (int64_t)blockIdx.y * a.stride_m;
     auto fetch = [&](int64_t tile, int item, double& xf, double& xc) {
         xf = xc = qnan;
         if (item < NS && tile < n_tiles) {
             const int64_t n = tile * NS + item;
-            if (n < a.n) {
-                xf = __ldcs(a.pairs + n * a.stride_n);
-                if (COARSE) xc = __ldcs(a.pairs + n * a.stride_n + a.stride_side);
+            if (n < a.n && (a.valid == nullptr || a.valid[n])) {
+                xf = __ldcs(pairs + n * a.stride_n);
+                if (COARSE) xc = __ldcs(pairs + n * a.stride_n + a.stride_side);
             }
         }
     };
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2) gram_kernel(c
 
     (void)tile_elems;
     // ---- epilogue: one partial [2 + 2 R R] per CTA, upper blocks mirrored ----
-    double* const out = a.partial + (int64_t)blockIdx.x * a.partial_stride;
+    double* const out = a.partial + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * a.partial_stride;
     double* const out_m = out + 2;
     double* const out_v = out + 2 + (int64_t)R * R;
 #pragma unroll
@@ -483,17 +486,25 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2) gram_kernel(c
 // transposed index inside each R x R matrix (sums, then sums of squares).  Entries that the kernel wrote mirrored are
 // bit-identical on both sides ((a + a) / 2 = a); the one-sided diagonal blocks of the fine + coarse modes become X + X^T.
 // One warp per output: lanes stride over the partials, shuffle tree.
+// Vector quantities: blockIdx.y = component of this launch (global number comp0 + blockIdx.y of n_comp); its matrices go
+// to acc[2 + mat * n_comp R^2 + comp R^2 + e] (flat index m R R + i R + j of quantity_estimate.py:131-147), the counts
+// (equal for all components: they share the sample mask) are added once, by component 0.
 __global__ void reduce_partials_sym_kernel(const double* __restrict__ partial, int n_partials, int64_t stride, int R,
-                                           int n_mats, double* __restrict__ acc) {
+                                           int n_mats, double* __restrict__ acc, int comp0, int n_comp) {
     const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int64_t R2 = (int64_t)R * R, len = 2 + n_mats * R2;
     if (j >= len) return;
-    int64_t jt = j;
+    const int comp = comp0 + blockIdx.y;
+    partial += (int64_t)blockIdx.y * n_partials * stride;
+    int64_t jt = j, jo = j;
     if (j >= 2) {
         const int64_t k = j - 2, mat = k / R2, e = k - mat * R2;
         const int64_t row = e / R, col = e - row * R;
         jt = 2 + mat * R2 + col * R + row;
+        jo = 2 + (mat * n_comp + comp) * R2 + e;
+    } else if (comp != 0) {
+        return;
     }
     double s1 = 0.0, s2 = 0.0;
     for (int b = lane; b < n_partials; b += 32) {
@@ -502,7 +513,7 @@ __global__ void reduce_partials_sym_kernel(const double* __restrict__ partial, i
     }
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
-    if (lane == 0) acc[j] += j < 2 ? s1 : 0.5 * (s1 + s2);
+    if (lane == 0) acc[jo] += j < 2 ? s1 : 0.5 * (s1 + s2);
 }
 
 int popcount4(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1); }
@@ -591,10 +602,10 @@ int make_plan(int R, int n_warps, int n_slots, GramPlan* pl, size_t* smem, int f
 }
 
 template <bool COARSE, int MODE, int GS, int WARPS, int SLOTS>
-int launch_gram(const GramArgs& a, int grid, size_t smem, cudaStream_t st) {
+int launch_gram(const GramArgs& a, int grid, int n_comp, size_t smem, cudaStream_t st) {
     auto kern = gram_kernel<COARSE, MODE, GS, WARPS, SLOTS>;
     MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, WARPS * 32, smem, st>>>(a);
+    kern<<<dim3((unsigned)grid, (unsigned)n_comp), WARPS * 32, smem, st>>>(a);
     MB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -602,14 +613,14 @@ int launch_gram(const GramArgs& a, int grid, size_t smem, cudaStream_t st) {
 // two_ctas: the 8-warp / 4-slot / two-CTAs-per-SM variant (sums-only modes: the sums-of-squares accumulators of mode 1
 // do not fit 128 registers per thread)
 template <bool COARSE, int MODE>
-int launch_gram_gs(const GramArgs& a, int grid, size_t smem, cudaStream_t st, bool two_ctas) {
+int launch_gram_gs(const GramArgs& a, int grid, int n_comp, size_t smem, cudaStream_t st, bool two_ctas) {
     if constexpr (MODE != 1) {
         if (two_ctas)
-            return a.plan.gs == 1 ? launch_gram<COARSE, MODE, 1, 8, 4>(a, grid, smem, st)
-                                  : launch_gram<COARSE, MODE, 2, 8, 4>(a, grid, smem, st);
+            return a.plan.gs == 1 ? launch_gram<COARSE, MODE, 1, 8, 4>(a, grid, n_comp, smem, st)
+                                  : launch_gram<COARSE, MODE, 2, 8, 4>(a, grid, n_comp, smem, st);
     }
-    return a.plan.gs == 1 ? launch_gram<COARSE, MODE, 1, 16, 2>(a, grid, smem, st)
-                          : launch_gram<COARSE, MODE, 2, 16, 2>(a, grid, smem, st);
+    return a.plan.gs == 1 ? launch_gram<COARSE, MODE, 1, 16, 2>(a, grid, n_comp, smem, st)
+                          : launch_gram<COARSE, MODE, 2, 16, 2>(a, grid, n_comp, smem, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -782,26 +793,46 @@ int maxent_grid(int64_t n_nodes, int ns) {
 using namespace mlmcb200;
 
 extern "C" int64_t mlmcb200_gram_workspace_bytes(int32_t size) {
-    if (size < 1 || size > MLMCB200_MAX_MOMENTS) return -1;
-    return 2 * (int64_t)sm_count() * (2 + 2 * (int64_t)size * size) * (int64_t)sizeof(double);   // up to two CTAs per SM
+    return mlmcb200_gram_workspace_bytes_comp(size, 1);
+}
+
+// partials of up to 2 CTAs per SM (scalar quantity) + one per component of a launch (at most kGramCompBatch at a time)
+constexpr int kGramCompBatch = 2048;
+
+extern "C" int64_t mlmcb200_gram_workspace_bytes_comp(int32_t size, int32_t n_comp) {
+    if (size < 1 || size > MLMCB200_MAX_MOMENTS || n_comp < 1) return -1;
+    const int64_t n_partials = 2 * (int64_t)sm_count() + (n_comp > 1 ? (n_comp < kGramCompBatch ? n_comp : kGramCompBatch) : 0);
+    return n_partials * (2 + 2 * (int64_t)size * size) * (int64_t)sizeof(double);
 }
 
 extern "C" int mlmcb200_gram_accumulate(const mlmcb200_basis_t* basis, const double* pairs, int64_t n,
                                         int64_t stride_n, int64_t stride_side, int32_t has_coarse,
                                         int32_t mode, int32_t want_var, double* acc,
                                         void* workspace, int64_t workspace_bytes, void* stream) {
+    return mlmcb200_gram_accumulate_comp(basis, pairs, n, 1, stride_n, stride_side, 0, has_coarse, nullptr, mode,
+                                         want_var, acc, workspace, workspace_bytes, stream);
+}
+
+extern "C" int mlmcb200_gram_accumulate_comp(const mlmcb200_basis_t* basis, const double* pairs, int64_t n,
+                                             int32_t n_comp, int64_t stride_n, int64_t stride_side, int64_t stride_m,
+                                             int32_t has_coarse, const uint8_t* valid, int32_t mode, int32_t want_var,
+                                             double* acc, void* workspace, int64_t workspace_bytes, void* stream) {
     if (check_basis(basis) != 0) return -1;
     MB_REQUIRE(n >= 0 && (mode == 0 || mode == 1), "gram_accumulate: bad n=%lld mode=%d", (long long)n, mode);
+    MB_REQUIRE(n_comp >= 1, "gram_accumulate: bad n_comp=%d", n_comp);
     MB_REQUIRE(acc != nullptr && workspace != nullptr, "gram_accumulate: null acc/workspace");
     MB_REQUIRE(mode == 0 || has_coarse, "gram_accumulate: mode 1 (difference Gram) needs a coarse side");
+    MB_REQUIRE(n_comp == 1 || valid != nullptr,
+               "gram_accumulate: a vector quantity needs the sample mask of mlmcb200_sample_mask");
     if (n == 0) return 0;
     MB_REQUIRE(pairs != nullptr, "gram_accumulate: null pairs");
     GramArgs a;
     a.basis = *basis;
-    a.pairs = pairs;
     a.n = n;
     a.stride_n = stride_n;
     a.stride_side = stride_side;
+    a.stride_m = stride_m;
+    a.valid = valid;
     size_t smem = 0;
     // MLMCB200_GRAM_2CTA=1: the sums-only modes as two 8-warp CTAs per SM on 64-sample tiles (one CTA's produce phase and
     // barrier waits overlap the other's DMMA stream).  It paid at R = 100 (+4 %) while every lane computed one
@@ -821,28 +852,37 @@ extern "C" int mlmcb200_gram_accumulate(const mlmcb200_basis_t* basis, const dou
     const int64_t R2 = (int64_t)basis->size * basis->size;
     const int64_t stride = 2 + 2 * R2;
     const int64_t tiles = (n + a.plan.ns - 1) / a.plan.ns;
-    int grid = sm_count() * (two_ctas ? 2 : 1);
+    // CTAs per component: the SMs are shared out between the components of a launch
+    const int sms = sm_count() * (two_ctas ? 2 : 1);
+    int grid = n_comp == 1 ? sms : (sms + n_comp - 1) / n_comp;
     if (tiles < grid) grid = (int)tiles;
-    MB_REQUIRE(workspace_bytes >= (int64_t)grid * stride * 8, "gram_accumulate: workspace too small");
+    const int64_t fit = workspace_bytes / ((int64_t)grid * stride * 8);
+    MB_REQUIRE(fit >= 1, "gram_accumulate: workspace too small");
+    int batch = n_comp < kGramCompBatch ? n_comp : kGramCompBatch;
+    if (fit < batch) batch = (int)fit;
     a.partial = static_cast<double*>(workspace);
     a.partial_stride = stride;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc;
-    if (mode == 1)
-        rc = launch_gram_gs<true, 2>(a, grid, smem, st, two_ctas);
-    else if (want_var)
-        rc = has_coarse ? launch_gram_gs<true, 1>(a, grid, smem, st, false)
-                        : launch_gram_gs<false, 1>(a, grid, smem, st, false);
-    else
-        rc = has_coarse ? launch_gram_gs<true, 0>(a, grid, smem, st, two_ctas)
-                        : launch_gram_gs<false, 0>(a, grid, smem, st, two_ctas);
-    if (rc != 0) return rc;
     // sums always; sums of squares only when they were produced
     const int n_mats = want_var && mode == 0 ? 2 : 1;
     const int64_t len = 2 + n_mats * R2;
-    reduce_partials_sym_kernel<<<(unsigned)((len * 32 + 255) / 256), 256, 0, st>>>(a.partial, grid, stride, basis->size,
-                                                                                    n_mats, acc);
-    MB_CUDA_OK(cudaGetLastError());
+    for (int comp0 = 0; comp0 < n_comp; comp0 += batch) {
+        const int nc = n_comp - comp0 < batch ? n_comp - comp0 : batch;
+        a.pairs = pairs + (int64_t)comp0 * stride_m;
+        int rc;
+        if (mode == 1)
+            rc = launch_gram_gs<true, 2>(a, grid, nc, smem, st, two_ctas);
+        else if (want_var)
+            rc = has_coarse ? launch_gram_gs<true, 1>(a, grid, nc, smem, st, false)
+                            : launch_gram_gs<false, 1>(a, grid, nc, smem, st, false);
+        else
+            rc = has_coarse ? launch_gram_gs<true, 0>(a, grid, nc, smem, st, two_ctas)
+                            : launch_gram_gs<false, 0>(a, grid, nc, smem, st, two_ctas);
+        if (rc != 0) return rc;
+        reduce_partials_sym_kernel<<<dim3((unsigned)((len * 32 + 255) / 256), (unsigned)nc), 256, 0, st>>>(
+            a.partial, grid, stride, basis->size, n_mats, acc, comp0, n_comp);
+        MB_CUDA_OK(cudaGetLastError());
+    }
     return 0;
 }
 

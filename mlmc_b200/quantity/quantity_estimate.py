@@ -9,8 +9,9 @@ quantity                               kernels
 =====================================  ======================================================================
 ``moments(q, basis)``                  ``mlmcb200_moments_accumulate`` (+ ``sample_mask`` when M > 128)
 ``moments(q, TransformedMoments)``     moments sums of the base functions + DMMA Gram of the differences,
-                                       then mean' = L s, sum d'^2 = diag(L G L^T)   (scalar q)
-``covariance(q, basis)`` (scalar q)    ``mlmcb200_gram_accumulate`` (DMMA), sums and sums of squares
+                                       then mean' = L s, sum d'^2 = diag(L G L^T)   (per component of q)
+``covariance(q, basis)``               ``mlmcb200_gram_accumulate_comp`` (DMMA), sums and sums of squares; vector
+                                       quantities: all components in one launch, one shared sample mask
 ``covariance(q, basis)``, means only   ``estimate_mean(..., variance=False)``: products of basis functions are linear
                                        combinations of a longer basis of the same family, so the level sums are
                                        ``C . (moment sums of 2R-1 functions)``: ``mlmcb200_moments_accumulate`` +
@@ -118,16 +119,22 @@ class _Plan:
             base_ok = fn.base_moments().size <= (226 if scalar else 113)
             if quantity._fused_kind == "moments" and base_ok and not transformed:
                 self.kind = "moments"
-            elif quantity._fused_kind == "moments" and base_ok and transformed and scalar \
-                    and fn.base_moments().size <= 104:
+            elif quantity._fused_kind == "moments" and base_ok and transformed and fn.base_moments().size <= 104 \
+                    and self._fits(inner.size() * fn.base_moments().size ** 2):
                 self.kind = "transformed"
             elif quantity._fused_kind == "covariance" and not variance and self._linearise(fn, scalar):
                 self.kind = "cov_linear"
-            elif quantity._fused_kind == "covariance" and scalar and not transformed and fn.size <= 104:
+            elif quantity._fused_kind == "covariance" and not transformed and fn.size <= 104 \
+                    and self._fits(inner.size() * fn.size ** 2):
                 self.kind = "covariance"
             if self.kind != "raw":
                 self.inner, self.fn, self.at_bottom = inner, fn, quantity._at_bottom
 
+
+    @staticmethod
+    def _fits(n_sums, limit=1 << 27):
+        """The fused covariance route keeps ``[L, 2 + 2 K]`` sums (K = M R^2) on the device: up to 1 GiB per level."""
+        return n_sums <= limit
 
     def _linearise(self, fn, scalar):
         """Covariance MEANS from the moment sums of the extended basis (``Moments.product_table``) if that basis fits
@@ -267,13 +274,12 @@ def estimate_mean(quantity, variance=True):
             base_basis = plan.fn.basis_struct()
             r0 = base_basis.size
             if acc is None:
-                acc = _native.LevelAccumulator(n_levels, r0, device)
-                gram = _native.LevelAccumulator(n_levels, r0 * r0, device)
-            _native.moments_accumulate(base_basis, x, acc.level(level_id))
-            if x.shape[2] == 2:
-                _native.gram_accumulate(base_basis, x, gram.level(level_id), mode=1, want_var=False)
-            else:
-                _native.gram_accumulate(base_basis, x, gram.level(level_id), mode=0, want_var=False)
+                acc = _native.LevelAccumulator(n_levels, x.shape[0] * r0, device)
+                gram = _native.LevelAccumulator(n_levels, x.shape[0] * r0 * r0, device)
+            valid = _native.sample_mask(base_basis, x) if x.shape[0] > 1 else None
+            _native.moments_accumulate(base_basis, x, acc.level(level_id), valid=valid)
+            _native.gram_accumulate(base_basis, x, gram.level(level_id), mode=1 if x.shape[2] == 2 else 0,
+                                    want_var=False, valid=valid)
         elif plan.kind == "cov_linear":
             basis = plan.ext_fn.basis_struct()
             if acc is None:
@@ -282,7 +288,7 @@ def estimate_mean(quantity, variance=True):
         elif plan.kind == "covariance":
             basis = plan.fn.basis_struct()
             if acc is None:
-                acc = _native.LevelAccumulator(n_levels, basis.size * basis.size, device)
+                acc = _native.LevelAccumulator(n_levels, x.shape[0] * basis.size * basis.size, device)
             _native.gram_accumulate(basis, x, acc.level(level_id), mode=0, want_var=True)
         else:
             if x.dtype == torch.bool:
@@ -299,12 +305,12 @@ def estimate_mean(quantity, variance=True):
             width = plan.inner.size() * plan.fn.size
         elif plan.kind == "transformed":
             r0 = plan.fn.base_moments().size
-            width = r0
-            gram = _native.LevelAccumulator(n_levels, r0 * r0, device)
+            width = plan.inner.size() * r0
+            gram = _native.LevelAccumulator(n_levels, width * r0, device)
         elif plan.kind == "cov_linear":
             width = plan.inner.size() * plan.ext_fn.size
         elif plan.kind == "covariance":
-            width = plan.fn.size * plan.fn.size
+            width = plan.inner.size() * plan.fn.size * plan.fn.size
         else:
             width = quantity.size()
         acc = _native.LevelAccumulator(n_levels, width, device)
@@ -358,14 +364,12 @@ def _quantity_mean_from_packed(quantity, plan, packed, L, K):
         l_vars = l_vars.reshape(L, -1, r).transpose(0, 2, 1).reshape(L, K)
         mean = mean.reshape(-1, r).T.reshape(K)
         var = var.reshape(-1, r).T.reshape(K)
-    elif plan.kind == "cov_linear" and not plan.at_bottom:
+    elif plan.kind in ("cov_linear", "covariance") and not plan.at_bottom:
         rr = plan.fn.size ** 2
         l_means = l_means.reshape(L, -1, rr).transpose(0, 2, 1).reshape(L, K)
         l_vars = l_vars.reshape(L, -1, rr).transpose(0, 2, 1).reshape(L, K)
         mean = mean.reshape(-1, rr).T.reshape(K)
         var = var.reshape(-1, rr).T.reshape(K)
-    elif plan.kind == "covariance" and not plan.at_bottom:
-        pass        # scalar input quantity: both layouts coincide
     return q_mod.QuantityMean(quantity.qtype, l_means=l_means, l_vars=l_vars, n_samples=n_samples,
                               n_rm_samples=n_rm_samples, mean=mean, var=var)
 
@@ -545,13 +549,15 @@ def _to_host(tensor):
 
 
 def _transform_sums(acc, gram, fn, device):
-    """Level sums of ``L phi`` from the sums / Gram of the base differences: ``sum d' = L sum d`` and
+    """Level sums of ``L phi`` from the sums / Gram of the base differences, per component: ``sum d' = L sum d`` and
     ``sum d'_k^2 = L_k G L_k^T`` (moments.py:256-259 applied under the sums)."""
     l_mat = fn._matrix_on(device)                         # [R1, R0]
     r1, r0 = l_mat.shape
-    out = _native.LevelAccumulator(acc.n_levels, r1, device)
+    n_comp = acc.K // r0
+    out = _native.LevelAccumulator(acc.n_levels, n_comp * r1, device)
     out.acc[:, :2] = acc.acc[:, :2]
-    out.acc[:, 2:2 + r1] = acc.acc[:, 2:2 + r0] @ l_mat.T
-    g = gram.acc[:, 2:2 + r0 * r0].reshape(-1, r0, r0)
-    out.acc[:, 2 + r1:] = torch.einsum("ki,lij,kj->lk", l_mat, g, l_mat)
+    sums = acc.acc[:, 2:2 + n_comp * r0].reshape(-1, n_comp, r0)
+    out.acc[:, 2:2 + n_comp * r1] = (sums @ l_mat.T).reshape(-1, n_comp * r1)
+    g = gram.acc[:, 2:2 + n_comp * r0 * r0].reshape(-1, n_comp, r0, r0)
+    out.acc[:, 2 + n_comp * r1:] = torch.einsum("ki,lmij,kj->lmk", l_mat, g, l_mat).reshape(-1, n_comp * r1)
     return out

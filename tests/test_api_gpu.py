@@ -550,3 +550,89 @@ def test_allocation_grows_as_target_variance_shrinks(golden):
     assert np.array_equal(n_est, orc.n_samples_for_target_variance(1e-9, want_vars, n_ops, 3))
     cov, _ = est.estimate_covariance()
     assert np.array_equal(cov, cov.T)
+
+
+def _vector_levels(rng, n_comp, sizes, spread=1.0):
+    """Correlated fine / coarse rows [N, 2, M] of a vector quantity, a few values far outside the unit domain."""
+    levels = []
+    for l, n in enumerate(sizes):
+        base = rng.normal(size=(n, 1, n_comp)) * spread
+        rows = np.concatenate([base + 0.3 * rng.normal(size=(n, 1, n_comp)) * 2.0 ** -l,
+                               base if l > 0 else np.zeros_like(base)], axis=1)
+        rows[rng.integers(0, n, size=max(1, n // 97)), rng.integers(0, 2 if l > 0 else 1), rng.integers(0, n_comp)] = 50.0
+        levels.append(rows)
+    return levels
+
+
+@pytest.mark.parametrize("n_comp,size,kind", [(5, 20, "legendre"), (3, 41, "legendre"), (200, 9, "monomial"),
+                                              (7, 13, "fourier")])
+def test_vector_covariance_is_fused(n_comp, size, kind):
+    """``covariance`` of a vector quantity (quantity_estimate.py:131-147 handles any shape): all components go through
+    the DMMA kernel in one launch, with the mask of ``mask_nan_samples`` shared by the components; both layouts."""
+    from mlmc_b200 import moments as mom
+    from mlmc_b200.quantity import quantity_estimate as qe
+    rng = np.random.default_rng(100 + n_comp)
+    levels = _vector_levels(rng, n_comp, [700, 333, 130])
+    storage, vec = scalar_setup(levels, n_comp=n_comp)
+    domain = (-3.0, 3.0)
+    fn = {"legendre": mom.Legendre, "monomial": mom.Monomial, "fourier": mom.Fourier}[kind](size, domain)
+    want = orc.estimate_covariance(levels, orc.Basis(kind, size, domain), chunk_rows=4096)
+    assert int(np.sum(want.n_rm_samples)) > 0
+    for bottom in (True, False):
+        quantity = qe.covariance(vec, fn, cov_at_bottom=bottom)
+        assert qe._Plan(quantity).kind == "covariance"
+        qm = qe.estimate_mean(quantity)
+        assert list(qm.n_samples) == list(want.n_samples) and list(qm.n_rm_samples) == list(want.n_rm_samples)
+
+        def layout(a):          # oracle: [.., M * R * R] in cov_at_bottom order
+            a = np.asarray(a)
+            if bottom:
+                return a
+            lead = a.shape[:-1]
+            return np.moveaxis(a.reshape(lead + (n_comp, size * size)), -1, -2).reshape(lead + (-1,))
+        for l in range(3):
+            rel_close(np.reshape(qm.l_means, (3, -1))[l], layout(want.l_means)[l], rtol=1e-8, atol_scale=1e-13)
+            rel_close(np.reshape(qm.l_vars, (3, -1))[l], layout(want.l_vars)[l], rtol=1e-8, atol_scale=1e-13)
+        rel_close(np.ravel(qm.mean), layout(want.mean), rtol=1e-8, atol_scale=1e-13)
+        rel_close(np.ravel(qm.var), layout(want.var), rtol=1e-8, atol_scale=1e-13)
+
+
+def test_vector_covariance_component_batches():
+    """More components than one launch takes (2048): the component batches land in the right slots."""
+    from mlmc_b200.moments import Legendre
+    from mlmc_b200.quantity import quantity_estimate as qe
+    rng = np.random.default_rng(7)
+    n_comp, size = 2100, 3
+    levels = _vector_levels(rng, n_comp, [40, 24], spread=0.5)
+    storage, vec = scalar_setup(levels, n_comp=n_comp)
+    fn = Legendre(size, (-60.0, 60.0))
+    qm = qe.estimate_mean(qe.covariance(vec, fn))
+    want = orc.estimate_covariance(levels, orc.Basis("legendre", size, (-60.0, 60.0)))
+    assert list(qm.n_samples) == [40, 24]
+    rel_close(np.ravel(qm.mean), want.mean, rtol=1e-8, atol_scale=1e-13)
+    rel_close(np.ravel(qm.var), want.var, rtol=1e-8, atol_scale=1e-13)
+
+
+def test_vector_transformed_moments_are_fused():
+    """``moments(vector quantity, TransformedMoments)``: sums and difference Gram of the base functions per component,
+    transformed under the sums (moments.py:256-259)."""
+    from mlmc_b200.moments import Legendre, TransformedMoments
+    from mlmc_b200.quantity import quantity_estimate as qe
+    rng = np.random.default_rng(11)
+    n_comp, r0, r1 = 4, 12, 7
+    levels = _vector_levels(rng, n_comp, [900, 400, 150])
+    storage, vec = scalar_setup(levels, n_comp=n_comp)
+    domain = (-3.0, 3.0)
+    l_mat = rng.normal(size=(r1, r0)) / np.sqrt(r0)
+    l_mat[0] = 0.0
+    l_mat[0, 0] = 1.0
+    fn = TransformedMoments(Legendre(r0, domain), l_mat)
+    want = orc.estimate_moments(levels, orc.Basis("legendre", r0, domain, matrix=l_mat), chunk_rows=4096)
+    assert int(np.sum(want.n_rm_samples)) > 0
+    quantity = qe.moments(vec, fn)
+    assert qe._Plan(quantity).kind == "transformed"
+    qm = qe.estimate_mean(quantity)
+    assert list(qm.n_samples) == list(want.n_samples) and list(qm.n_rm_samples) == list(want.n_rm_samples)
+    for l in range(3):
+        rel_close(np.reshape(qm.l_means, (3, -1))[l], want.l_means[l], rtol=1e-9, atol_scale=1e-13)
+        rel_close(np.reshape(qm.l_vars, (3, -1))[l], want.l_vars[l], rtol=1e-8, atol_scale=1e-12)
