@@ -268,6 +268,15 @@ int mlmcb200_maxent_fgh(const double* phi, int64_t ld, const double* w, const do
                         int64_t n_nodes, int32_t size, int32_t what, double* out,
                         void* workspace, int64_t workspace_bytes, void* stream);
 
+/*
+ * SimpleDistribution.density (mlmc/tool/simple_distribution.py:96-105) for values x[n] (device):
+ *     out[k] = exp(clip(-sum_{i < n_coef} coef[i] phi_i(x[k]), -200, 200)),   coef = lambda / sigma  (device, n_coef <= size)
+ * phi as mlmcb200_basis_eval (same operations); a value outside a clipped domain gives NaN, as in the reference.
+ * For a TransformedMoments basis (phi' = L phi) pass coef = L[:n]^T (lambda / sigma) and the base functions.
+ */
+int mlmcb200_density_eval(const mlmcb200_basis_t* basis, const double* x, int64_t n, const double* coef,
+                          int32_t n_coef, double* out, void* stream);
+
 /* FP64 pipe micro-benchmarks used by bench.py for the roofline denominators (not on the data path).
  * kind & 15: 0 = DFMA with two loop-invariant operands, 1 = DMMA m8n8k4, 2 = DFMA with three distinct register
  * operands: sustained throughput in FLOP/s (FMA = 2), CUDA events; 3 = latency of a dependent DFMA in SM cycles.

@@ -81,6 +81,7 @@ _SIGNATURES = {
     "mlmcb200_maxent_workspace_bytes": (_c_i64, [_c_i64, _c_i32]),
     "mlmcb200_maxent_fgh": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i32, _c_i32, _c_vp, _c_vp,
                                            _c_i64, _c_vp]),
+    "mlmcb200_density_eval": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_vp, _c_i32, _c_vp, _c_vp]),
     "mlmcb200_fp64_peak": (ctypes.c_int, [_c_i32, ctypes.POINTER(_c_dbl), _c_vp]),
 }
 
@@ -532,6 +533,21 @@ def maxent_fgh(phi, w, lam_scaled, what=7, out=None, workspace=None):
         _check(lib.mlmcb200_maxent_fgh(_ptr(phi), ld, _ptr(w), _ptr(lam_scaled), Q, R, what, _ptr(out), _ptr(ws),
                                        ws.numel(), _stream()), "maxent_fgh")
     launch_count += 3
+    return out
+
+
+def density_eval(basis, x, coef):
+    """exp(clip(-phi(x) . coef, -200, 200)) for a flat CUDA float64 tensor x; coef: CUDA float64 [n_coef <= basis.size]."""
+    global launch_count
+    _require_cuda(x, "x")
+    _require_cuda(coef, "coef")
+    x = x.contiguous()
+    coef = coef.contiguous()
+    out = torch.empty(x.numel(), dtype=torch.float64, device=x.device)
+    with _on_device(x.device):
+        _check(load().mlmcb200_density_eval(ctypes.byref(basis), _ptr(x), x.numel(), _ptr(coef), coef.numel(),
+                                            _ptr(out), _stream()), "density_eval")
+    launch_count += 1
     return out
 
 

@@ -94,10 +94,66 @@ __global__ void basis_eval_kernel(const EvalArgs a) {
     }
 }
 
+// SimpleDistribution.density (mlmc/tool/simple_distribution.py:96-105): exp(clip(-phi(x) . coef, -200, 200)) without the
+// table: one thread per value walks the recurrence (the table's own operations) and accumulates the dot product.
+__global__ void density_eval_kernel(const mlmcb200_basis_t basis, const double* __restrict__ x, int64_t n,
+                                    const double* __restrict__ coef, int n_coef, double* __restrict__ out) {
+    extern __shared__ double cf[];
+    for (int i = threadIdx.x; i < n_coef; i += blockDim.x) cf[i] = coef[i];
+    __syncthreads();
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const double xv = x[k];
+        double dot;
+        if (basis.kind == MLMCB200_RAW) {
+            dot = cf[0] * xv;
+        } else {
+            const double t = map_to_ref(basis, xv);
+            if (basis.kind == MLMCB200_FOURIER) {
+                dot = cf[0];
+                for (int i = 1; i < n_coef; ++i) {
+                    const double kt = __dmul_rn(t, (double)((i + 1) >> 1));
+                    dot = fma(cf[i], (i & 1) ? cos(kt) : sin(kt), dot);
+                }
+            } else {
+                double p0 = __dadd_rn(__dmul_rn(t, 0.0), 1.0), p1 = t;
+                dot = cf[0] * p0;
+                if (n_coef > 1) dot = fma(cf[1], p1, dot);
+                for (int i = 2; i < n_coef; ++i) {
+                    const double p2 = basis.kind == MLMCB200_LEGENDRE ? legendre_step_exact(p1, p0, t, i)
+                                                                       : __dmul_rn(p1, t);
+                    dot = fma(cf[i], p2, dot);
+                    p0 = p1;
+                    p1 = p2;
+                }
+            }
+        }
+        // np.minimum(np.maximum(power, -200), 200) keeps NaN (a value outside a clipped domain); fmin / fmax would not
+        const double power = isnan(dot) ? dot : fmin(fmax(-dot, -200.0), 200.0);
+        out[k] = exp(power);
+    }
+}
+
 }  // namespace
 }  // namespace mlmcb200
 
 using namespace mlmcb200;
+
+extern "C" int mlmcb200_density_eval(const mlmcb200_basis_t* basis, const double* x, int64_t n, const double* coef,
+                                     int32_t n_coef, double* out, void* stream) {
+    if (check_basis(basis) != 0) return -1;
+    MB_REQUIRE(n >= 0 && n_coef >= 1 && n_coef <= basis->size, "density_eval: bad n=%lld n_coef=%d (basis size %d)",
+               (long long)n, n_coef, basis->size);
+    if (n == 0) return 0;
+    MB_REQUIRE(x != nullptr && coef != nullptr && out != nullptr, "density_eval: null pointer");
+    const int threads = 128;
+    int64_t blocks = (n + threads - 1) / threads;
+    const int64_t max_blocks = (int64_t)sm_count() * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
+    density_eval_kernel<<<(unsigned)blocks, threads, (size_t)n_coef * sizeof(double), (cudaStream_t)stream>>>(
+        *basis, x, n, coef, n_coef, out);
+    MB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int mlmcb200_basis_eval(const mlmcb200_basis_t* basis, const double* x, int64_t n,
                                    const double* matrix, int32_t n_rows, int32_t n_out,

@@ -278,7 +278,8 @@ __device__ __forceinline__ void slot_tile(double (&am)[GS][GS][2], double (&av)[
 }
 
 // the block masks the planner can emit (make_plan).  Off the block diagonal: whole group, one column, one row (edge
-// groups), single block; on it: upper triangle, its first row, its last block, single block.
+// groups), the lower block of the first column, single block; on it: upper triangle, its first row, its last block,
+// single block.
 #define MB_SLOT_SWITCH(MASKVAR, DIAGVAR, CALL)                                  \
     if (DIAGVAR) {                                                              \
         switch (MASKVAR) {                                                      \
@@ -294,6 +295,7 @@ __device__ __forceinline__ void slot_tile(double (&am)[GS][GS][2], double (&av)[
             case 0x5: CALL(0x5, false); break;                                  \
             case 0xA: CALL(0xA, false); break;                                  \
             case 0x3: CALL(0x3, false); break;                                  \
+            case 0x4: CALL(0x4, false); break;                                  \
             case 0x1: CALL(0x1, false); break;                                  \
             default: break;                                                     \
         }                                                                       \
@@ -516,11 +518,76 @@ __global__ void reduce_partials_sym_kernel(const double* __restrict__ partial, i
     if (lane == 0) acc[jo] += j < 2 ? s1 : 0.5 * (s1 + s2);
 }
 
-int popcount4(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1); }
+// ---- task planner ------------------------------------------------------------------------------------------------
+// The upper triangle of 8x8 blocks is cut into tasks (a GS x GS group of blocks, or a part of one that the kernel has a
+// straight-line specialisation for) and dealt to the warps.  What has to be balanced is the DMMA count per SM
+// SUB-PARTITION (warp w issues on sub-partition w % 4; each has its own FP64 tensor pipe, and two resident warps keep it
+// busy), with the cost of a block depending on the mode: a diagonal block needs one product where an off-diagonal one
+// needs two (sums of fine + coarse levels), 3 vs 5 with the sums of squares.  The planner tries every small number of
+// splits of each kind, packs the pieces into the four sub-partitions (longest processing time first + pairwise
+// improvement) and keeps the split with the lowest maximum; inside a sub-partition the pieces go to its warps the same way.
+struct PlanTask { int gi, gj, mask, cost; };
 
-// n_warps / n_slots: warps that contract and task slots per warp
-int make_plan(int R, int n_warps, int n_slots, GramPlan* pl, size_t* smem, int fixed_ld = 0, int ns_cap = 128,
-              size_t budget = 216u * 1024u) {
+int block_cost_sum(int gi, int gj, int mask, int gs, int cd, int co) {
+    int c = 0;
+    for (int u = 0; u < gs; ++u)
+        for (int v = 0; v < gs; ++v)
+            if ((mask >> (u * gs + v)) & 1) c += (gi * gs + u == gj * gs + v) ? cd : co;
+    return c;
+}
+
+// pieces -> n_bins bins of at most cap pieces; returns the largest bin load (or -1 if they do not fit)
+int pack_bins(const PlanTask* pieces, int n, int n_bins, int cap, int* bin_of) {
+    int order[kWarps * kMaxSlots];
+    for (int i = 0; i < n; ++i) order[i] = i;
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j)
+            if (pieces[order[j]].cost > pieces[order[i]].cost) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+    int load[kWarps] = {0}, cnt[kWarps] = {0};
+    for (int k = 0; k < n; ++k) {
+        int best = -1;
+        for (int b = 0; b < n_bins; ++b)
+            if (cnt[b] < cap && (best < 0 || load[b] < load[best])) best = b;
+        if (best < 0) return -1;
+        bin_of[order[k]] = best;
+        load[best] += pieces[order[k]].cost;
+        ++cnt[best];
+    }
+    // improvement: move or swap pieces between the heaviest bin and another one while that lowers the pair's maximum
+    for (int pass = 0; pass < 64; ++pass) {
+        int hb = 0;
+        for (int b = 1; b < n_bins; ++b) if (load[b] > load[hb]) hb = b;
+        bool changed = false;
+        for (int i = 0; i < n && !changed; ++i) {
+            if (bin_of[i] != hb) continue;
+            for (int ob = 0; ob < n_bins && !changed; ++ob) {
+                if (ob == hb) continue;
+                if (cnt[ob] < cap && load[ob] + pieces[i].cost < load[hb]) {            // move
+                    bin_of[i] = ob; load[hb] -= pieces[i].cost; load[ob] += pieces[i].cost; --cnt[hb]; ++cnt[ob];
+                    changed = true;
+                    break;
+                }
+                for (int j = 0; j < n; ++j) {                                           // swap
+                    if (bin_of[j] != ob) continue;
+                    const int d = pieces[i].cost - pieces[j].cost;
+                    if (d > 0 && load[ob] + d < load[hb]) {
+                        bin_of[i] = ob; bin_of[j] = hb; load[hb] -= d; load[ob] += d;
+                        changed = true;
+                        break;
+                    }
+                }
+            }
+        }
+        if (!changed) break;
+    }
+    int worst = 0;
+    for (int b = 0; b < n_bins; ++b) worst = load[b] > worst ? load[b] : worst;
+    return worst;
+}
+
+// n_warps / n_slots: warps that contract and task slots per warp; cd / co: DMMAs per diagonal / off-diagonal block
+int make_plan_uncached(int R, int n_warps, int n_slots, GramPlan* pl, size_t* smem, int fixed_ld, int ns_cap,
+                       size_t budget, int cd, int co) {
     const int nb = (R + 7) / 8;
     if (fixed_ld && R > kGramMaxMoments) {
         set_error("gram: %d moments do not fit the shared-memory tile (max %d)", R, kGramMaxMoments);
@@ -532,8 +599,8 @@ int make_plan(int R, int n_warps, int n_slots, GramPlan* pl, size_t* smem, int f
     const int ng = (nb + gs - 1) / gs;
     const int kMaxTasks = n_warps * n_slots;
     // natural tasks: one per pair of block groups on/above the diagonal; mask = blocks that exist and have J >= I
-    struct T { int gi, gj, mask, w; } tasks[kWarps * kMaxSlots + 2];
-    int nt = 0, total = 0;
+    PlanTask nat[kWarps * kMaxSlots];
+    int n_nat = 0, total = 0;
     for (int gi = 0; gi < ng; ++gi)
         for (int gj = gi; gj < ng; ++gj) {
             int mask = 0;
@@ -542,46 +609,75 @@ int make_plan(int R, int n_warps, int n_slots, GramPlan* pl, size_t* smem, int f
                     const int I = gi * gs + u, J = gj * gs + v;
                     if (I < nb && J < nb && J >= I) mask |= 1 << (u * gs + v);
                 }
-            if (nt >= kMaxTasks) {
+            if (n_nat >= kMaxTasks) {
                 set_error("gram: %d moments need more than %d block tasks", R, kMaxTasks);
                 return -1;
             }
-            tasks[nt++] = {gi, gj, mask, popcount4(mask)};
-            total += popcount4(mask);
+            nat[n_nat] = {gi, gj, mask, block_cost_sum(gi, gj, mask, gs, cd, co)};
+            total += nat[n_nat++].cost;
         }
-    // longest-processing-time assignment; while the heaviest warp exceeds the ideal load, split the biggest splittable
-    // task (whole group -> two columns, triangle -> first row + last block) and redo the assignment
-    const int target = (total + n_warps - 1) / n_warps;
-    int load[kWarps];
-    for (int round = 0; round < kMaxTasks; ++round) {
-        for (int i = 0; i < nt; ++i)
-            for (int j = i + 1; j < nt; ++j)
-                if (tasks[j].w > tasks[i].w) { T t = tasks[i]; tasks[i] = tasks[j]; tasks[j] = t; }
-        for (int w = 0; w < kWarps; ++w) { pl->n_tasks[w] = 0; load[w] = 0; }
-        for (int i = 0; i < nt; ++i) {
-            int best = -1;
-            for (int w = 0; w < n_warps; ++w)
-                if (pl->n_tasks[w] < n_slots && (best < 0 || load[w] < load[best])) best = w;
-            const int k = pl->n_tasks[best]++;
-            pl->gi[best][k] = (unsigned char)tasks[i].gi;
-            pl->gj[best][k] = (unsigned char)tasks[i].gj;
-            pl->mk[best][k] = (unsigned char)tasks[i].mask;
-            load[best] += tasks[i].w;
+    // splits the kernel has specialisations for: whole off-diagonal group -> two columns (0xF -> 0x5 + 0xA), diagonal
+    // triangle -> first row + last block (0xB -> 0x3 + 0x8), off-diagonal column -> two blocks (0x5 -> 0x1 + 0x4)
+    int n_full = 0, n_tri = 0, n_col = 0;
+    for (int i = 0; i < n_nat; ++i) {
+        const bool dg = nat[i].gi == nat[i].gj;
+        n_full += !dg && nat[i].mask == 0xF;
+        n_tri += dg && nat[i].mask == 0xB;
+        n_col += !dg && nat[i].mask == 0x5;
+    }
+    const int n_bins = n_warps < 4 ? n_warps : 4, cap = (n_warps / n_bins) * n_slots;
+    const int ideal = (total + n_bins - 1) / n_bins;
+    PlanTask best[kWarps * kMaxSlots];
+    int best_bin[kWarps * kMaxSlots], best_n = 0, best_worst = -1;
+    for (int sa = 0; sa <= (gs == 2 ? n_full : 0) && sa <= 4; ++sa)
+        for (int sb = 0; sb <= (gs == 2 ? n_tri : 0) && sb <= 6; ++sb)
+            for (int sc = 0; sc <= (gs == 2 ? n_col : 0) && sc <= 6; ++sc) {
+                if (n_nat + sa + sb + sc > kMaxTasks) continue;
+                if (best_worst == ideal && n_nat + sa + sb + sc >= best_n) continue;
+                PlanTask pc[kWarps * kMaxSlots];
+                int n = 0, ua = 0, ub = 0, uc = 0;
+                for (int i = 0; i < n_nat; ++i) {
+                    const PlanTask t = nat[i];
+                    const bool dg = t.gi == t.gj;
+                    int m1 = t.mask, m2 = 0;
+                    if (!dg && t.mask == 0xF && ua < sa) { m1 = 0x5; m2 = 0xA; ++ua; }
+                    else if (dg && t.mask == 0xB && ub < sb) { m1 = 0x3; m2 = 0x8; ++ub; }
+                    else if (!dg && t.mask == 0x5 && uc < sc) { m1 = 0x1; m2 = 0x4; ++uc; }
+                    pc[n++] = {t.gi, t.gj, m1, block_cost_sum(t.gi, t.gj, m1, gs, cd, co)};
+                    if (m2) pc[n++] = {t.gi, t.gj, m2, block_cost_sum(t.gi, t.gj, m2, gs, cd, co)};
+                }
+                int bin_of[kWarps * kMaxSlots];
+                const int worst = pack_bins(pc, n, n_bins, cap, bin_of);
+                if (worst < 0) continue;
+                if (best_worst < 0 || worst < best_worst || (worst == best_worst && n < best_n)) {
+                    best_worst = worst;
+                    best_n = n;
+                    for (int i = 0; i < n; ++i) { best[i] = pc[i]; best_bin[i] = bin_of[i]; }
+                }
+            }
+    if (best_worst < 0) {
+        set_error("gram: no task plan for %d moments", R);
+        return -1;
+    }
+    // inside a sub-partition: its pieces to its warps (b, b + 4, ...), at most n_slots each
+    for (int w = 0; w < kWarps; ++w) pl->n_tasks[w] = 0;
+    for (int b = 0; b < n_bins; ++b) {
+        PlanTask mine[kWarps * kMaxSlots];
+        int n = 0;
+        for (int i = 0; i < best_n; ++i)
+            if (best_bin[i] == b) mine[n++] = best[i];
+        int warp_of[kWarps * kMaxSlots];
+        const int n_sub = n_warps / n_bins;
+        if (pack_bins(mine, n, n_sub, n_slots, warp_of) < 0) {
+            set_error("gram: task plan for %d moments does not fit the warps", R);
+            return -1;
         }
-        int worst = 0;
-        for (int w = 0; w < n_warps; ++w) worst = load[w] > worst ? load[w] : worst;
-        if (worst <= target || gs == 1 || nt + 1 > kMaxTasks) break;
-        int pick = -1;
-        for (int i = 0; i < nt; ++i)
-            if ((tasks[i].mask == 0xF || tasks[i].mask == 0xB) && (pick < 0 || tasks[i].w > tasks[pick].w)) pick = i;
-        if (pick < 0) break;
-        const T t = tasks[pick];
-        if (t.mask == 0xF) {
-            tasks[pick] = {t.gi, t.gj, 0x5, 2};
-            tasks[nt++] = {t.gi, t.gj, 0xA, 2};
-        } else {
-            tasks[pick] = {t.gi, t.gj, 0x3, 2};
-            tasks[nt++] = {t.gi, t.gj, 0x8, 1};
+        for (int i = 0; i < n; ++i) {
+            const int w = b + n_bins * warp_of[i];
+            const int k = pl->n_tasks[w]++;
+            pl->gi[w][k] = (unsigned char)mine[i].gi;
+            pl->gj[w][k] = (unsigned char)mine[i].gj;
+            pl->mk[w][k] = (unsigned char)mine[i].mask;
         }
     }
     int ld = 8 * nb;
@@ -598,6 +694,34 @@ int make_plan(int R, int n_warps, int n_slots, GramPlan* pl, size_t* smem, int f
     }
     pl->ns = ns;
     *smem = (size_t)2 * ns * ld * sizeof(double);
+    return 0;
+}
+
+// The search above costs ~1 ms of host time: plans are memoised per thread (a handful of distinct keys per process).
+int make_plan(int R, int n_warps, int n_slots, GramPlan* pl, size_t* smem, int fixed_ld = 0, int ns_cap = 128,
+              size_t budget = 216u * 1024u, int cd = 1, int co = 1) {
+    struct Entry { int key[8]; GramPlan plan; size_t smem; };
+    constexpr int kCache = 16;
+    static thread_local Entry cache[kCache];
+    static thread_local int n_cached = 0, next = 0;
+    const int key[8] = {R, n_warps, n_slots, fixed_ld, ns_cap, (int)budget, cd, co};
+    for (int i = 0; i < n_cached; ++i) {
+        bool same = true;
+        for (int k = 0; k < 8; ++k) same = same && cache[i].key[k] == key[k];
+        if (same) {
+            *pl = cache[i].plan;
+            *smem = cache[i].smem;
+            return 0;
+        }
+    }
+    const int rc = make_plan_uncached(R, n_warps, n_slots, pl, smem, fixed_ld, ns_cap, budget, cd, co);
+    if (rc != 0) return rc;
+    Entry& e = cache[next];
+    for (int k = 0; k < 8; ++k) e.key[k] = key[k];
+    e.plan = *pl;
+    e.smem = *smem;
+    next = (next + 1) % kCache;
+    if (n_cached < kCache) ++n_cached;
     return 0;
 }
 
@@ -844,10 +968,16 @@ extern "C" int mlmcb200_gram_accumulate_comp(const mlmcb200_basis_t* basis, cons
         two_env = e ? atoi(e) : 0;
     }
     const bool two_ctas = two_env > 0 && (mode == 1 || !want_var);
+    // DMMAs per diagonal / off-diagonal block of the mode (slot_mma)
+    int cd = 1, co = 1;
+    if (mode == 0 && has_coarse) {
+        cd = want_var ? 3 : 1;
+        co = want_var ? 5 : 2;
+    }
     if (two_ctas) {
-        if (make_plan(basis->size, 8, 4, &a.plan, &smem, kLD, 64, 111u * 1024u) != 0) return -1;
+        if (make_plan(basis->size, 8, 4, &a.plan, &smem, kLD, 64, 111u * 1024u, cd, co) != 0) return -1;
     } else {
-        if (make_plan(basis->size, kWarps, 2, &a.plan, &smem, kLD) != 0) return -1;
+        if (make_plan(basis->size, kWarps, 2, &a.plan, &smem, kLD, 128, 216u * 1024u, cd, co) != 0) return -1;
     }
     const int64_t R2 = (int64_t)basis->size * basis->size;
     const int64_t stride = 2 + 2 * R2;

@@ -302,10 +302,18 @@ class SimpleDistribution:
         as_numpy = not isinstance(value, torch.Tensor)
         if as_numpy:
             value = torch.from_numpy(np.atleast_1d(np.asarray(value, dtype=np.float64))).to(_device())
-        moms = self.moments_fn.eval_all(value.reshape(-1), self.approx_size)
-        lam = torch.from_numpy(np.asarray(self.multipliers / self._moment_errs, dtype=np.float64)).to(moms.device)
-        out = torch.exp(torch.clamp(-(moms @ lam), -200, 200))
+        out = _native.density_eval(self.moments_fn.basis_struct(), value.reshape(-1).to(torch.float64),
+                                   self._density_coefficients(value.device))
         return out.cpu().numpy() if as_numpy else out
+
+    def _density_coefficients(self, device):
+        """``lambda / sigma`` in terms of the BASE functions (a TransformedMoments basis ``L phi``: ``L[:n]^T lambda / sigma``),
+        for the one-launch ``mlmcb200_density_eval`` (no moment table, no library matmul)."""
+        lam = np.asarray(self.multipliers / self._moment_errs, dtype=np.float64)
+        l_mat = self.moments_fn.transform_matrix()
+        if l_mat is not None:
+            lam = l_mat[:self.approx_size].T @ lam
+        return torch.from_numpy(np.ascontiguousarray(lam)).to(device)
 
     def cdf(self, values):
         """Cumulative 10-point Gauss sums between consecutive values (``:108-125``), all intervals evaluated in

@@ -608,3 +608,28 @@ def test_percentile_stats_equal_numpy(case):
         want = np.percentile(host, percents)
     got = _percentiles(values, percents)
     assert np.array_equal(got, want, equal_nan=True), (case, got, want)
+
+
+@pytest.mark.parametrize("kind,size,n_coef", [("legendre", 25, 25), ("legendre", 50, 37), ("monomial", 8, 8),
+                                              ("fourier", 9, 9)])
+def test_density_eval_matches_oracle(kind, size, n_coef):
+    """mlmcb200_density_eval = SimpleDistribution.density (simple_distribution.py:96-105): exp(clip(-phi . lambda/sigma)),
+    NaN outside a clipped domain, the +-200 clip honoured."""
+    nat = native()
+    rng = np.random.default_rng(size)
+    b = orc.Basis(kind, size, (-2.0, 3.0))
+    x = np.concatenate([rng.uniform(-2.0, 3.0, 5000), [-2.0, 3.0, 3.5, -2.5]])
+    coef = rng.normal(size=n_coef) * 0.7
+    coef[0] = 1.3
+    for scale in (1.0, 400.0):                                     # the second one drives |power| beyond 200
+        want_pow = -np.sum(orc.basis_eval(b, x, n_coef) * coef * scale, axis=1)
+        want = np.exp(np.minimum(np.maximum(want_pow, -200), 200))
+        got = nat.density_eval(to_struct(b), torch.from_numpy(x).to(dev()), torch.from_numpy(coef * scale).to(dev()))
+        got = got.cpu().numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(want)) and np.isnan(got[-2:]).all()
+        inside = ~np.isnan(want)
+        # d exp(p) = exp(p) dp: the dot product of n_coef terms of size |coef| differs by a few ulp of its largest term
+        tol = 1e-13 * scale * np.sum(np.abs(coef)) + 1e-15
+        assert np.max(np.abs(np.log(got[inside]) - np.log(want[inside]))) <= tol
+        if scale > 1.0:
+            assert (got[inside] == np.exp(200.0)).any() or (got[inside] == np.exp(-200.0)).any()
