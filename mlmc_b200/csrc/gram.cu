@@ -24,10 +24,13 @@ constexpr int kWarps = 16;
 constexpr int kThreadsGram = kWarps * 32;
 constexpr int kMaxSlots = 4;     // tasks per warp (array bound; the plans use 2 ... 4)
 constexpr int kMaxGroup = 2;     // blocks per task side
-// Leading dimension of the covariance tiles, a compile-time constant (4 mod 8, >= 8 * 13 + 3 for the row skew) so that
-// every fragment address of a tile is "slot base register + immediate": holds up to 13 blocks = 104 moments.
-constexpr int kLD = 108;
+// Leading dimension of the covariance tiles: a compile-time constant (template parameter; 4 mod 8, >= 8 nb + 3 for the
+// row skew) so that every fragment address of a tile is "slot base register + immediate".  Three sizes: up to 4 / 7 / 13
+// blocks of 8 moments -- a narrower tile holds more samples (128 -> 224 -> 384 with two arrays), which spreads the
+// produce phase over more warps and the per-tile costs (two barriers, task dispatch) over more DMMAs.
+constexpr int kLDSmall = 36, kLDMid = 60, kLDWide = 108;
 constexpr int kGramMaxMoments = 104;
+inline int gram_ld(int nb) { return nb <= 4 ? kLDSmall : nb <= 7 ? kLDMid : kLDWide; }
 
 struct GramPlan {
     int nb;          // 8x8 blocks per side
@@ -123,17 +126,22 @@ __device__ __forceinline__ void write_row(const mlmcb200_basis_t& b, double t, b
 // (d_ij = f_i f_j - c_i c_j = (D_i S_j + S_i D_j) / 2: no cancellation between two Gram matrices, see slot_mma).
 // One thread runs both recurrences of a sample (two independent chains; a lane-pair variant that exchanged every
 // element by shuffle was 4 % slower).  Zero rows for a dropped sample.
+// ONLY_D (Gram of the differences): the tile is the single array D.
+template <bool ONLY_D>
 __device__ __forceinline__ void write_rows_sd(const mlmcb200_basis_t& b, double tf, double tc, bool good, double* row_s,
                                               double* row_d, int r_pad) {
     const int R = b.size;
     if (!good) {
-        for (int i = 0; i < r_pad; ++i) row_s[i] = row_d[i] = 0.0;
+        for (int i = 0; i < r_pad; ++i) {
+            if (!ONLY_D) row_s[i] = 0.0;
+            row_d[i] = 0.0;
+        }
         return;
     }
-#define MB_PUT(I, F, C)            \
-    {                              \
-        row_s[I] = (F) + (C);      \
-        row_d[I] = (F) - (C);      \
+#define MB_PUT(I, F, C)                         \
+    {                                           \
+        if (!ONLY_D) row_s[I] = (F) + (C);      \
+        row_d[I] = (F) - (C);                   \
     }
     if (b.kind == MLMCB200_RAW) {
         MB_PUT(0, tf, tc)
@@ -186,7 +194,10 @@ __device__ __forceinline__ void write_rows_sd(const mlmcb200_basis_t& b, double 
         }
     }
 #undef MB_PUT
-    for (int i = R; i < r_pad; ++i) row_s[i] = row_d[i] = 0.0;
+    for (int i = R; i < r_pad; ++i) {
+        if (!ONLY_D) row_s[i] = 0.0;
+        row_d[i] = 0.0;
+    }
 }
 
 // All DMMAs of one task for one 4-sample step.  MASK = the 8x8 blocks of the GS x GS group this slot owns
@@ -258,20 +269,20 @@ __device__ __forceinline__ void slot_mma(double (&am)[GS][GS][2], double (&av)[G
 }
 
 // All k-steps of one tile for one task slot.  The fragment pointers of the slot are computed once per tile; inside
-// the 4-k-step unrolled body every shared-memory address is pointer + immediate (constant kLD, the row skew has
+// the 4-k-step unrolled body every shared-memory address is pointer + immediate (constant LD, the row skew has
 // period 4 k-steps), so the loop carries no address arithmetic and the loads of a k-step can be hoisted over the DMMAs
 // of the previous one.  NS is a multiple of 16.
-template <bool COARSE, int MODE, int GS, int MASK, bool DIAG>
+template <bool COARSE, int MODE, int GS, int MASK, bool DIAG, int LD>
 __device__ __forceinline__ void slot_tile(double (&am)[GS][GS][2], double (&av)[GS][GS][2], const double* phi_f,
                                           const double* phi_c, const int (&off_r)[GS], const int (&off_c)[GS],
                                           int NS) {
     for (int k0 = 0; k0 < NS; k0 += 16) {
-        const double* pf = phi_f + (size_t)k0 * kLD;
-        const double* pc = phi_c + (size_t)k0 * kLD;
+        const double* pf = phi_f + (size_t)k0 * LD;
+        const double* pc = phi_c + (size_t)k0 * LD;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const double* pfq = pf + q * 4 * kLD + q;
-            const double* pcq = pc + q * 4 * kLD + q;
+            const double* pfq = pf + q * 4 * LD + q;
+            const double* pcq = pc + q * 4 * LD + q;
             slot_mma<COARSE, MODE, GS, MASK, DIAG>(am, av, pfq, pcq, off_r, off_c);  // skew of rows k0 + 4q .. : q
         }
     }
@@ -308,16 +319,18 @@ __device__ __forceinline__ void slot_tile(double (&am)[GS][GS][2], double (&av)[
 // a second tile while 12 warps contracted the first) was slower: an FP64-pipe instruction issued while DMMAs are in
 // flight costs the tensor pipe ~10 cycles (measured: contraction alone 33.5 TFLOP/s, producers alone 1/3 of that time,
 // together 26.6 TFLOP/s), so the phases do not overlap for free and the larger single tile wins (28.6 TFLOP/s).
-// WARPS / SLOTS: 16 warps x 2 task slots, one CTA per SM (128-sample tiles) -- or 8 warps x 4 slots, TWO CTAs per SM
-// (64-sample tiles): a CTA's produce phase and barrier waits then overlap the other CTA's DMMA stream.
-template <bool COARSE, int MODE, int GS, int WARPS, int SLOTS>
+// WARPS / SLOTS: 16 warps x 2 task slots, one CTA per SM.  (Two 8-warp CTAs per SM on half-size tiles, so that one
+// CTA's produce phase overlaps the other's DMMA stream, lost to this with the S / D tiles and was removed.)
+template <bool COARSE, int MODE, int GS, int WARPS, int SLOTS, int LD>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2) gram_kernel(const GramArgs a) {
     extern __shared__ double sm[];
     const GramPlan& pl = a.plan;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int LD = kLD;
     const int NS = pl.ns, nb = pl.nb, r_pad = 8 * nb, R = a.basis.size;
-    const size_t tile_elems = (size_t)2 * NS * LD;             // Phi_f rows then Phi_c rows
+    // arrays of NS rows in the tile: S and D (fine + coarse covariance); D alone (difference Gram); phi(f) (level 0)
+    constexpr bool ONLY_D = COARSE && MODE == 2;
+    constexpr int N_ARRAYS = (COARSE && !ONLY_D) ? 2 : 1;
+    const size_t tile_elems = (size_t)N_ARRAYS * NS * LD;
     __shared__ unsigned cnt_sm[2];
     if (tid == 0) cnt_sm[0] = cnt_sm[1] = 0;
 
@@ -391,24 +404,24 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2) gram_kernel(c
             cnt_rm += good ? 0u : 1u;
         }
         if (COARSE)
-            write_rows_sd(a.basis, tf, tc, good, row, row + (size_t)NS * LD, r_pad);
+            write_rows_sd<ONLY_D>(a.basis, tf, tc, good, row, ONLY_D ? row : row + (size_t)NS * LD, r_pad);
         else
             write_row(a.basis, tf, good, row, r_pad);
     };
     auto consume = [&](const double* tile_base) {
         const double* phi_f = tile_base + frag_off;
-        const double* phi_c = phi_f + (size_t)NS * LD;
+        const double* phi_c = N_ARRAYS == 2 ? phi_f + (size_t)NS * LD : phi_f;
 #pragma unroll
         for (int slot = 0; slot < SLOTS; ++slot) {
             if (GS == 1) {
                 if (mask[slot] && diag[slot])
-                    slot_tile<COARSE, MODE, GS, 0x1, true>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], phi_f, phi_c,
-                                                           off_r[slot], off_c[slot], NS);
+                    slot_tile<COARSE, MODE, GS, 0x1, true, LD>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], phi_f, phi_c,
+                                                               off_r[slot], off_c[slot], NS);
                 else if (mask[slot])
-                    slot_tile<COARSE, MODE, GS, 0x1, false>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], phi_f, phi_c,
-                                                            off_r[slot], off_c[slot], NS);
+                    slot_tile<COARSE, MODE, GS, 0x1, false, LD>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], phi_f, phi_c,
+                                                                off_r[slot], off_c[slot], NS);
             } else {
-#define MB_CALL(M, D) slot_tile<COARSE, MODE, GS, M, D>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], phi_f, phi_c, off_r[slot], off_c[slot], NS)
+#define MB_CALL(M, D) slot_tile<COARSE, MODE, GS, M, D, LD>(acc_m[slot], acc_v[MODE == 1 ? slot : 0], phi_f, phi_c, off_r[slot], off_c[slot], NS)
                 MB_SLOT_SWITCH(mask[slot], diag[slot], MB_CALL)   // warp-uniform, once per slot and tile
 #undef MB_CALL
             }
@@ -587,7 +600,7 @@ int pack_bins(const PlanTask* pieces, int n, int n_bins, int cap, int* bin_of) {
 
 // n_warps / n_slots: warps that contract and task slots per warp; cd / co: DMMAs per diagonal / off-diagonal block
 int make_plan_uncached(int R, int n_warps, int n_slots, GramPlan* pl, size_t* smem, int fixed_ld, int ns_cap,
-                       size_t budget, int cd, int co) {
+                       size_t budget, int cd, int co, int n_arrays) {
     const int nb = (R + 7) / 8;
     if (fixed_ld && R > kGramMaxMoments) {
         set_error("gram: %d moments do not fit the shared-memory tile (max %d)", R, kGramMaxMoments);
@@ -684,40 +697,41 @@ int make_plan_uncached(int R, int n_warps, int n_slots, GramPlan* pl, size_t* sm
     while (ld % 8 != 4) ++ld;
     if (fixed_ld) ld = fixed_ld;
     pl->ld = ld;
-    // tile of Phi_f + Phi_c rows; NS a multiple of 4
-    int ns = (int)(budget / ((size_t)2 * ld * sizeof(double)));
-    ns = fixed_ld ? (ns / 16) * 16 : (ns / 4) * 4;      // covariance tiles: whole 4-k-step unrolled bodies
+    // tile of n_arrays arrays of NS rows; NS a multiple of 4
+    int ns = (int)(budget / ((size_t)n_arrays * ld * sizeof(double)));
     if (ns > ns_cap) ns = ns_cap;
+    ns = fixed_ld ? (ns / 16) * 16 : (ns / 4) * 4;      // covariance tiles: whole 4-k-step unrolled bodies
     if (ns < 8) {
         set_error("gram: %d moments do not fit the shared-memory tile", R);
         return -1;
     }
     pl->ns = ns;
-    *smem = (size_t)2 * ns * ld * sizeof(double);
+    *smem = (size_t)n_arrays * ns * ld * sizeof(double);
     return 0;
 }
 
 // The search above costs ~1 ms of host time: plans are memoised per thread (a handful of distinct keys per process).
 int make_plan(int R, int n_warps, int n_slots, GramPlan* pl, size_t* smem, int fixed_ld = 0, int ns_cap = 128,
-              size_t budget = 216u * 1024u, int cd = 1, int co = 1) {
-    struct Entry { int key[8]; GramPlan plan; size_t smem; };
+              size_t budget = 216u * 1024u, int cd = 1, int co = 1, int n_arrays = 2) {
+    constexpr int kKey = 9;
+    struct Entry { int key[kKey]; GramPlan plan; size_t smem; };
     constexpr int kCache = 16;
     static thread_local Entry cache[kCache];
     static thread_local int n_cached = 0, next = 0;
-    const int key[8] = {R, n_warps, n_slots, fixed_ld, ns_cap, (int)budget, cd, co};
+    const int key[kKey] = {R, n_warps, n_slots, fixed_ld, ns_cap, (int)budget, cd, co, n_arrays};
     for (int i = 0; i < n_cached; ++i) {
         bool same = true;
-        for (int k = 0; k < 8; ++k) same = same && cache[i].key[k] == key[k];
+        for (int k = 0; k < kKey; ++k) same = same && cache[i].key[k] == key[k];
         if (same) {
             *pl = cache[i].plan;
             *smem = cache[i].smem;
             return 0;
         }
     }
-    const int rc = make_plan_uncached(R, n_warps, n_slots, pl, smem, fixed_ld, ns_cap, budget, cd, co);
+    const int rc = make_plan_uncached(R, n_warps, n_slots, pl, smem, fixed_ld, ns_cap, budget, cd, co, n_arrays);
     if (rc != 0) return rc;
     Entry& e = cache[next];
-    for (int k = 0; k < 8; ++k) e.key[k] = key[k];
+    for (int k = 0; k < kKey; ++k) e.key[k] = key[k];
     e.plan = *pl;
     e.smem = *smem;
     next = (next + 1) % kCache;
@@ -725,26 +739,24 @@ int make_plan(int R, int n_warps, int n_slots, GramPlan* pl, size_t* smem, int f
     return 0;
 }
 
-template <bool COARSE, int MODE, int GS, int WARPS, int SLOTS>
+template <bool COARSE, int MODE, int GS, int LD>
 int launch_gram(const GramArgs& a, int grid, int n_comp, size_t smem, cudaStream_t st) {
-    auto kern = gram_kernel<COARSE, MODE, GS, WARPS, SLOTS>;
+    auto kern = gram_kernel<COARSE, MODE, GS, kWarps, 2, LD>;
     MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3((unsigned)grid, (unsigned)n_comp), WARPS * 32, smem, st>>>(a);
+    kern<<<dim3((unsigned)grid, (unsigned)n_comp), kWarps * 32, smem, st>>>(a);
     MB_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-// two_ctas: the 8-warp / 4-slot / two-CTAs-per-SM variant (sums-only modes: the sums-of-squares accumulators of mode 1
-// do not fit 128 registers per thread)
+// tile width and block-group size follow from the number of 8-moment blocks (gram_ld, make_plan): up to 4 blocks
+// (narrow tile, single blocks), 5 (mid tile, single blocks), 6-7 (mid tile, 2 x 2 groups), 8-13 (wide tile, 2 x 2 groups)
 template <bool COARSE, int MODE>
-int launch_gram_gs(const GramArgs& a, int grid, int n_comp, size_t smem, cudaStream_t st, bool two_ctas) {
-    if constexpr (MODE != 1) {
-        if (two_ctas)
-            return a.plan.gs == 1 ? launch_gram<COARSE, MODE, 1, 8, 4>(a, grid, n_comp, smem, st)
-                                  : launch_gram<COARSE, MODE, 2, 8, 4>(a, grid, n_comp, smem, st);
-    }
-    return a.plan.gs == 1 ? launch_gram<COARSE, MODE, 1, 16, 2>(a, grid, n_comp, smem, st)
-                          : launch_gram<COARSE, MODE, 2, 16, 2>(a, grid, n_comp, smem, st);
+int launch_gram_gs(const GramArgs& a, int grid, int n_comp, size_t smem, cudaStream_t st) {
+    const int nb = a.plan.nb;
+    if (nb <= 4) return launch_gram<COARSE, MODE, 1, kLDSmall>(a, grid, n_comp, smem, st);
+    if (nb <= 5) return launch_gram<COARSE, MODE, 1, kLDMid>(a, grid, n_comp, smem, st);
+    if (nb <= 7) return launch_gram<COARSE, MODE, 2, kLDMid>(a, grid, n_comp, smem, st);
+    return launch_gram<COARSE, MODE, 2, kLDWide>(a, grid, n_comp, smem, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -958,32 +970,24 @@ extern "C" int mlmcb200_gram_accumulate_comp(const mlmcb200_basis_t* basis, cons
     a.stride_m = stride_m;
     a.valid = valid;
     size_t smem = 0;
-    // MLMCB200_GRAM_2CTA=1: the sums-only modes as two 8-warp CTAs per SM on 64-sample tiles (one CTA's produce phase and
-    // barrier waits overlap the other's DMMA stream).  It paid at R = 100 (+4 %) while every lane computed one
-    // recurrence; with the S / D tiles (one thread, both recurrences of a sample) the 16-warp CTA on 128-sample tiles
-    // is faster at every size (R = 100: 6.14 vs 6.29 ms per 8e6 samples), so it is off by default.
-    static int two_env = -2;
-    if (two_env == -2) {
-        const char* e = getenv("MLMCB200_GRAM_2CTA");
-        two_env = e ? atoi(e) : 0;
-    }
-    const bool two_ctas = two_env > 0 && (mode == 1 || !want_var);
     // DMMAs per diagonal / off-diagonal block of the mode (slot_mma)
     int cd = 1, co = 1;
     if (mode == 0 && has_coarse) {
         cd = want_var ? 3 : 1;
         co = want_var ? 5 : 2;
     }
-    if (two_ctas) {
-        if (make_plan(basis->size, 8, 4, &a.plan, &smem, kLD, 64, 111u * 1024u, cd, co) != 0) return -1;
-    } else {
-        if (make_plan(basis->size, kWarps, 2, &a.plan, &smem, kLD, 128, 216u * 1024u, cd, co) != 0) return -1;
-    }
+    // the tile holds S and D (fine + coarse covariance) or ONE array (level 0: phi(f); difference Gram: D): a single
+    // array takes twice the samples.  One sample per thread and tile at most.
+    const int n_arrays = (has_coarse && mode == 0) ? 2 : 1;
+    const int nb_blocks = (basis->size + 7) / 8;
+    if (make_plan(basis->size, kWarps, 2, &a.plan, &smem, gram_ld(nb_blocks), kThreadsGram, 216u * 1024u, cd, co,
+                  n_arrays) != 0)
+        return -1;
     const int64_t R2 = (int64_t)basis->size * basis->size;
     const int64_t stride = 2 + 2 * R2;
     const int64_t tiles = (n + a.plan.ns - 1) / a.plan.ns;
     // CTAs per component: the SMs are shared out between the components of a launch
-    const int sms = sm_count() * (two_ctas ? 2 : 1);
+    const int sms = sm_count();
     int grid = n_comp == 1 ? sms : (sms + n_comp - 1) / n_comp;
     if (tiles < grid) grid = (int)tiles;
     const int64_t fit = workspace_bytes / ((int64_t)grid * stride * 8);
@@ -1001,13 +1005,11 @@ extern "C" int mlmcb200_gram_accumulate_comp(const mlmcb200_basis_t* basis, cons
         a.pairs = pairs + (int64_t)comp0 * stride_m;
         int rc;
         if (mode == 1)
-            rc = launch_gram_gs<true, 2>(a, grid, nc, smem, st, two_ctas);
+            rc = launch_gram_gs<true, 2>(a, grid, nc, smem, st);
         else if (want_var)
-            rc = has_coarse ? launch_gram_gs<true, 1>(a, grid, nc, smem, st, false)
-                            : launch_gram_gs<false, 1>(a, grid, nc, smem, st, false);
+            rc = has_coarse ? launch_gram_gs<true, 1>(a, grid, nc, smem, st) : launch_gram_gs<false, 1>(a, grid, nc, smem, st);
         else
-            rc = has_coarse ? launch_gram_gs<true, 0>(a, grid, nc, smem, st, two_ctas)
-                            : launch_gram_gs<false, 0>(a, grid, nc, smem, st, two_ctas);
+            rc = has_coarse ? launch_gram_gs<true, 0>(a, grid, nc, smem, st) : launch_gram_gs<false, 0>(a, grid, nc, smem, st);
         if (rc != 0) return rc;
         reduce_partials_sym_kernel<<<dim3((unsigned)((len * 32 + 255) / 256), (unsigned)nc), 256, 0, st>>>(
             a.partial, grid, stride, basis->size, n_mats, acc, comp0, n_comp);
