@@ -200,6 +200,75 @@ __device__ __forceinline__ void write_rows_sd(const mlmcb200_basis_t& b, double 
     }
 }
 
+// Coefficients of TWO steps of the monic Legendre recurrence at once (gen_tables.py):
+//     W_j = (t^2 - A_j) W_{j-2} - B_j W_{j-4}
+// The even and the odd moments of a sample are then independent chains, and the producers of a tile split every sample
+// over two threads (by parity): twice as many warps advance the tile, which matters because the produce phase is bound
+// by the latency of its dependent FP64 chains (one warp per SM sub-partition issued an instruction every ~3.3 cycles),
+// not by the FP64 pipe.
+static __constant__ double kLegA2[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_A2_INIT;
+static __constant__ double kLegB2[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_B2_INIT;
+
+// Moments PARITY, PARITY + 2, ... of one sample (Legendre, monic W_j): rows S / D (COARSE), D alone (ONLY_D) or phi(f).
+// PARITY is a template parameter, the stores walk their own pointers and the caller reaches this code through
+// warp-uniform branches only, so that the moment index j depends on nothing but constants and kernel parameters: the
+// compiler keeps it -- and the coefficients it fetches -- in UNIFORM registers (ULDC instead of an indexed LDC per
+// coefficient through the MIO queue, which the stores need).  tf = tc = 0 for a dropped sample.
+template <bool COARSE, bool ONLY_D, int PARITY>
+__device__ __forceinline__ void write_rows_parity(int R, double tf, double tc, bool good, double* row_s, double* row_d,
+                                                  int r_pad) {
+#define MB_PUT(OFF, F, C)                                   \
+    {                                                       \
+        if (!COARSE) ps[OFF] = (F);                         \
+        else {                                              \
+            if (!ONLY_D) ps[OFF] = (F) + (C);               \
+            pd[OFF] = (F) - (C);                            \
+        }                                                   \
+    }
+    double* ps = row_s + PARITY;
+    double* pd = row_d + PARITY;
+    if (PARITY >= R) {                                      // uniform: a basis of one function has no odd moments
+        for (int i = PARITY; i < r_pad; i += 2, ps += 2, pd += 2) MB_PUT(0, 0.0, 0.0)
+        return;
+    }
+    // A dropped sample starts from W = 0 (t = 0) and so produces exact zeros: no thread-dependent branch around the
+    // loop, which therefore runs converged and may use the uniform datapath.
+    const double uf = tf * tf, uc = tc * tc;
+    double f0 = 0.0, c0 = 0.0;                              // W_{j-4}
+    double f1 = good ? (PARITY ? tf : 1.0) : 0.0, c1 = good ? (PARITY ? tc : 1.0) : 0.0;   // W_{j-2}
+    MB_PUT(0, f1, c1)
+    ps += 2;
+    pd += 2;
+    int j = PARITY + 2;
+    for (; j + 2 < R; j += 4, ps += 4, pd += 4) {           // two steps per iteration
+        const double a0 = kLegA2[j], b0 = kLegB2[j], a1 = kLegA2[j + 2], b1 = kLegB2[j + 2];
+        const double qf0 = fma(uf - a0, f1, -(b0 * f0));
+        const double qf1 = fma(uf - a1, qf0, -(b1 * f1));
+        double qc0 = 0.0, qc1 = 0.0;
+        if (COARSE) {
+            qc0 = fma(uc - a0, c1, -(b0 * c0));
+            qc1 = fma(uc - a1, qc0, -(b1 * c1));
+        }
+        MB_PUT(0, qf0, qc0)
+        MB_PUT(2, qf1, qc1)
+        f0 = qf0;
+        f1 = qf1;
+        c0 = qc0;
+        c1 = qc1;
+    }
+    if (j < R) {
+        const double a0 = kLegA2[j], b0 = kLegB2[j];
+        const double qf = fma(uf - a0, f1, -(b0 * f0));
+        const double qc = COARSE ? fma(uc - a0, c1, -(b0 * c0)) : 0.0;
+        MB_PUT(0, qf, qc)
+        j += 2;
+        ps += 2;
+        pd += 2;
+    }
+    for (; j < r_pad; j += 2, ps += 2, pd += 2) MB_PUT(0, 0.0, 0.0)
+#undef MB_PUT
+}
+
 // All DMMAs of one task for one 4-sample step.  MASK = the 8x8 blocks of the GS x GS group this slot owns
 // (bit u*GS+v).  Products into the same accumulator are issued in separate passes so that consecutive DMMAs are
 // independent; only the fragments the mask needs are loaded.
@@ -373,11 +442,19 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2) gram_kernel(c
     // producing thread.  The raw values of an item are FETCHED one tile ahead (registers), so the DRAM latency hides
     // behind the contraction of the current tile.
     // A sample the mask of a vector quantity drops is fetched as NaN: the domain test below then drops it here too.
+    // Legendre: item = (sample, parity of the moments) whenever the CTA has two threads per sample of the tile -- threads
+    // [0, NS) take the even moments, [NS, 2 NS) the odd ones (write_rows_parity).
     const double* const pairs = a.pairs + (int64_t)blockIdx.y * a.stride_m;
+    const bool split = a.basis.kind == MLMCB200_LEGENDRE && 2 * NS <= WARPS * 32 && (NS & 31) == 0;
+    const int n_items = split ? 2 * NS : NS;
+    // warp index as a value the compiler knows to be warp-uniform (shuffle from lane 0): the branches on it below are
+    // uniform, the code behind them runs converged
+    const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int parity_u = (split && warp_u >= (NS >> 5)) ? 1 : 0;
     auto fetch = [&](int64_t tile, int item, double& xf, double& xc) {
         xf = xc = qnan;
-        if (item < NS && tile < n_tiles) {
-            const int64_t n = tile * NS + item;
+        if (item < n_items && tile < n_tiles) {
+            const int64_t n = tile * NS + (item >= NS ? item - NS : item);
             if (n < a.n && (a.valid == nullptr || a.valid[n])) {
                 xf = __ldcs(pairs + n * a.stride_n);
                 if (COARSE) xc = __ldcs(pairs + n * a.stride_n + a.stride_side);
@@ -385,8 +462,12 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2) gram_kernel(c
         }
     };
     auto generate = [&](int64_t tile, double* tile_base, int item, double xf, double xc) {
-        if (item >= NS) return;
-        const int s = item;
+        if (split) {
+            if (warp_u >= (NS >> 4)) return;                 // uniform: 2 NS / 32 producing warps
+        } else if (item >= NS) {
+            return;
+        }
+        const int s = item - parity_u * NS;
         const int64_t n = tile * NS + s;
         // rows are skewed by (s / 4) % 4 doubles: the 16 lanes of a half-warp then store to 16 distinct 8-byte
         // bank pairs (row stride LD = 4 mod 8 alone gives only 4), and a k-step's 4 rows share one skew
@@ -400,13 +481,24 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2) gram_kernel(c
                 tc = a.basis.kind == MLMCB200_RAW ? xc : map_to_ref(a.basis, xc);
                 good = good && moments_finite(a.basis, tc);
             }
-            cnt_ok += good ? 1u : 0u;
-            cnt_rm += good ? 0u : 1u;
+            if (!parity_u) {
+                cnt_ok += good ? 1u : 0u;
+                cnt_rm += good ? 0u : 1u;
+            }
         }
-        if (COARSE)
-            write_rows_sd<ONLY_D>(a.basis, tf, tc, good, row, ONLY_D ? row : row + (size_t)NS * LD, r_pad);
-        else
+        double* const row2 = (COARSE && !ONLY_D) ? row + (size_t)NS * LD : row;
+        if (split) {
+            tf = good ? tf : 0.0;
+            tc = good ? tc : 0.0;
+            if (parity_u)
+                write_rows_parity<COARSE, ONLY_D, 1>(R, tf, tc, good, row, row2, r_pad);
+            else
+                write_rows_parity<COARSE, ONLY_D, 0>(R, tf, tc, good, row, row2, r_pad);
+        } else if (COARSE) {
+            write_rows_sd<ONLY_D>(a.basis, tf, tc, good, row, row2, r_pad);
+        } else {
             write_row(a.basis, tf, good, row, r_pad);
+        }
     };
     auto consume = [&](const double* tile_base) {
         const double* phi_f = tile_base + frag_off;
@@ -522,9 +614,19 @@ __global__ void reduce_partials_sym_kernel(const double* __restrict__ partial, i
         return;
     }
     double s1 = 0.0, s2 = 0.0;
-    for (int b = lane; b < n_partials; b += 32) {
-        s1 += partial[(int64_t)b * stride + j];
-        s2 += partial[(int64_t)b * stride + jt];
+    for (int b0 = lane; b0 < n_partials; b0 += 32 * 5) {      // batches of independent loads, added in index order
+        double v1[5], v2[5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            const int b = b0 + 32 * u;
+            v1[u] = b < n_partials ? partial[(int64_t)b * stride + j] : 0.0;
+            v2[u] = b < n_partials ? partial[(int64_t)b * stride + jt] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            s1 += v1[u];
+            s2 += v2[u];
+        }
     }
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);

@@ -582,8 +582,19 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
         const int64_t j = gid >> 5;
         const int lane = threadIdx.x & 31;
         if (j >= len) return;
+        // the loads of a lane are independent: batches of 12 are issued together (one L2 round trip per batch instead
+        // of one per partial -- a one-wave launch has ~300 partials), then added in index order
         double s = 0.0;
-        for (int b = lane; b < n_partials; b += 32) s += partial[(int64_t)b * stride + j];
+        for (int b0 = lane; b0 < n_partials; b0 += 32 * 12) {
+            double v[12];
+#pragma unroll
+            for (int u = 0; u < 12; ++u) {
+                const int b = b0 + 32 * u;
+                v[u] = b < n_partials ? partial[(int64_t)b * stride + j] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 12; ++u) s += v[u];
+        }
         s = warp_sum(s);
         if (lane == 0) acc[j] += s;
     } else {
