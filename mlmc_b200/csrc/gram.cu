@@ -293,13 +293,24 @@ __device__ __forceinline__ void slot_mma(double (&am)[GS][GS][2], double (&av)[G
             row_used = row_used || ((MASK >> (u * GS + v)) & 1);
             col_used = col_used || ((MASK >> (v * GS + u)) & 1);
         }
-        if (row_used) {
-            if (!(COARSE && MODE == 2)) sr[u] = ps[off_r[u]];
-            if (COARSE) dr[u] = pd[off_r[u]];
-        }
-        if (col_used) {
-            if (!(COARSE && MODE == 2)) scol[u] = ps[off_c[u]];
-            if (COARSE) dcol[u] = pd[off_c[u]];
+        if (DIAG) {
+            // a task on the block diagonal has the same moment blocks on both sides: one set of fragments (and, with the
+            // sums of squares, one set of element-wise products) serves rows and columns
+            if (row_used || col_used) {
+                if (!(COARSE && MODE == 2)) sr[u] = ps[off_r[u]];
+                if (COARSE) dr[u] = pd[off_r[u]];
+            }
+            scol[u] = sr[u];
+            dcol[u] = dr[u];
+        } else {
+            if (row_used) {
+                if (!(COARSE && MODE == 2)) sr[u] = ps[off_r[u]];
+                if (COARSE) dr[u] = pd[off_r[u]];
+            }
+            if (col_used) {
+                if (!(COARSE && MODE == 2)) scol[u] = ps[off_c[u]];
+                if (COARSE) dcol[u] = pd[off_c[u]];
+            }
         }
     }
 #define MB_FOR_BLOCKS(COND, BODY)                                               \
@@ -324,9 +335,9 @@ __device__ __forceinline__ void slot_mma(double (&am)[GS][GS][2], double (&av)[G
                 ar[u] = dr[u] * dr[u];
                 br[u] = sr[u] * sr[u];
                 er[u] = dr[u] * sr[u];
-                ac[u] = dcol[u] * dcol[u];
-                bc[u] = scol[u] * scol[u];
-                ec[u] = dcol[u] * scol[u];
+                ac[u] = DIAG ? ar[u] : dcol[u] * dcol[u];
+                bc[u] = DIAG ? br[u] : scol[u] * scol[u];
+                ec[u] = DIAG ? er[u] : dcol[u] * scol[u];
             }
             MB_FOR_BLOCKS(true, dmma(av[u][v][0], av[u][v][1], ar[u], bc[v]);)
             MB_FOR_BLOCKS(MB_OFFDIAG, dmma(av[u][v][0], av[u][v][1], br[u], ac[v]);)
@@ -1090,7 +1101,8 @@ extern "C" int mlmcb200_gram_accumulate_comp(const mlmcb200_basis_t* basis, cons
     const int64_t tiles = (n + a.plan.ns - 1) / a.plan.ns;
     // CTAs per component: the SMs are shared out between the components of a launch
     const int sms = sm_count();
-    int grid = n_comp == 1 ? sms : (sms + n_comp - 1) / n_comp;
+    int grid = sms / n_comp;                          // whole waves: n_comp * grid <= SMs (one CTA per SM)
+    if (grid < 1) grid = 1;
     if (tiles < grid) grid = (int)tiles;
     const int64_t fit = workspace_bytes / ((int64_t)grid * stride * 8);
     MB_REQUIRE(fit >= 1, "gram_accumulate: workspace too small");

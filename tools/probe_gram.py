@@ -50,3 +50,21 @@ for R in (25, 50, 100):
         us = n * useful / (ms * 1e-3) / 1e12
         print("R=%3d %-13s %8.3f ms  executed %5.2f TFLOP/s (%.2f)  useful %5.2f TFLOP/s (%.2f)" % (
             R, name, ms, ex, ex / peak, us, us / peak), flush=True)
+
+# vector quantity: all components in one launch (mlmcb200_gram_accumulate_comp) against one scalar launch per component
+for M, R, nv in ((8, 25, 1_000_000), (64, 25, 100_000), (1000, 10, 4096)):
+    basis = nat.make_basis(nat.LEGENDRE, R, (-3.72, 3.72), (-1.0, 1.0))
+    rows_v = torch.randn(nv, 2, M, generator=g, device=dev, dtype=torch.float64)
+    rows_v[:, 1] = rows_v[:, 0] + 0.1 * rows_v[:, 1]
+    xv = rows_v.permute(2, 0, 1)
+    acc_v = nat.LevelAccumulator(1, M * R * R, dev)
+    acc_s = nat.LevelAccumulator(1, R * R, dev)
+    valid = nat.sample_mask(basis, xv)
+    ms_vec = timed(lambda: nat.gram_accumulate(basis, xv, acc_v.level(0), mode=0, want_var=True, valid=valid))
+
+    def one_by_one():
+        for m in range(M):
+            nat.gram_accumulate(basis, xv[m:m + 1], acc_s.level(0), mode=0, want_var=True)
+    ms_sep = timed(one_by_one)
+    print("vector M=%4d R=%2d n=%7d sums+squares: one launch %8.3f ms, %d scalar launches %8.3f ms" % (
+        M, R, nv, ms_vec, M, ms_sep), flush=True)
