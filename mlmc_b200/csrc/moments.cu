@@ -90,11 +90,14 @@ __device__ __forceinline__ void accumulate(double* __restrict__ col, int sq_off,
     }
 }
 
-// raw (fine, coarse) values of the S samples of one tile owned by this thread; out-of-range samples read NaN
+// raw (fine, coarse) values of the S samples of one tile owned by this thread; out-of-range samples read NaN.
+// vmask: bit s = the caller's sample mask (a.valid) of sample s, fetched here -- one tile ahead, with the values -- so
+// that the classification of the tile does not wait for it.
 template <bool COARSE, int S>
 __device__ __forceinline__ void load_tile(const MomentsArgs& a, const double* base_f, const int32_t* idx, int64_t n0,
-                                          int TN, bool active, double (&xf)[S], double (&xc)[S]) {
+                                          int TN, bool active, double (&xf)[S], double (&xc)[S], unsigned& vmask) {
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    vmask = 0;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
         int64_t n = n0 + (int64_t)s * TN;
@@ -102,6 +105,7 @@ __device__ __forceinline__ void load_tile(const MomentsArgs& a, const double* ba
         xc[s] = qnan;
         if (active && n < a.n) {
             if (idx != nullptr) n = __ldg(idx + n);                 // re-sampled row
+            if (a.valid != nullptr) vmask |= (a.valid[n] != 0 ? 1u : 0u) << s;
             if (COARSE && a.vec2) {
                 const double2 v = __ldcs(reinterpret_cast<const double2*>(a.pairs) + n);
                 xf[s] = v.x;
@@ -170,6 +174,7 @@ moments_acc_kernel(const MomentsArgs a) {
 
     // software pipeline: the raw values of the NEXT tile are in flight while the current tile is reduced
     double xf[S], xc[S];
+    unsigned vmask = 0;                                      // generic path: the external sample mask of the tile in flight
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     // FAST addressing: sample (tile, s, tid) = pairs[(tile * S * T + s * T + tid) * stride_n (+ 1 for the coarse half)]
     auto load_fast = [&](int64_t tile) {
@@ -238,7 +243,7 @@ moments_acc_kernel(const MomentsArgs a) {
     } else if (FAST) {
         load_fast(blockIdx.y);
     } else {
-        load_tile<COARSE, S>(a, base_f, idx, (int64_t)blockIdx.y * tile_n + tn, TN, active, xf, xc);
+        load_tile<COARSE, S>(a, base_f, idx, (int64_t)blockIdx.y * tile_n + tn, TN, active, xf, xc, vmask);
     }
 
     int64_t k_tile = 0;
@@ -333,7 +338,7 @@ moments_acc_kernel(const MomentsArgs a) {
                     tc[s] = COARSE ? map_to_ref_t<LOG>(a.basis, xc[s]) : 0.0;
                 }
                 if (a.valid != nullptr) {
-                    own[s] = in && a.valid[idx != nullptr && in ? (int64_t)__ldg(idx + n) : n] != 0;
+                    own[s] = in && ((vmask >> s) & 1u);
                 } else {
                     own[s] = in && moments_finite(a.basis, tf[s]) && (!COARSE || moments_finite(a.basis, tc[s]));
                 }
@@ -371,7 +376,7 @@ moments_acc_kernel(const MomentsArgs a) {
                 ok[s] = good;
             }
             if (tile + gridDim.y < n_tiles)
-                load_tile<COARSE, S>(a, base_f, idx, (tile + gridDim.y) * tile_n + tn, TN, active, xf, xc);
+                load_tile<COARSE, S>(a, base_f, idx, (tile + gridDim.y) * tile_n + tn, TN, active, xf, xc, vmask);
         }
 
         double* col = col0;                                      // column entry of the next moment to reduce

@@ -633,3 +633,35 @@ def test_density_eval_matches_oracle(kind, size, n_coef):
         assert np.max(np.abs(np.log(got[inside]) - np.log(want[inside]))) <= tol
         if scale > 1.0:
             assert (got[inside] == np.exp(200.0)).any() or (got[inside] == np.exp(-200.0)).any()
+
+
+@pytest.mark.parametrize("R", [1, 2, 8, 9, 32, 33, 40, 41, 56, 57, 96, 104])
+def test_covariance_block_boundaries_all_modes(R):
+    """Every tile width (<= 4 / 7 / 13 moment blocks), group size and producer variant of the DMMA kernel at the sizes where
+    they change over: sums, sums + squares, level 0, Gram of the differences; several ragged tiles per launch."""
+    rng = np.random.default_rng(300 + R)
+    n0, n1 = 1100, 777
+    rows0 = orc.synth_level_rows(rng.normal(size=n0), 0.3, None)
+    rows1 = orc.synth_level_rows(rng.normal(size=n1), 0.1, 0.3)
+    rows1[5, 1, 0] = 40.0                                          # coarse value outside the domain: sample dropped
+    b = orc.Basis("legendre", R, (-3.3, 3.1))
+    want = orc.estimate_covariance([rows0, rows1], b, chunk_rows=512)
+    res = run_gram(to_struct(b), [rows0, rows1], True)
+    assert np.array_equal(res["n"], want.n_samples) and np.array_equal(res["n_rm"], want.n_rm_samples)
+    rel_close(res["l_means"], want.l_means, rtol=1e-8, atol_scale=1e-13, per_level=True)
+    rel_close(res["l_vars"], want.l_vars, rtol=1e-8, atol_scale=1e-12, per_level=True)
+    sums_only = run_gram(to_struct(b), [rows0, rows1], False)
+    rel_close(sums_only["l_means"], want.l_means, rtol=1e-8, atol_scale=1e-13, per_level=True)
+    m = sums_only["l_means"].reshape(2, R, R)
+    assert np.array_equal(m, np.swapaxes(m, 1, 2))
+    # Gram of the differences (single-array tile)
+    phi = orc.basis_eval(b, rows1[:, :, 0])
+    good = ~np.isnan(phi).any(axis=(1, 2))
+    d = phi[good, 0] - phi[good, 1]
+    nat = native()
+    acc = nat.LevelAccumulator(1, R * R, dev())
+    nat.gram_accumulate(to_struct(b), torch.from_numpy(rows1).to(dev()).permute(2, 0, 1), acc.level(0), mode=1,
+                        want_var=False)
+    a = acc.acc.cpu().numpy()[0]
+    assert a[0] == good.sum() and a[1] == (~good).sum()
+    rel_close(a[2:2 + R * R].reshape(R, R), d.T @ d, rtol=1e-8, atol_scale=1e-13)
