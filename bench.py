@@ -974,6 +974,13 @@ def main():
         run_reference_arm(args)
     else:
         run_gpu_arm(args)
+        try:                                        # leave the process group cleanly (NCCL warns otherwise)
+            import torch.distributed as td
+            if td.is_available() and td.is_initialized():
+                td.barrier()
+                td.destroy_process_group()
+        except Exception:
+            pass
 
 
 if __name__ == "__main__":

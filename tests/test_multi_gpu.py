@@ -66,6 +66,16 @@ def _worker(rank, world, port, out_dir):
         qm4 = qe.estimate_mean(qe.moments(value, Legendre(12, tuple(g["A_domain"]))))       # next epoch works again
         peer.update(s_l_means=qm3.l_means, s_l_vars=qm3.l_vars, s_n=qm3.n_samples, s_fallbacks=dist.peer_fallbacks(),
                     s2_l_means=qm4.l_means, s2_fallbacks=dist.peer_fallbacks())
+    # vector quantity (6 components, 4 levels): fused covariance and transformed moments, rows sharded over the ranks
+    levels_c = [g["C_rows%d" % l] for l in range(4)]
+    spec_c = [QuantitySpec(name="v", unit="", shape=(6, 1), times=[0.0], locations=["0"])]
+    storage_c = Memory.from_arrays(levels_c, result_format=spec_c)
+    vec = make_root_quantity(storage_c, spec_c)["v"][0.0]["0"]
+    vcov = qe.estimate_mean(qe.covariance(vec, Legendre(3, tuple(g["C_domain"]))))
+    from mlmc_b200.moments import TransformedMoments
+    l_mat = np.array([[1.0, 0.0, 0.0, 0.0, 0.0], [0.3, -1.2, 0.5, 0.0, 0.1], [0.0, 0.4, 0.0, -0.7, 2.0]])
+    vtm = qe.estimate_mean(qe.moments(vec, TransformedMoments(Legendre(5, tuple(g["C_domain"])), l_mat)))
+    peer.update(v_cov=vcov.mean, v_cov_var=vcov.var, v_tm_mean=vtm.mean, v_tm_var=vtm.var)
     # linearised covariance means (moment sums of the 2R-1 basis, all-reduce, C applied once)
     lin = qe.estimate_mean(qe.covariance(value, Legendre(8, tuple(g["A_domain"]))), variance=False)
     peer["lin_cov"] = lin.mean
@@ -94,6 +104,15 @@ def test_two_gpu_sharded_estimate(tmp_path, golden):
         assert np.allclose(out["cov"], g["A_cov_mean"], rtol=1e-8, atol=1e-14)
         assert np.allclose(out["cov_var"], g["A_cov_var"], rtol=1e-8, atol=1e-16)
         assert np.allclose(out["lin_cov"], g["A_cov_mean"], rtol=1e-8, atol=1e-14)
+        assert np.allclose(out["v_cov"], g["C_cov_mean"], rtol=1e-8, atol=1e-14)
+        assert np.allclose(out["v_cov_var"], g["C_cov_var"], rtol=1e-8, atol=1e-16)
+        # transformed moments of the vector quantity against the oracle on all rows
+        from oracle import mlmc_oracle as orc
+        l_mat = np.array([[1.0, 0.0, 0.0, 0.0, 0.0], [0.3, -1.2, 0.5, 0.0, 0.1], [0.0, 0.4, 0.0, -0.7, 2.0]])
+        want = orc.estimate_moments([g["C_rows%d" % l] for l in range(4)],
+                                    orc.Basis("legendre", 5, tuple(g["C_domain"]), matrix=l_mat))
+        assert np.allclose(np.ravel(out["v_tm_mean"]), want.mean, rtol=1e-9, atol=1e-14)
+        assert np.allclose(np.ravel(out["v_tm_var"]), want.var, rtol=1e-8, atol=1e-16)
     a, b = (np.load(os.path.join(str(tmp_path), "r%d.npz" % r)) for r in range(2))
     assert a["bs_l_means"].shape == (5, 3, 6) and np.array_equal(a["bs_l_means"], b["bs_l_means"])
     assert np.array_equal(a["bs_n"], b["bs_n"]) and np.all(a["bs_n"].sum(axis=1) > 0)
