@@ -23,7 +23,6 @@ namespace {
 constexpr int kWarps = 16;
 constexpr int kThreadsGram = kWarps * 32;
 constexpr int kMaxSlots = 4;     // tasks per warp (array bound; the plans use 2 ... 4)
-constexpr int kMaxGroup = 2;     // blocks per task side
 // Leading dimension of the covariance tiles: a compile-time constant (template parameter; 4 mod 8, >= 8 nb + 3 for the
 // row skew) so that every fragment address of a tile is "slot base register + immediate".  Three sizes: up to 4 / 7 / 13
 // blocks of 8 moments -- a narrower tile holds more samples (128 -> 224 -> 384 with two arrays), which spreads the

@@ -32,7 +32,7 @@ def timed(fn, reps=3):
     return best
 
 
-print("n = %d, DMMA peak %.2f TFLOP/s, MLMCB200_GRAM_2CTA=%s" % (n, peak, os.environ.get("MLMCB200_GRAM_2CTA", "default")))
+print("n = %d, DMMA peak %.2f TFLOP/s" % (n, peak))
 for R in (25, 50, 100):
     basis = nat.make_basis(nat.LEGENDRE, R, (-3.72, 3.72), (-1.0, 1.0))
     acc = nat.LevelAccumulator(1, R * R, dev)
