@@ -753,12 +753,12 @@ int make_plan_uncached(int R, int n_warps, int n_slots, GramPlan* pl, size_t* sm
     const int n_bins = n_warps < 4 ? n_warps : 4, cap = (n_warps / n_bins) * n_slots;
     const int ideal = (total + n_bins - 1) / n_bins;
     PlanTask best[kWarps * kMaxSlots];
-    int best_bin[kWarps * kMaxSlots], best_n = 0, best_worst = -1;
-    for (int sa = 0; sa <= (gs == 2 ? n_full : 0) && sa <= 4; ++sa)
+    int best_bin[kWarps * kMaxSlots], best_n = 0, best_worst = -1, best_warp = 0;
+    (void)ideal;
+    for (int sa = 0; sa <= (gs == 2 ? n_full : 0) && sa <= 8; ++sa)
         for (int sb = 0; sb <= (gs == 2 ? n_tri : 0) && sb <= 6; ++sb)
             for (int sc = 0; sc <= (gs == 2 ? n_col : 0) && sc <= 6; ++sc) {
                 if (n_nat + sa + sb + sc > kMaxTasks) continue;
-                if (best_worst == ideal && n_nat + sa + sb + sc >= best_n) continue;
                 PlanTask pc[kWarps * kMaxSlots];
                 int n = 0, ua = 0, ub = 0, uc = 0;
                 for (int i = 0; i < n_nat; ++i) {
@@ -774,8 +774,24 @@ int make_plan_uncached(int R, int n_warps, int n_slots, GramPlan* pl, size_t* sm
                 int bin_of[kWarps * kMaxSlots];
                 const int worst = pack_bins(pc, n, n_bins, cap, bin_of);
                 if (worst < 0) continue;
-                if (best_worst < 0 || worst < best_worst || (worst == best_worst && n < best_n)) {
+                // second criterion: the heaviest WARP (a sub-partition whose load sits in one or two warps leaves the
+                // pipe to a lone warp for part of the tile, and a lone warp does not hide its own latencies)
+                int warp_worst = 0;
+                bool fits = true;
+                for (int b = 0; b < n_bins && fits; ++b) {
+                    PlanTask mine[kWarps * kMaxSlots];
+                    int m = 0, warp_of[kWarps * kMaxSlots];
+                    for (int i = 0; i < n; ++i)
+                        if (bin_of[i] == b) mine[m++] = pc[i];
+                    const int ww = pack_bins(mine, m, n_warps / n_bins, n_slots, warp_of);
+                    fits = ww >= 0;
+                    warp_worst = ww > warp_worst ? ww : warp_worst;
+                }
+                if (!fits) continue;
+                if (best_worst < 0 || worst < best_worst || (worst == best_worst && warp_worst < best_warp) ||
+                    (worst == best_worst && warp_worst == best_warp && n < best_n)) {
                     best_worst = worst;
+                    best_warp = warp_worst;
                     best_n = n;
                     for (int i = 0; i < n; ++i) { best[i] = pc[i]; best_bin[i] = bin_of[i]; }
                 }
