@@ -41,6 +41,15 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert lib.mlmcb200_moments_workspace_bytes(50, 1) > 0
     assert lib.mlmcb200_moments_workspace_bytes(5000, 1) < 0       # does not fit shared memory
     assert lib.mlmcb200_gram_workspace_bytes(100) > 0
+    assert lib.mlmcb200_gram_workspace_bytes_comp(25, 300) > lib.mlmcb200_gram_workspace_bytes_comp(25, 1) > 0
+    good = _native.make_basis(_native.LEGENDRE, 7, (2.0, 6.0), (-1.0, 1.0))
+    one = ctypes.c_void_p(8)                                       # never dereferenced: the argument checks come first
+    rc = lib.mlmcb200_gram_accumulate_comp(ctypes.byref(good), one, 10, 3, 6, 3, 1, 1, None, 0, 1, one, one, 1 << 20, None)
+    assert rc < 0 and b"sample mask" in lib.mlmcb200_last_error()
+    rc = lib.mlmcb200_gram_accumulate_comp(ctypes.byref(good), one, 10, 1, 2, 1, 0, 0, None, 1, 0, one, one, 1 << 20, None)
+    assert rc < 0 and b"needs a coarse side" in lib.mlmcb200_last_error()
+    rc = lib.mlmcb200_density_eval(ctypes.byref(good), one, 5, one, 8, one, None)
+    assert rc < 0 and b"n_coef" in lib.mlmcb200_last_error()
 
 
 def test_sass_contains_fp64_tensor_and_no_legacy_half_mma():
