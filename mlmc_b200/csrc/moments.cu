@@ -92,7 +92,7 @@ __device__ __forceinline__ void accumulate(double* __restrict__ col, int sq_off,
 
 // raw (fine, coarse) values of the S samples of one tile owned by this thread; out-of-range samples read NaN.
 // vmask: bit s = the caller's sample mask (a.valid) of sample s, fetched here -- one tile ahead, with the values -- so
-// that the classification of the tile does not wait for it.
+// that the classification of the tile does not wait for it; bit 16 + s = sample s exists (in range, active thread).
 template <bool COARSE, int S>
 __device__ __forceinline__ void load_tile(const MomentsArgs& a, const double* base_f, const int32_t* idx, int64_t n0,
                                           int TN, bool active, double (&xf)[S], double (&xc)[S], unsigned& vmask) {
@@ -104,6 +104,7 @@ __device__ __forceinline__ void load_tile(const MomentsArgs& a, const double* ba
         xf[s] = qnan;
         xc[s] = qnan;
         if (active && n < a.n) {
+            vmask |= 0x10000u << s;                                 // bit 16 + s: the sample exists
             if (idx != nullptr) n = __ldg(idx + n);                 // re-sampled row
             if (a.valid != nullptr) vmask |= (a.valid[n] != 0 ? 1u : 0u) << s;
             if (COARSE && a.vec2) {
@@ -323,6 +324,33 @@ moments_acc_kernel(const MomentsArgs a) {
                 }
             }
             if (STAGES == 0 && tile + gridDim.y < n_tiles) load_fast(tile + gridDim.y);
+        } else if (a.valid != nullptr) {
+            // External sample mask (wide vector quantities): a kept sample has every component inside the domain, so
+            // the affine map needs no test and the classification is bit tests and selects -- no branches, no 64-bit
+            // index arithmetic (half of this variant's instructions used to be the generic per-sample tests).
+            const unsigned vm = vmask;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const bool in = (vm >> (16 + s)) & 1u, good = (vm >> s) & 1u;
+                double t_f = xf[s], t_c = xc[s];
+                if (KIND != MLMCB200_RAW) {
+                    const double vf = LOG ? log(t_f) : t_f;
+                    t_f = __dadd_rn(__dmul_rn(__dsub_rn(vf, a.basis.shift), a.basis.scale), a.basis.ref_lo);
+                    if (COARSE) {
+                        const double vc = LOG ? log(t_c) : t_c;
+                        t_c = __dadd_rn(__dmul_rn(__dsub_rn(vc, a.basis.shift), a.basis.scale), a.basis.ref_lo);
+                    }
+                }
+                if (count_here) {
+                    cnt_ok += good ? 1u : 0u;
+                    cnt_rm += (in && !good) ? 1u : 0u;
+                }
+                tf[s] = good ? t_f : 0.0;
+                tc[s] = (COARSE && good) ? t_c : 0.0;
+                ok[s] = good;
+            }
+            if (tile + gridDim.y < n_tiles)
+                load_tile<COARSE, S>(a, base_f, idx, (tile + gridDim.y) * tile_n + tn, TN, active, xf, xc, vmask);
         } else {
             const int64_t n0 = tile * tile_n + tn;
             bool own[S];                                   // this component's verdict on the sample, then the sample's
@@ -337,11 +365,7 @@ moments_acc_kernel(const MomentsArgs a) {
                     tf[s] = map_to_ref_t<LOG>(a.basis, xf[s]);
                     tc[s] = COARSE ? map_to_ref_t<LOG>(a.basis, xc[s]) : 0.0;
                 }
-                if (a.valid != nullptr) {
-                    own[s] = in && ((vmask >> s) & 1u);
-                } else {
-                    own[s] = in && moments_finite(a.basis, tf[s]) && (!COARSE || moments_finite(a.basis, tc[s]));
-                }
+                own[s] = in && moments_finite(a.basis, tf[s]) && (!COARSE || moments_finite(a.basis, tc[s]));
             }
             if (a.fuse_mask) {
                 // mask_nan_samples across the components of a sample: flag per (s, sample lane), double-buffered over
