@@ -80,11 +80,12 @@ __device__ __forceinline__ void accumulate(double* __restrict__ col, int sq_off,
 }
 
 // raw (fine, coarse) values of the S samples of one tile owned by this thread; out-of-range samples read NaN.
-// vmask: bit s = the caller's sample mask (a.valid) of sample s, fetched here -- one tile ahead, with the values -- so
-// that the classification of the tile does not wait for it; bit 16 + s = sample s exists (in range, active thread).
+// vmask: bit 16 + s = sample s exists (in range, active thread); vraw[s] = the caller's sample mask (a.valid) of sample
+// s, fetched here -- one tile ahead, with the values -- and left untouched (testing it here would wait for the load).
 template <bool COARSE, int S>
 __device__ __forceinline__ void load_tile(const MomentsArgs& a, const double* base_f, const int32_t* idx, int64_t n0,
-                                          int TN, bool active, double (&xf)[S], double (&xc)[S], unsigned& vmask) {
+                                          int TN, bool active, double (&xf)[S], double (&xc)[S], unsigned& vmask,
+                                          unsigned char (&vraw)[S]) {
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     vmask = 0;
 #pragma unroll
@@ -92,10 +93,11 @@ __device__ __forceinline__ void load_tile(const MomentsArgs& a, const double* ba
         int64_t n = n0 + (int64_t)s * TN;
         xf[s] = qnan;
         xc[s] = qnan;
+        vraw[s] = 0;
         if (active && n < a.n) {
             vmask |= 0x10000u << s;                                 // bit 16 + s: the sample exists
             if (idx != nullptr) n = __ldg(idx + n);                 // re-sampled row
-            if (a.valid != nullptr) vmask |= (a.valid[n] != 0 ? 1u : 0u) << s;
+            if (a.valid != nullptr) vraw[s] = a.valid[n];
             if (COARSE && a.vec2) {
                 const double2 v = __ldcs(reinterpret_cast<const double2*>(a.pairs) + n);
                 xf[s] = v.x;
@@ -164,7 +166,8 @@ moments_acc_kernel(const MomentsArgs a) {
 
     // software pipeline: the raw values of the NEXT tile are in flight while the current tile is reduced
     double xf[S], xc[S];
-    unsigned vmask = 0;                                      // generic path: the external sample mask of the tile in flight
+    unsigned vmask = 0;                                      // generic path: which samples of the tile in flight exist
+    unsigned char vraw[S];                                   // ... and the caller's sample mask of each
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     // FAST addressing: sample (tile, s, tid) = pairs[(tile * S * T + s * T + tid) * stride_n (+ 1 for the coarse half)]
     auto load_fast = [&](int64_t tile) {
@@ -233,7 +236,7 @@ moments_acc_kernel(const MomentsArgs a) {
     } else if (FAST) {
         load_fast(blockIdx.y);
     } else {
-        load_tile<COARSE, S>(a, base_f, idx, (int64_t)blockIdx.y * tile_n + tn, TN, active, xf, xc, vmask);
+        load_tile<COARSE, S>(a, base_f, idx, (int64_t)blockIdx.y * tile_n + tn, TN, active, xf, xc, vmask, vraw);
     }
 
     int64_t k_tile = 0;
@@ -320,7 +323,7 @@ moments_acc_kernel(const MomentsArgs a) {
             const unsigned vm = vmask;
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-                const bool in = (vm >> (16 + s)) & 1u, good = (vm >> s) & 1u;
+                const bool in = (vm >> (16 + s)) & 1u, good = vraw[s] != 0;
                 double t_f = xf[s], t_c = xc[s];
                 if (KIND != MLMCB200_RAW) {
                     const double vf = LOG ? log(t_f) : t_f;
@@ -339,7 +342,7 @@ moments_acc_kernel(const MomentsArgs a) {
                 ok[s] = good;
             }
             if (tile + gridDim.y < n_tiles)
-                load_tile<COARSE, S>(a, base_f, idx, (tile + gridDim.y) * tile_n + tn, TN, active, xf, xc, vmask);
+                load_tile<COARSE, S>(a, base_f, idx, (tile + gridDim.y) * tile_n + tn, TN, active, xf, xc, vmask, vraw);
         } else {
             const int64_t n0 = tile * tile_n + tn;
             bool own[S];                                   // this component's verdict on the sample, then the sample's
@@ -389,7 +392,7 @@ moments_acc_kernel(const MomentsArgs a) {
                 ok[s] = good;
             }
             if (tile + gridDim.y < n_tiles)
-                load_tile<COARSE, S>(a, base_f, idx, (tile + gridDim.y) * tile_n + tn, TN, active, xf, xc, vmask);
+                load_tile<COARSE, S>(a, base_f, idx, (tile + gridDim.y) * tile_n + tn, TN, active, xf, xc, vmask, vraw);
         }
 
         double* col = col0;                                      // column entry of the next moment to reduce
