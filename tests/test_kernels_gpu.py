@@ -665,3 +665,28 @@ def test_covariance_block_boundaries_all_modes(R):
     a = acc.acc.cpu().numpy()[0]
     assert a[0] == good.sum() and a[1] == (~good).sum()
     rel_close(a[2:2 + R * R].reshape(R, R), d.T @ d, rtol=1e-8, atol_scale=1e-13)
+
+
+@pytest.mark.parametrize("n_comp,has_coarse,log", [(130, True, False), (257, False, False), (64, True, True),
+                                                   (1000, True, False)])
+def test_sample_mask_row_and_generic_kernels_agree(n_comp, has_coarse, log):
+    """mlmcb200_sample_mask: the row-streaming kernel (storage layout, 16-byte loads, one warp per sample) and the generic
+    strided kernel give the mask of mask_nan_samples applied to the moments of all components (quantity_estimate.py:6-14)."""
+    nat = native()
+    rng = np.random.default_rng(n_comp)
+    n = 700
+    rows = rng.uniform(0.5, 2.5, size=(n, 2 if has_coarse else 1, n_comp))
+    bad = rng.choice(n, size=40, replace=False)
+    rows[bad, rng.integers(0, rows.shape[1], 40), rng.integers(0, n_comp, 40)] = \
+        rng.choice([7.0, 0.1, np.nan, np.inf], size=40)
+    b = orc.Basis("legendre", 9, (0.4, 2.6), log=log)
+    t = orc.to_ref_domain(b, rows)
+    want = ~np.isnan(t).any(axis=(1, 2))
+    d = torch.from_numpy(rows).to(dev())
+    x = d.permute(2, 0, 1)                                          # storage layout: row-streaming kernel
+    got_rows = nat.sample_mask(to_struct(b), x).cpu().numpy().astype(bool)
+    wide = torch.zeros((n, rows.shape[1], n_comp + 3), dtype=torch.float64, device=dev())
+    wide[:, :, 1:n_comp + 1] = d                                    # components at an odd offset of wider rows: generic kernel
+    got_generic = nat.sample_mask(to_struct(b), wide[:, :, 1:n_comp + 1].permute(2, 0, 1)).cpu().numpy().astype(bool)
+    assert np.array_equal(got_rows, want) and np.array_equal(got_generic, want)
+    assert 0 < want.sum() < n
