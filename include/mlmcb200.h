@@ -130,6 +130,36 @@ int mlmcb200_moments_accumulate_resampled(const mlmcb200_basis_t* basis, const d
                                           void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * Bootstrap re-sampling of one level in ONE pass over its rows (scalar quantity, Legendre basis of at most
+ * mlmcb200_moments_weighted_max_size() moments): the same replicate loop as above (mlmc/estimator.py:171-218,
+ * mlmc/quantity/quantity.py:307-322), written as the weighted sums
+ *     acc[b][2 + r] += sum_i w_bi d_r(i),   acc[b][2 + R + r] += sum_i w_bi d_r(i)^2,   acc[b][0 / 1] += sum_i w_bi ok_i / rm_i
+ * with w_bi = how many times replicate b drew row i: the dense product W^T [ok | rm | D | D.D] on FP64 tensor-core
+ * tiles (DMMA m8n8k4).  The basis recurrence of a row runs once for ALL replicates and the rows are read once, in
+ * storage order.  The better choice when a replicate draws about as many rows as the level holds (the usual bootstrap);
+ * few draws from many rows stay with mlmcb200_moments_accumulate_resampled.
+ *
+ * mlmcb200_resample_counts: counts[b * counts_stride + i] (device bytes) = multiplicity of row i among the draws
+ * block_cum[b][0] .. block_cum[b][n_blocks] of replicate rep_offset + b -- exactly the draws mlmcb200_resample_indices
+ * lists for the same (seed, stream_id, n_rows, n_blocks, block_cum); block_cum is required here (n_blocks = 1:
+ * {0, n_draws}).  Row blocks hold at most mlmcb200_resample_counts_block_rows() rows (byte counters of a block live in
+ * shared memory); max_draws = the largest block_cum[b][n_blocks], at most 8 n_rows (byte counters).
+ * mlmcb200_moments_accumulate_weighted: pairs = the level's rows in storage order (has_coarse: (fine, coarse) pairs,
+ * stride_n = 2; level 0: stride_n doubles apart); counts rows 16-byte aligned, counts_stride % 16 == 0.  ADDS into
+ * acc + b * acc_rep_stride (layout of mlmcb200_moments_accumulate).
+ */
+int32_t mlmcb200_resample_counts_block_rows(void);
+int mlmcb200_resample_counts(uint64_t seed, uint64_t stream_id, int64_t n_rows, int64_t max_draws, int32_t n_rep,
+                             int32_t rep_offset, int32_t n_blocks, const int64_t* block_cum, uint8_t* counts,
+                             int64_t counts_stride, void* stream);
+int32_t mlmcb200_moments_weighted_max_size(void);
+int64_t mlmcb200_moments_weighted_workspace_bytes(int64_t n_rows, int32_t n_rep);
+int mlmcb200_moments_accumulate_weighted(const mlmcb200_basis_t* basis, const double* pairs, int64_t n_rows,
+                                         int64_t stride_n, int32_t has_coarse, const uint8_t* counts,
+                                         int64_t counts_stride, int32_t n_rep, double* acc, int64_t acc_rep_stride,
+                                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * Level accumulator of the moment-covariance estimate (scalar quantity).  Replaces estimate_mean over a
  * `covariance` quantity: mlmc/quantity/quantity_estimate.py:131-147 + :43-65.  With R = basis->size:
  *     acc[0] = n_samples, acc[1] = n_rm_samples,

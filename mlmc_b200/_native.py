@@ -52,6 +52,13 @@ _SIGNATURES = {
     "mlmcb200_moments_accumulate_resampled": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_i32,
                                                              _c_i64, _c_i64, _c_i64, _c_i32, _c_vp, _c_vp, _c_i64,
                                                              _c_i32, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp]),
+    "mlmcb200_resample_counts_block_rows": (_c_i32, []),
+    "mlmcb200_resample_counts": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, _c_i64, _c_i64, _c_i32, _c_i32,
+                                                _c_i32, _c_vp, _c_vp, _c_i64, _c_vp]),
+    "mlmcb200_moments_weighted_max_size": (_c_i32, []),
+    "mlmcb200_moments_weighted_workspace_bytes": (_c_i64, [_c_i64, _c_i32]),
+    "mlmcb200_moments_accumulate_weighted": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_i64, _c_i32,
+                                                            _c_vp, _c_i64, _c_i32, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp]),
     "mlmcb200_gram_workspace_bytes": (_c_i64, [_c_i32]),
     "mlmcb200_gram_accumulate": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_i64, _c_i64,
                                                 _c_i32, _c_i32, _c_i32, _c_vp, _c_vp, _c_i64, _c_vp]),
@@ -351,6 +358,64 @@ def moments_accumulate_resampled(basis, x, idx, acc_level, valid=None):
                                                          _ptr(acc_level), acc_level.stride(0), _ptr(ws), ws.numel(),
                                                          _stream()),
                "moments_accumulate_resampled")
+    launch_count += 2
+
+
+def resample_counts(seed, stream_id, n_rows, block_cum, max_draws, device, rep_offset=0):
+    """uint8 CUDA tensor [n_rep, stride] (stride = n_rows rounded up to 16): ``counts[b, i]`` = how many times replicate
+    ``rep_offset + b`` drew row i -- the multiplicities of exactly the rows ``resample_indices`` lists for the same
+    arguments.  ``block_cum`` ([n_rep, P + 1] int64 CUDA) is required (one block: ``[[0, k]]``)."""
+    global launch_count
+    _require_cuda(block_cum, "block_cum", torch.int64)
+    if block_cum.dim() != 2 or not block_cum.is_contiguous() or block_cum.shape[1] < 2:
+        raise NativeError("block_cum must be a contiguous [n_rep, n_blocks + 1] tensor")
+    n_rep, n_blocks = block_cum.shape[0], block_cum.shape[1] - 1
+    stride = -(-int(n_rows) // 16) * 16
+    counts = torch.empty((n_rep, stride), dtype=torch.uint8, device=device)
+    with _on_device(counts.device):
+        _check(load().mlmcb200_resample_counts(int(seed) & (2 ** 64 - 1), int(stream_id) & (2 ** 64 - 1), int(n_rows),
+                                               int(max_draws), n_rep, int(rep_offset), n_blocks, _ptr(block_cum),
+                                               _ptr(counts), stride, _stream()), "resample_counts")
+    launch_count += 1
+    return counts
+
+
+def counts_block_rows():
+    return int(load().mlmcb200_resample_counts_block_rows())
+
+
+def weighted_max_size():
+    return int(load().mlmcb200_moments_weighted_max_size())
+
+
+def moments_accumulate_weighted(basis, x, counts, acc_level):
+    """All bootstrap replicates of one level in one pass (scalar quantity, Legendre, size <= ``weighted_max_size()``).
+
+    x [1, n_rows, S] in storage order; counts [B, stride] uint8 (``resample_counts``); acc_level [B, 2 + 2 R] (rows
+    contiguous, any replicate stride).  Adds what ``moments_accumulate_resampled`` adds for the rows behind the counts."""
+    global launch_count
+    M, n_rows, has_coarse, sn, ss, sm = _chunk_layout(x)
+    _require_cuda(acc_level, "acc")
+    _require_cuda(counts, "counts", torch.uint8)
+    if M != 1 or (has_coarse and (sn != 2 or ss != 1)):
+        raise NativeError("moments_accumulate_weighted: scalar quantity in storage order expected")
+    B = counts.shape[0]
+    if counts.dim() != 2 or counts.stride(1) != 1 or counts.shape[1] < n_rows:
+        raise NativeError("counts must be a [n_replicates, >= n_rows] tensor with contiguous rows")
+    if acc_level.dim() != 2 or acc_level.shape != (B, 2 + 2 * basis.size) or acc_level.stride(1) != 1:
+        raise NativeError("replicate accumulators must have shape [%d, %d] with contiguous rows" % (B, 2 + 2 * basis.size))
+    if B == 0 or n_rows == 0:
+        return
+    lib = load()
+    with _on_device(x.device):
+        ws_bytes = lib.mlmcb200_moments_weighted_workspace_bytes(n_rows, B)
+        if ws_bytes < 0:
+            raise NativeError("weighted moments workspace: %s" % lib.mlmcb200_last_error().decode())
+        ws = _workspace(x.device, ws_bytes)
+        _check(lib.mlmcb200_moments_accumulate_weighted(ctypes.byref(basis), _ptr(x), n_rows, sn, has_coarse,
+                                                        _ptr(counts), counts.stride(0), B, _ptr(acc_level),
+                                                        acc_level.stride(0), _ptr(ws), ws.numel(), _stream()),
+               "moments_accumulate_weighted")
     launch_count += 2
 
 

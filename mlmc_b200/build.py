@@ -13,8 +13,8 @@ SRC_DIR = os.path.join(PKG_DIR, "csrc")
 OUT_DIR = os.path.join(PKG_DIR, "_lib")
 LIB_PATH = os.path.join(OUT_DIR, "libmlmcb200.so")
 SOURCES = ["moments_k_legendre_coarse.cu", "moments_k_legendre_level0.cu", "moments_k_monomial.cu", "moments_k_raw_fourier.cu",
-           "gram.cu", "api.cu", "moments.cu", "basis_eval.cu", "maxent.cu", "select.cu", "peer.cu"]
-HEADERS = ["common.cuh", "legendre_tables.inc", "moments_types.cuh", "moments_kernel.cuh",
+           "gram.cu", "api.cu", "moments.cu", "basis_eval.cu", "maxent.cu", "select.cu", "peer.cu", "bootstrap.cu"]
+HEADERS = ["common.cuh", "legendre_tables.inc", "moments_types.cuh", "moments_kernel.cuh", "philox.cuh",
            os.path.join("..", "..", "include", "mlmcb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

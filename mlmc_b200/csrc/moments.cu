@@ -2,6 +2,7 @@
 // The accumulate kernel itself (moments_kernel.cuh) is instantiated per basis family in moments_k_*.cu.
 #include <stdlib.h>
 #include "moments_types.cuh"
+#include "philox.cuh"
 
 namespace mlmcb200 {
 
@@ -46,21 +47,7 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
     }
 }
 
-// ---- row numbers of the bootstrap replicates (counter-based Philox4x32-10: reproducible, no state) ----
-__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-    for (int round = 0; round < 10; ++round) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-        c[0] = hi1 ^ c[1] ^ k0;
-        c[1] = lo1;
-        c[2] = hi0 ^ c[3] ^ k1;
-        c[3] = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-}
-
+// ---- row numbers of the bootstrap replicates (counter-based Philox4x32-10, philox.cuh: reproducible, no state) ----
 // Replicate blockIdx.y, draws 2*g and 2*g+1 of thread g.  Draw j belongs to the row block p with
 // cum[p] <= j < cum[p+1] (block p = rows [p n / P, (p+1) n / P)) and is uniform inside it: floor(r64 * size / 2^64).
 // The Philox counter carries the GLOBAL replicate number (rep_offset + blockIdx.y) and the key only the seed and the

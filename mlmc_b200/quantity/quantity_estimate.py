@@ -22,6 +22,8 @@ anything else                          generic: chunk evaluated by device ops, r
 Level sums are reduced across ranks (``mlmc_b200.dist``) when sample sharding is active, then finalised on the
 device (``mlmcb200_finalize_levels``) and copied to the host once.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -374,8 +376,31 @@ def _quantity_mean_from_packed(quantity, plan, packed, L, K):
                               n_rm_samples=n_rm_samples, mean=mean, var=var)
 
 
+_WEIGHTED_BLOCK_ROWS = 131072        # rows per row block of the multiplicity histogram (<= counts_block_rows())
+
+
+def _weighted_bootstrap_applies(method, basis, x, sizes, n_chunk):
+    """One-pass weighted sums (``mlmcb200_moments_accumulate_weighted``) or per-replicate gather
+    (``mlmcb200_moments_accumulate_resampled``)?  The weighted pass costs ~ n_chunk x (replicates rounded up to 8), the
+    gather ~ 3.6 x the draws (per moment): the pass wins when the replicates draw about as many rows as the chunk holds.
+    ``method``: None (choose), "weighted" (wherever the kernel applies), "gather"."""
+    method = method or os.environ.get("MLMCB200_BOOTSTRAP") or None
+    if method == "gather":
+        return False
+    if method not in (None, "weighted"):
+        raise ValueError("bootstrap method must be None, 'weighted' or 'gather'")
+    M, n, S = x.shape
+    sn, ss = x.stride(1), x.stride(2)
+    ok = (basis.kind == _native.LEGENDRE and basis.size <= _native.weighted_max_size() and M == 1 and n_chunk >= 1
+          and (S == 1 or (sn == 2 and ss == 1)) and x.data_ptr() % 8 == 0
+          and int(sizes.max()) <= 8 * n_chunk and int(sizes.max()) > 0)
+    if not ok or method == "weighted":
+        return ok
+    return float(sizes.sum()) >= 0.35 * n_chunk * 8 * (-(-len(sizes) // 8))
+
+
 def bootstrap_moments(quantity, moments_fn, sample_vector, n_subsamples, seed=None, mom_at_bottom=False,
-                      return_indices=False):
+                      return_indices=False, method=None):
     """All ``n_subsamples`` bootstrap replicates of ``estimate_mean(moments(quantity.subsample(sample_vector)))``
     (the loop body of ``Estimate.est_bootstrap``, mlmc/estimator.py:185-193) fused on the device.
 
@@ -455,7 +480,35 @@ def bootstrap_moments(quantity, moments_fn, sample_vector, n_subsamples, seed=No
             return _native.resample_indices(seed, stream_id, n_chunk, k, b1 - b0, device, block_cum=cum,
                                             rep_offset=b_lo + b0)
 
-        if np.all(sizes == sizes[0]):
+        if _weighted_bootstrap_applies(method, basis, x, sizes, n_chunk):
+            # ONE pass over the rows for all replicates: multiplicities (the same Philox draws, histogrammed) times the
+            # moment differences on FP64 tensor tiles (csrc/bootstrap.cu)
+            n_wblocks = max(1, -(-n_chunk // _WEIGHTED_BLOCK_ROWS))
+            edges = (np.arange(n_wblocks + 1, dtype=np.int64) * n_chunk) // n_wblocks
+            p_block = np.diff(edges) / n_chunk
+            cum_h = np.zeros((B, n_wblocks + 1), dtype=np.int64)
+            for b in range(B):
+                if n_wblocks > 1:
+                    np.cumsum(host_rngs[b].multinomial(int(sizes[b]), p_block), out=cum_h[b, 1:])
+                else:
+                    cum_h[b, 1] = int(sizes[b])
+            stride = -(-n_chunk // 16) * 16
+            group = max(8, min(B, ((2 << 30) // stride) // 8 * 8))            # <= 2 GB of multiplicities at a time
+            for b0 in range(0, B, group):
+                b1 = min(B, b0 + group)
+                cum = torch.from_numpy(cum_h[b0:b1]).to(device)
+                counts = _native.resample_counts(seed, stream_id, n_chunk, cum, int(sizes[b0:b1].max()), device,
+                                                 rep_offset=b_lo + b0)
+                _native.moments_accumulate_weighted(basis, x, counts, level_acc[b0:b1])
+                del counts
+            if return_indices:                                                 # test hook: the rows behind the counts
+                for b in range(B):
+                    if sizes[b] > 0:
+                        cum = torch.from_numpy(cum_h[b:b + 1]).to(device) if n_wblocks > 1 else None
+                        idx = _native.resample_indices(seed, stream_id, n_chunk, int(sizes[b]), 1, device,
+                                                       block_cum=cum, rep_offset=b_lo + b)
+                        indices[level_id].append((offsets[level_id], b_lo + b, idx))
+        elif np.all(sizes == sizes[0]):
             k = int(sizes[0])
             if k > 0:
                 group = max(1, min(B, max_draws // k))

@@ -374,8 +374,10 @@ def test_bootstrap_and_subsample(golden):
     assert list(qm.n_samples + qm.n_rm_samples) == [100, 50, 25]
 
 
-def test_fused_bootstrap_matches_oracle_on_same_rows(golden):
-    """qe.bootstrap_moments: every replicate equals the oracle's estimate on exactly the rows it drew."""
+@pytest.mark.parametrize("method", ["gather", "weighted"])
+def test_fused_bootstrap_matches_oracle_on_same_rows(golden, method):
+    """qe.bootstrap_moments: every replicate equals the oracle's estimate on exactly the rows it drew -- by the per-replicate
+    gather kernel and by the one-pass weighted sums on tensor tiles (multiplicities of the same draws)."""
     import torch
     from mlmc_b200.moments import Legendre
     from mlmc_b200.quantity import quantity_estimate as qe
@@ -385,7 +387,7 @@ def test_fused_bootstrap_matches_oracle_on_same_rows(golden):
     domain = tuple(g["A_domain"])
     fn = Legendre(8, domain)
     sample_vec = [1500, 700, 300]
-    out = qe.bootstrap_moments(value, fn, sample_vec, 6, seed=11, return_indices=True)
+    out = qe.bootstrap_moments(value, fn, sample_vec, 6, seed=11, return_indices=True, method=method)
     assert out["mean"].shape == (6, 8) and out["l_vars"].shape == (6, 3, 8)
     assert np.all(out["mean"][:, 0] == 1.0) and np.all(out["var"][:, 0] == 0.0)
     basis = orc.Basis("legendre", 8, domain)
@@ -402,7 +404,7 @@ def test_fused_bootstrap_matches_oracle_on_same_rows(golden):
         rel_close(out["mean"][b], want.mean, rtol=1e-10, atol_scale=1e-14)
         rel_close(out["var"][b], want.var, rtol=1e-10, atol_scale=1e-13)
     # same seed -> same replicates
-    again = qe.bootstrap_moments(value, fn, sample_vec, 6, seed=11)
+    again = qe.bootstrap_moments(value, fn, sample_vec, 6, seed=11, method=method)
     assert np.array_equal(again["mean"], out["mean"]) and np.array_equal(again["l_vars"], out["l_vars"])
 
 
@@ -451,7 +453,8 @@ def test_bases_beyond_the_fused_kernel_limits(golden):
     rel_close(np.ravel(cm.var), wc.var, rtol=1e-8, atol_scale=1e-13)
 
 
-def test_fused_bootstrap_streamed_chunks(golden):
+@pytest.mark.parametrize("method", ["gather", "weighted"])
+def test_fused_bootstrap_streamed_chunks(golden, method):
     """A level that arrives in several device chunks: hypergeometric split of the draws over the chunks
     (quantity.py:317), ragged draws per replicate -- every replicate still equals the oracle on its own rows."""
     from mlmc_b200.moments import Legendre
@@ -464,7 +467,7 @@ def test_fused_bootstrap_streamed_chunks(golden):
     domain = tuple(g["A_domain"])
     fn = Legendre(6, domain)
     sample_vec = [900, 400, 150]
-    out = qe.bootstrap_moments(value, fn, sample_vec, 5, seed=2, return_indices=True)
+    out = qe.bootstrap_moments(value, fn, sample_vec, 5, seed=2, return_indices=True, method=method)
     basis = orc.Basis("legendre", 6, domain)
     n_chunks = [len({off for off, _, _ in out["indices"][l]}) for l in range(3)]
     assert max(n_chunks) > 1

@@ -568,6 +568,75 @@ def test_resample_indices_blocks_and_uniformity():
         assert np.array_equal(np.bincount(block_of, minlength=P), counts[r])
 
 
+def _block_cum(rng, n_rows, ks, P):
+    edges = (np.arange(P + 1, dtype=np.int64) * n_rows) // P
+    cum = np.zeros((len(ks), P + 1), dtype=np.int64)
+    for b, k in enumerate(ks):
+        np.cumsum(rng.multinomial(int(k), np.diff(edges) / n_rows), out=cum[b, 1:])
+    return cum
+
+
+@pytest.mark.parametrize("n_rows,P,ks", [(1_000_003, 7, [400_001, 400_001, 400_001]), (300_001, 3, [1, 0, 250_000, 999_999]),
+                                         (5000, 1, [5000, 123]), (131, 1, [1000])])
+def test_resample_counts_are_the_multiplicities_of_the_indices(n_rows, P, ks):
+    """mlmcb200_resample_counts: counts[b, i] = how often mlmcb200_resample_indices lists row i for replicate b (same seed,
+    stream, blocks): shared-memory histogram of the same Philox draws; ragged draws per replicate, unaligned block edges."""
+    nat = native()
+    rng = np.random.default_rng(1)
+    cum = _block_cum(rng, n_rows, ks, P)
+    cum_d = torch.from_numpy(cum).to(dev())
+    counts = nat.resample_counts(5, 3, n_rows, cum_d, max(ks), dev(), rep_offset=2)
+    assert counts.shape[0] == len(ks) and counts.shape[1] % 16 == 0 and counts.shape[1] >= n_rows
+    for b, k in enumerate(ks):
+        want = np.zeros(n_rows, dtype=np.int64)
+        if k > 0:
+            idx = nat.resample_indices(5, 3, n_rows, k, 1, dev(), block_cum=cum_d[b:b + 1].contiguous() if P > 1 else None,
+                                       rep_offset=2 + b).cpu().numpy()[0]
+            want = np.bincount(idx, minlength=n_rows)
+        assert np.array_equal(counts[b, :n_rows].cpu().numpy().astype(np.int64), want)
+
+
+@pytest.mark.parametrize("R,n_rep,level0,log,n_rows", [(50, 100, False, False, 300_001), (51, 13, True, False, 70_000),
+                                                       (7, 300, False, True, 20_011), (1, 5, False, False, 999),
+                                                       (25, 16, True, True, 4096), (12, 40, False, False, 100)])
+def test_weighted_sums_equal_the_gather_kernel(R, n_rep, level0, log, n_rows):
+    """mlmcb200_moments_accumulate_weighted (all replicates in one pass: multiplicities x moment differences on DMMA tiles)
+    adds what mlmcb200_moments_accumulate_resampled adds for the rows behind the multiplicities; samples outside the
+    domain / NaN are counted as removed in both (mask_nan_samples, quantity_estimate.py:6-14)."""
+    nat = native()
+    rng = np.random.default_rng(R + n_rep)
+    fine = rng.lognormal(size=n_rows) if log else rng.normal(size=n_rows)
+    rows = np.stack([fine, fine * (1 + 0.03 * rng.normal(size=n_rows))], axis=1)
+    bad = rng.choice(n_rows, size=max(1, n_rows // 50), replace=False)
+    rows[bad[::3], 0] = np.nan
+    rows[bad[1::3], 1] = 1e9
+    rows[bad[2::3], 0] = -1e9 if not log else 1e-300
+    if level0:
+        rows = rows[:, :1]
+    domain = (0.05, 12.0) if log else (-3.0, 3.0)
+    basis = to_struct(orc.Basis("legendre", R, domain, log=log))
+    x = torch.from_numpy(np.ascontiguousarray(rows)).to(dev()).reshape(n_rows, rows.shape[1], 1).permute(2, 0, 1)
+    P = max(1, -(-n_rows // 131072))
+    ks = rng.integers(max(1, n_rows // 2), 2 * n_rows, size=n_rep)
+    ks[0] = n_rows
+    cum = torch.from_numpy(_block_cum(rng, n_rows, ks, P)).to(dev())
+    counts = nat.resample_counts(9, 4, n_rows, cum, int(ks.max()), dev())
+    width = 2 + 2 * R
+    acc_w = torch.zeros((n_rep, width + 3), dtype=torch.float64, device=dev())[:, :width]      # strided replicate rows
+    acc_w[:, :] = 0.5                                                                            # the call ADDS
+    nat.moments_accumulate_weighted(basis, x, counts, acc_w)
+    acc_g = torch.zeros((n_rep, width), dtype=torch.float64, device=dev())
+    for b in range(n_rep):
+        idx = nat.resample_indices(9, 4, n_rows, int(ks[b]), 1, dev(), block_cum=cum[b:b + 1].contiguous() if P > 1 else None,
+                                   rep_offset=b)
+        nat.moments_accumulate_resampled(basis, x, idx, acc_g[b:b + 1])
+    got, want = acc_w.cpu().numpy() - 0.5, acc_g.cpu().numpy()
+    assert np.array_equal(got[:, :2], want[:, :2]) and np.all(got[:, 0] + got[:, 1] == ks)
+    assert want[:, 1].max() > 0                                       # removed samples were drawn
+    rel_close(got[:, 2:2 + R], want[:, 2:2 + R], rtol=1e-10, atol_scale=1e-13)
+    rel_close(got[:, 2 + R:], want[:, 2 + R:], rtol=1e-10, atol_scale=1e-13)
+
+
 # ------------------------------------------------------------------------------------------------------
 # order statistics for estimate_domain (estimator.py:299: np.percentile of the fine samples)
 @pytest.mark.parametrize("case", ["normal", "dups", "tiny1", "tiny2", "tiny3", "signed_zero_inf", "strided", "big"])

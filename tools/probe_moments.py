@@ -1,4 +1,4 @@
-"""Moments-kernel timing sweep (CUDA events, best of 5): R in 8..199, fine+coarse / level 0, full and sums-only."""
+"""Moments-kernel timing sweep (CUDA events, best of 5 regions of PROBE_B2B back-to-back calls): R in 8..199, fine+coarse / level 0, full and sums-only."""
 import os
 import sys
 
@@ -18,6 +18,9 @@ x = rows.permute(2, 0, 1)
 peak = nat.fp64_peak(0) / 2          # FP64 lane-instructions / s
 
 
+BACK_TO_BACK = int(os.environ.get("PROBE_B2B", "10"))      # launches per timed region (1: a lone call, launch latency exposed)
+
+
 def timed(fn, reps=5):
     fn()
     torch.cuda.synchronize()
@@ -25,10 +28,11 @@ def timed(fn, reps=5):
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(BACK_TO_BACK):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1))
+        best = min(best, e0.elapsed_time(e1) / BACK_TO_BACK)
     return best
 
 
