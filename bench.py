@@ -814,6 +814,30 @@ def bench_cfg4(ctx, levels, steps):
                                 "max_abs_pdf_err_vs_normal_interior": float(np.max(np.abs(dobj.density(xs2)
                                                                                          - stats.norm.pdf(xs2)))),
                                 "data_passes": 1}
+    out["_storage_value"] = (storage, value)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ bootstrap
+def bench_bootstrap(ctx, storage, value, n_rep=100):
+    """Estimate.est_bootstrap (mlmc/estimator.py:171-218) on cfg2's resident levels, Legendre 50,
+    100 replicates -- one pass per level (multiplicities x moment differences on DMMA tiles) against the per-replicate
+    gather kernel; the reference re-runs the whole estimate per replicate."""
+    from mlmc_b200.moments import Legendre
+    from mlmc_b200.estimator import Estimate
+    n = [int(v) for v in storage.get_n_collected()]
+    est = Estimate(value, storage, Legendre(N_MOMENTS, domain()))
+    out = {"workload": "est_bootstrap on cfg2's levels (%s rows), Legendre R=%d, %d replicates" % (n, N_MOMENTS, n_rep)}
+    for method in ("weighted", "gather"):
+        os.environ["MLMCB200_BOOTSTRAP"] = method
+        try:
+            before = ctx.nat.launch_count
+            ms, _ = ctx.timed_wall(lambda: est.est_bootstrap(n_subsamples=n_rep, seed=1), 2, warmup=1)
+            out[method + "_ms"] = ms
+            out[method + "_launches"] = (ctx.nat.launch_count - before) // 3
+        finally:
+            os.environ.pop("MLMCB200_BOOTSTRAP", None)
+    out["replicate_sample_moments_per_s"] = n_rep * float(sum(n)) * N_MOMENTS / (out["weighted_ms"] * 1e-3)
     return out
 
 
@@ -929,6 +953,10 @@ def run_gpu_arm(args):
     if ctx.world == 1:
         if "cfg4" in wanted:
             configs["cfg4"] = bench_cfg4(ctx, levels, steps)
+            storage_value = configs["cfg4"].pop("_storage_value")
+            if "bootstrap" in wanted:
+                configs["bootstrap"] = bench_bootstrap(ctx, *storage_value)
+            del storage_value
         if "cfg1" in wanted:
             configs["cfg1"] = bench_cfg1(ctx)
         if "cfg5" in wanted:
@@ -968,7 +996,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples-per-level", type=int, default=N_PER_LEVEL)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--configs", default="cfg1,cfg3,cfg4,cfg5",
+    ap.add_argument("--configs", default="cfg1,cfg3,cfg4,cfg5,bootstrap",
                     help="further BASELINE configs reported under `configs` in the same JSON line ('' = none)")
     ap.add_argument("--cfg3-samples", type=int, default=1_000_000_000)
     args = ap.parse_args()

@@ -11,9 +11,9 @@
 // re-evaluates it per replicate: 7.25 FP64 instructions per replicate-sample-moment against 2 flop on the tensor pipe
 // here) and the rows are read once, in storage order, instead of B times through L2 in random order.
 //
-// Tile: 128 samples.  X [128][108] doubles in shared memory (columns: ok, rm, d_0.., d_0^2.., zero padding; row stride
+// Tile: 192 samples.  X [192][108] doubles in shared memory (columns: ok, rm, d_0.., d_0^2.., zero padding; row stride
 // 4 mod 8 and rows skewed by (s / 4) % 4 as in gram.cu: conflict-free fragment loads and producer stores), the
-// multiplicities of up to 128 replicates as bytes [replicate][144].  m8n8k4 fragments (lane l): A[m = replicate l/4]
+// multiplicities of up to 128 replicates as bytes [replicate][208].  m8n8k4 fragments (lane l): A[m = replicate l/4]
 // [k = sample l%4] = count byte, B[k = sample l%4][n = column l/4] = X element, C[replicate l/4][columns 2(l%4), +1].
 // A warp owns 8 replicates x all column blocks (<= 26 accumulator registers); when the number of replicate blocks is
 // 1 or 2 (mod 4) the last one / two are cut into column ranges over 4 warps so that the four SM sub-partitions (each
@@ -27,11 +27,15 @@ namespace mlmcb200 {
 namespace {
 
 constexpr int kBsThreads = 512;
-constexpr int kBsTile = 128;            // samples per tile
+constexpr int kBsTile = 192;            // samples per tile (12 producing warps; X tile 166 kB)
 constexpr int kBsLD = 108;              // row stride of the X tile (doubles)
 constexpr int kBsMaxColBlocks = 13;     // 104 columns >= 2 + 2 R  ->  R <= 51
 constexpr int kBsMaxRepBlocks = 16;     // 128 replicates per CTA (grid.y runs over groups of replicates)
-constexpr int kBsPitch = 144;           // bytes per replicate row of the count tile (16-byte aligned, 4 banks apart)
+constexpr int kBsPitch = kBsTile + 16;   // bytes per replicate row of the count tile (16-byte aligned; 208 = 52 words:
+                                        // the 8 rows of a fragment start 20 banks apart -> 8 disjoint 4-bank groups)
+constexpr int kBsPieces = kBsTile / 16; // 16-byte pieces per replicate row
+constexpr int kBsPiecesPerThread = kBsMaxRepBlocks * 8 * kBsPieces / kBsThreads;
+static_assert(kBsMaxRepBlocks * 8 * kBsPieces % kBsThreads == 0, "count tile pieces per thread");
 constexpr int kBsOutPitch = 8 * kBsMaxColBlocks;
 constexpr int kCountCapRows = 196608;   // rows per row block of mlmcb200_resample_counts: byte counters in 192 kB
 
@@ -78,8 +82,8 @@ template <bool COARSE>
 __global__ void __launch_bounds__(kBsThreads, 1)
 weighted_moments_kernel(const WeightedArgs a) {
     extern __shared__ __align__(16) double smem_d[];
-    double* const X = smem_d;                                                   // [128][108] + skew
-    uint8_t* const Wt = reinterpret_cast<uint8_t*>(smem_d + kBsTile * kBsLD + 8);  // [128][144]
+    double* const X = smem_d;                                                   // [kBsTile][108] + skew
+    uint8_t* const Wt = reinterpret_cast<uint8_t*>(smem_d + kBsTile * kBsLD + 8);  // [128][kBsPitch]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int R = a.basis.size;
     const int ncb = a.n_col_blocks;
@@ -125,22 +129,24 @@ weighted_moments_kernel(const WeightedArgs a) {
         if (!producer || s >= a.n) return qnan;
         return __ldcs(a.pairs + s * a.stride_n + side);
     };
-    // count tile: 128 replicates x 8 pieces of 16 samples = 1024 16-byte pieces, two per thread
+    // count tile: 128 replicates x kBsPieces pieces of 16 samples, kBsPiecesPerThread per thread
     auto fetch_counts = [&](int64_t tile, int piece) {
-        const int i = tid + piece * kBsThreads, r = i >> 3, o = (i & 7) * 16;
+        const int i = tid + piece * kBsThreads, r = i / kBsPieces, o = (i - r * kBsPieces) * 16;
         const int64_t s0 = tile * kBsTile + o;
         if (r >= n_rep || s0 + 16 > a.counts_stride) return make_uint4(0u, 0u, 0u, 0u);
         return __ldcs(reinterpret_cast<const uint4*>(a.counts + (int64_t)(rep0 + r) * a.counts_stride + s0));
     };
     double v_next = fetch_value(blockIdx.x);
-    uint4 w_next[2] = {fetch_counts(blockIdx.x, 0), fetch_counts(blockIdx.x, 1)};
+    uint4 w_next[kBsPiecesPerThread];
+#pragma unroll
+    for (int piece = 0; piece < kBsPiecesPerThread; ++piece) w_next[piece] = fetch_counts(blockIdx.x, piece);
     __syncthreads();
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ---------------- produce ----------------
 #pragma unroll
-        for (int piece = 0; piece < 2; ++piece) {
-            const int i = tid + piece * kBsThreads, r = i >> 3, o = (i & 7) * 16;
+        for (int piece = 0; piece < kBsPiecesPerThread; ++piece) {
+            const int i = tid + piece * kBsThreads, r = i / kBsPieces, o = (i - r * kBsPieces) * 16;
             *reinterpret_cast<uint4*>(Wt + r * kBsPitch + o) = w_next[piece];
         }
         if (producer) {
@@ -187,8 +193,8 @@ weighted_moments_kernel(const WeightedArgs a) {
         const int64_t nxt = tile + gridDim.x;
         if (nxt < n_tiles) {
             v_next = fetch_value(nxt);
-            w_next[0] = fetch_counts(nxt, 0);
-            w_next[1] = fetch_counts(nxt, 1);
+#pragma unroll
+            for (int piece = 0; piece < kBsPiecesPerThread; ++piece) w_next[piece] = fetch_counts(nxt, piece);
         }
         if (brow >= 0) {
             const double* xb = X + (size_t)(lane & 3) * kBsLD + (lane >> 2) + 8 * c_lo;

@@ -379,10 +379,12 @@ def _quantity_mean_from_packed(quantity, plan, packed, L, K):
 _WEIGHTED_BLOCK_ROWS = 131072        # rows per row block of the multiplicity histogram (<= counts_block_rows())
 
 
-def _weighted_bootstrap_applies(method, basis, x, sizes, n_chunk):
+def _weighted_bootstrap_applies(method, basis, x, sizes, n_chunk, expected_draws, n_replicates):
     """One-pass weighted sums (``mlmcb200_moments_accumulate_weighted``) or per-replicate gather
     (``mlmcb200_moments_accumulate_resampled``)?  The weighted pass costs ~ n_chunk x (replicates rounded up to 8), the
     gather ~ 3.6 x the draws (per moment): the pass wins when the replicates draw about as many rows as the chunk holds.
+    The choice depends on the EXPECTED draws of a replicate in this chunk and on the total number of replicates only
+    (not on this rank's share of them), so that a seed gives the same replicates for every world size.
     ``method``: None (choose), "weighted" (wherever the kernel applies), "gather"."""
     method = method or os.environ.get("MLMCB200_BOOTSTRAP") or None
     if method == "gather":
@@ -393,10 +395,10 @@ def _weighted_bootstrap_applies(method, basis, x, sizes, n_chunk):
     sn, ss = x.stride(1), x.stride(2)
     ok = (basis.kind == _native.LEGENDRE and basis.size <= _native.weighted_max_size() and M == 1 and n_chunk >= 1
           and (S == 1 or (sn == 2 and ss == 1)) and x.data_ptr() % 8 == 0
-          and int(sizes.max()) <= 8 * n_chunk and int(sizes.max()) > 0)
+          and expected_draws <= 6 * n_chunk and 0 < int(sizes.max()) <= 8 * n_chunk)
     if not ok or method == "weighted":
         return ok
-    return float(sizes.sum()) >= 0.35 * n_chunk * 8 * (-(-len(sizes) // 8))
+    return expected_draws * n_replicates >= 0.35 * n_chunk * 8 * (-(-n_replicates // 8))
 
 
 def bootstrap_moments(quantity, moments_fn, sample_vector, n_subsamples, seed=None, mom_at_bottom=False,
@@ -480,7 +482,8 @@ def bootstrap_moments(quantity, moments_fn, sample_vector, n_subsamples, seed=No
             return _native.resample_indices(seed, stream_id, n_chunk, k, b1 - b0, device, block_cum=cum,
                                             rep_offset=b_lo + b0)
 
-        if _weighted_bootstrap_applies(method, basis, x, sizes, n_chunk):
+        expected = float(sample_vector[level_id]) * n_chunk / max(1, n_collected[level_id])
+        if _weighted_bootstrap_applies(method, basis, x, sizes, n_chunk, expected, n_total):
             # ONE pass over the rows for all replicates: multiplicities (the same Philox draws, histogrammed) times the
             # moment differences on FP64 tensor tiles (csrc/bootstrap.cu)
             n_wblocks = max(1, -(-n_chunk // _WEIGHTED_BLOCK_ROWS))

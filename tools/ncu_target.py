@@ -47,5 +47,19 @@ if which == "resampled":
             idx = (torch.randint(0, bs, (nb, n), dtype=torch.int32, device=dev) + seg[None, :] * bs).contiguous()
         acc_r = torch.zeros((nb, 2 + 2 * bench.N_MOMENTS), dtype=torch.float64, device=dev)
         nat.moments_accumulate_resampled(basis, views[1], idx, acc_r)
+if which == "weighted":
+    # all bootstrap replicates of the middle level in one pass: multiplicities (shared-memory histogram of the Philox
+    # draws) + weighted sums on DMMA tiles (csrc/bootstrap.cu)
+    B, P = 100, max(1, -(-n // 131072))
+    edges = (np.arange(P + 1, dtype=np.int64) * n) // P
+    rng = np.random.default_rng(0)
+    cum_h = np.zeros((B, P + 1), dtype=np.int64)
+    for b in range(B):
+        np.cumsum(rng.multinomial(n, np.diff(edges) / n), out=cum_h[b, 1:])
+    cum = torch.from_numpy(cum_h).to(dev)
+    acc_w = torch.zeros((B, 2 + 2 * bench.N_MOMENTS), dtype=torch.float64, device=dev)
+    for rep in range(2):
+        counts = nat.resample_counts(1, 1, n, cum, n, dev)
+        nat.moments_accumulate_weighted(basis, views[1], counts, acc_w)
 torch.cuda.synchronize()
 print("ok", float(out["mean"][1]) if which in ("all", "moments") else "")
