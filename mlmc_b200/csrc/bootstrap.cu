@@ -12,7 +12,8 @@
 // here) and the rows are read once, in storage order, instead of B times through L2 in random order.
 //
 // Tile: 192 samples.  X [192][108] doubles in shared memory (columns: ok, rm, d_0.., d_0^2.., zero padding; row stride
-// 4 mod 8 and rows skewed by (s / 4) % 4 as in gram.cu: conflict-free fragment loads and producer stores), the
+// 4 mod 8 and rows skewed by (s / 4) % 4 as in gram.cu: conflict-free fragment loads and producer stores; a sample is
+// produced by two threads, one per moment parity, each running the fine and the coarse chain side by side), the
 // multiplicities of up to 128 replicates as bytes [replicate][208].  m8n8k4 fragments (lane l): A[m = replicate l/4]
 // [k = sample l%4] = count byte, B[k = sample l%4][n = column l/4] = X element, C[replicate l/4][columns 2(l%4), +1].
 // A warp owns 8 replicates x all column blocks (<= 26 accumulator registers); when the number of replicate blocks is
@@ -78,6 +79,40 @@ __device__ __forceinline__ void contract_tile(double (&acc)[kBsMaxColBlocks][2],
     }
 }
 
+// Two steps of the monic Legendre recurrence at once, W_j = (t^2 - A_j) W_{j-2} - B_j W_{j-4} (gen_tables.py; gram.cu
+// uses the same split): the even and the odd moments of a sample are independent chains, so TWO threads produce a sample
+// (2 x 192 threads = 12 warps advance the tile instead of 6), each running the fine and the coarse chain side by side.
+static __constant__ double kLegA2[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_A2_INIT;
+static __constant__ double kLegB2[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_B2_INIT;
+
+// d_j = W_j(fine) - W_j(coarse) and d_j^2 for j = PARITY, PARITY + 2, ... < R into pd[j], pq[j].  PARITY is a template
+// parameter and the caller branches warp-uniformly, so j and the coefficients stay in uniform registers.
+// tf = tc = 0 and good = false for a dropped sample: it starts from W = 0 and writes exact zeros.
+template <bool COARSE, int PARITY>
+__device__ __forceinline__ void produce_moments(int R, double tf, double tc, bool good, double* pd, double* pq) {
+    if (PARITY >= R) return;
+    const double uf = tf * tf, uc = tc * tc;
+    double f0 = 0.0, c0 = 0.0;                                                   // W_{j-4}
+    double f1 = good ? (PARITY ? tf : 1.0) : 0.0, c1 = good ? (PARITY ? tc : 1.0) : 0.0;   // W_{j-2}
+    {
+        const double d = COARSE ? f1 - c1 : f1;
+        pd[PARITY] = d;
+        pq[PARITY] = d * d;
+    }
+    for (int j = PARITY + 2; j < R; j += 2) {
+        const double a2 = kLegA2[j], b2 = kLegB2[j];
+        const double qf = fma(uf - a2, f1, -(b2 * f0));
+        const double qc = COARSE ? fma(uc - a2, c1, -(b2 * c0)) : 0.0;
+        f0 = f1;
+        f1 = qf;
+        c0 = c1;
+        c1 = qc;
+        const double d = COARSE ? qf - qc : qf;
+        pd[j] = d;
+        pq[j] = d * d;
+    }
+}
+
 template <bool COARSE>
 __global__ void __launch_bounds__(kBsThreads, 1)
 weighted_moments_kernel(const WeightedArgs a) {
@@ -120,14 +155,15 @@ weighted_moments_kernel(const WeightedArgs a) {
 
     const int64_t n_tiles = (a.n + kBsTile - 1) / kBsTile;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    // producers: COARSE -> lanes (2s, 2s+1) hold the fine and the coarse value of sample s; level 0 -> one thread a sample
-    const int n_prod = COARSE ? 2 * kBsTile : kBsTile;
-    const int ps = COARSE ? tid >> 1 : tid, side = COARSE ? (tid & 1) : 0;
-    const bool producer = tid < n_prod;
+    // producers: threads s and kBsTile + s produce the even / the odd moments of sample s (parity is warp-uniform)
+    const int parity = tid >= kBsTile ? 1 : 0;
+    const int ps = tid - parity * kBsTile;
+    const bool producer = tid < 2 * kBsTile;
     auto fetch_value = [&](int64_t tile) {
         const int64_t s = tile * kBsTile + ps;
-        if (!producer || s >= a.n) return qnan;
-        return __ldcs(a.pairs + s * a.stride_n + side);
+        if (!producer || s >= a.n) return make_double2(qnan, qnan);
+        if (COARSE) return __ldcs(reinterpret_cast<const double2*>(a.pairs) + s);
+        return make_double2(__ldcs(a.pairs + s * a.stride_n), 0.0);
     };
     // count tile: 128 replicates x kBsPieces pieces of 16 samples, kBsPiecesPerThread per thread
     auto fetch_counts = [&](int64_t tile, int piece) {
@@ -136,7 +172,7 @@ weighted_moments_kernel(const WeightedArgs a) {
         if (r >= n_rep || s0 + 16 > a.counts_stride) return make_uint4(0u, 0u, 0u, 0u);
         return __ldcs(reinterpret_cast<const uint4*>(a.counts + (int64_t)(rep0 + r) * a.counts_stride + s0));
     };
-    double v_next = fetch_value(blockIdx.x);
+    double2 v_next = fetch_value(blockIdx.x);
     uint4 w_next[kBsPiecesPerThread];
 #pragma unroll
     for (int piece = 0; piece < kBsPiecesPerThread; ++piece) w_next[piece] = fetch_counts(blockIdx.x, piece);
@@ -152,40 +188,27 @@ weighted_moments_kernel(const WeightedArgs a) {
         if (producer) {
             const int64_t s = tile * kBsTile + ps;
             const bool in = s < a.n;
-            double t = a.basis.is_log ? log(v_next) : v_next;
-            t = __dadd_rn(__dmul_rn(__dsub_rn(t, a.basis.shift), a.basis.scale), a.basis.ref_lo);
-            bool good = a.basis.is_clip ? (t >= a.basis.ref_lo && t <= a.basis.ref_hi) : moments_finite(a.basis, t);
-            if (COARSE) {                                 // the shuffle is executed by every lane (no short-circuit)
-                const int other_good = __shfl_xor_sync(0xffffffffu, good ? 1 : 0, 1);
-                good = good && other_good != 0;
+            double tf = a.basis.is_log ? log(v_next.x) : v_next.x;
+            tf = __dadd_rn(__dmul_rn(__dsub_rn(tf, a.basis.shift), a.basis.scale), a.basis.ref_lo);
+            bool good = a.basis.is_clip ? (tf >= a.basis.ref_lo && tf <= a.basis.ref_hi) : moments_finite(a.basis, tf);
+            double tc = 0.0;
+            if (COARSE) {
+                tc = a.basis.is_log ? log(v_next.y) : v_next.y;
+                tc = __dadd_rn(__dmul_rn(__dsub_rn(tc, a.basis.shift), a.basis.scale), a.basis.ref_lo);
+                const bool good_c = a.basis.is_clip ? (tc >= a.basis.ref_lo && tc <= a.basis.ref_hi)
+                                                    : moments_finite(a.basis, tc);
+                good = good && good_c;
             }
             good = good && in;
-            t = good ? t : 0.0;
+            tf = good ? tf : 0.0;
+            tc = good ? tc : 0.0;
             double* const row = X + (size_t)ps * kBsLD + ((ps >> 2) & 3);
-            if (side == 0) row[0] = good ? 1.0 : 0.0;
-            if (!COARSE || side == 1) row[1] = (in && !good) ? 1.0 : 0.0;
-            // monic Legendre recurrence W_k = t W_{k-1} - e_k W_{k-2} (P_k = kLegAlpha[k] W_k is applied to the sums)
-            double w2 = good ? 1.0 : 0.0, w1 = t;
-            double* pd = row + 2;                       // d_k
-            double* pq = row + 2 + R;                   // d_k^2
-            for (int k = 0; k < R; ++k) {
-                double w;
-                if (k == 0) w = w2;
-                else if (k == 1) w = w1;
-                else {
-                    w = fma(-kLegCoef[k], w2, t * w1);
-                    w2 = w1;
-                    w1 = w;
-                }
-                if (COARSE) {
-                    const double other = __shfl_xor_sync(0xffffffffu, w, 1);
-                    const double d = side == 0 ? w - other : other - w;
-                    if (side == 0) pd[k] = d;
-                    else pq[k] = d * d;
-                } else {
-                    pd[k] = w;
-                    pq[k] = w * w;
-                }
+            if (parity == 0) {
+                row[0] = good ? 1.0 : 0.0;
+                row[1] = (in && !good) ? 1.0 : 0.0;
+                produce_moments<COARSE, 0>(R, tf, tc, good, row + 2, row + 2 + R);
+            } else {
+                produce_moments<COARSE, 1>(R, tf, tc, good, row + 2, row + 2 + R);
             }
         }
         __syncthreads();
@@ -383,9 +406,9 @@ extern "C" int mlmcb200_moments_accumulate_weighted(const mlmcb200_basis_t* basi
     MB_REQUIRE(acc_rep_stride >= 2 + 2 * (int64_t)basis->size, "moments_accumulate_weighted: replicate stride too small");
     MB_REQUIRE(counts_stride >= n_rows && counts_stride % 16 == 0 && (reinterpret_cast<uintptr_t>(counts) & 15) == 0,
                "moments_accumulate_weighted: counts rows must be 16-byte aligned and at least n_rows long");
-    MB_REQUIRE(has_coarse ? stride_n == 2 : stride_n >= 1,
-               "moments_accumulate_weighted: scalar quantity in storage order expected (stride_n=%lld)",
-               (long long)stride_n);
+    MB_REQUIRE(has_coarse ? (stride_n == 2 && (reinterpret_cast<uintptr_t>(pairs) & 15) == 0) : stride_n >= 1,
+               "moments_accumulate_weighted: scalar quantity in storage order expected ((fine, coarse) pairs 16-byte "
+               "aligned, stride_n=%lld)", (long long)stride_n);
     if (n_rows == 0) return 0;
     MB_REQUIRE(pairs != nullptr, "moments_accumulate_weighted: null pairs");
     MB_REQUIRE(workspace_bytes >= mlmcb200_moments_weighted_workspace_bytes(n_rows, n_rep),

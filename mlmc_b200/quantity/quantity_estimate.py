@@ -394,7 +394,7 @@ def _weighted_bootstrap_applies(method, basis, x, sizes, n_chunk, expected_draws
     M, n, S = x.shape
     sn, ss = x.stride(1), x.stride(2)
     ok = (basis.kind == _native.LEGENDRE and basis.size <= _native.weighted_max_size() and M == 1 and n_chunk >= 1
-          and (S == 1 or (sn == 2 and ss == 1)) and x.data_ptr() % 8 == 0
+          and (S == 1 or (sn == 2 and ss == 1 and x.data_ptr() % 16 == 0))
           and expected_draws <= 6 * n_chunk and 0 < int(sizes.max()) <= 8 * n_chunk)
     if not ok or method == "weighted":
         return ok
