@@ -39,11 +39,15 @@ def _worker(rank, world, port, out_dir):
     qm = qe.estimate_mean(qe.moments(value, Legendre(12, tuple(g["A_domain"]))))
     cm = qe.estimate_mean(qe.covariance(value, Legendre(8, tuple(g["A_domain"]))))
     # bootstrap: replicates are sharded over the ranks, every rank ends up with all of them
-    bs = qe.bootstrap_moments(value, Legendre(6, tuple(g["A_domain"])), [800, 400, 200], 5, seed=4)
-    bs1 = None
-    if rank == 0:                                   # the same call on one rank (sharding off) for comparison
+    bs = qe.bootstrap_moments(value, Legendre(6, tuple(g["A_domain"])), [800, 400, 200], 5, seed=4, method="gather")
+    # ... also on the one-pass weighted path (multiplicities x moment differences on DMMA tiles), 11 replicates
+    bsw = qe.bootstrap_moments(value, Legendre(6, tuple(g["A_domain"])), [800, 400, 200], 11, seed=4, method="weighted")
+    bs1 = bsw1 = None
+    if rank == 0:                                   # the same calls on one rank (sharding off) for comparison
         dist.disable()
-        bs1 = qe.bootstrap_moments(value, Legendre(6, tuple(g["A_domain"])), [800, 400, 200], 5, seed=4)
+        bs1 = qe.bootstrap_moments(value, Legendre(6, tuple(g["A_domain"])), [800, 400, 200], 5, seed=4, method="gather")
+        bsw1 = qe.bootstrap_moments(value, Legendre(6, tuple(g["A_domain"])), [800, 400, 200], 11, seed=4,
+                                    method="weighted")
         dist.enable(rank, world)
     # the same estimates with the sum over the ranks fused into the finalize launch (NVLink peer memory)
     peer_ok = dist.enable_peer_reduce()
@@ -81,7 +85,8 @@ def _worker(rank, world, port, out_dir):
     peer["lin_cov"] = lin.mean
     np.savez(os.path.join(out_dir, "r%d.npz" % rank), l_means=qm.l_means, l_vars=qm.l_vars, n=qm.n_samples,
              n_rm=qm.n_rm_samples, cov=cm.mean, cov_var=cm.var, bs_l_means=bs["l_means"], bs_n=bs["n_samples"],
-             bs1_l_means=bs1["l_means"] if bs1 is not None else np.zeros(0), peer_ok=int(peer_ok), **peer)
+             bs1_l_means=bs1["l_means"] if bs1 is not None else np.zeros(0), bsw_l_vars=bsw["l_vars"], bsw_n=bsw["n_samples"],
+             bsw1_l_vars=bsw1["l_vars"] if bsw1 is not None else np.zeros(0), peer_ok=int(peer_ok), **peer)
     import torch.distributed as td
     td.barrier()
     td.destroy_process_group()
@@ -118,6 +123,10 @@ def test_two_gpu_sharded_estimate(tmp_path, golden):
     assert np.array_equal(a["bs_n"], b["bs_n"]) and np.all(a["bs_n"].sum(axis=1) > 0)
     # replicates are keyed by (seed, global replicate number): sharded over two ranks or not, the same five replicates
     assert np.array_equal(a["bs_l_means"], a["bs1_l_means"])
+    # weighted path: the replicates of a seed do not depend on the world size; the CTA partials are summed in CTA order,
+    # so even the bits agree
+    assert a["bsw_l_vars"].shape[0] == 11 and np.array_equal(a["bsw_l_vars"], a["bsw1_l_vars"])
+    assert np.all(a["bsw_n"].sum(axis=1) > 0)
     assert np.all(np.abs(a["bs_l_means"][:, :, 0].sum(axis=1) - 1.0) < 1e-12)
     # fused peer-memory reduce: same numbers as the NCCL route (two ranks: a + b either way), no time-out
     assert int(a["peer_ok"]) == int(b["peer_ok"])
