@@ -496,7 +496,12 @@ def bootstrap_moments(quantity, moments_fn, sample_vector, n_subsamples, seed=No
                 else:
                     cum_h[b, 1] = int(sizes[b])
             stride = -(-n_chunk // 16) * 16
-            group = max(8, min(B, ((2 << 30) // stride) // 8 * 8))            # <= 2 GB of multiplicities at a time
+            # multiplicities of as many replicates at a time as a quarter of the free device memory holds (>= 2 GB), in
+            # whole groups of the kernel (104 replicates) where possible: few replicates per pass waste the tensor tiles
+            budget = max(2 << 30, torch.cuda.mem_get_info(device)[0] // 4)
+            group = min(B, max(8, (budget // stride) // 8 * 8))
+            if group < B and group > 104:
+                group = group // 104 * 104
             for b0 in range(0, B, group):
                 b1 = min(B, b0 + group)
                 cum = torch.from_numpy(cum_h[b0:b1]).to(device)
