@@ -50,6 +50,52 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc < 0 and b"needs a coarse side" in lib.mlmcb200_last_error()
     rc = lib.mlmcb200_density_eval(ctypes.byref(good), one, 5, one, 8, one, None)
     assert rc < 0 and b"n_coef" in lib.mlmcb200_last_error()
+    # one-pass bootstrap (csrc/bootstrap.cu)
+    assert lib.mlmcb200_moments_weighted_max_size() == 51 and 0 < lib.mlmcb200_resample_counts_block_rows() <= 196608
+    assert lib.mlmcb200_moments_weighted_workspace_bytes(10_000_000, 300) == \
+        3 * lib.mlmcb200_moments_weighted_workspace_bytes(10_000_000, 100) > 0
+    mono = _native.make_basis(_native.MONOMIAL, 7, (2.0, 6.0), (0.0, 1.0))
+    wide = _native.make_basis(_native.LEGENDRE, 52, (2.0, 6.0), (-1.0, 1.0))
+    for b in (mono, wide):
+        rc = lib.mlmcb200_moments_accumulate_weighted(ctypes.byref(b), one, 10, 2, 1, one, 16, 3, one, 200, one, 1 << 30, None)
+        assert rc < 0 and b"Legendre bases of at most 51" in lib.mlmcb200_last_error()
+    rc = lib.mlmcb200_moments_accumulate_weighted(ctypes.byref(good), one, 10, 3, 1, ctypes.c_void_p(16), 16, 3, one, 200, one,
+                                                  1 << 30, None)
+    assert rc < 0 and b"storage order" in lib.mlmcb200_last_error()
+    rc = lib.mlmcb200_moments_accumulate_weighted(ctypes.byref(good), ctypes.c_void_p(16), 10, 2, 1, ctypes.c_void_p(16), 10, 3,
+                                                  one, 200, one, 1 << 30, None)
+    assert rc < 0 and b"16-byte aligned" in lib.mlmcb200_last_error()
+    rc = lib.mlmcb200_resample_counts(1, 1, 1_000_000, 10, 2, 0, 2, one, one, 1_000_000, None)
+    assert rc < 0 and b"row blocks of more than" in lib.mlmcb200_last_error()
+    rc = lib.mlmcb200_resample_counts(1, 1, 1000, 8001, 2, 0, 1, one, one, 1008, None)
+    assert rc < 0 and b"more than 8 draws per row" in lib.mlmcb200_last_error()
+
+
+def test_bootstrap_path_choice_is_world_size_independent():
+    """quantity_estimate._weighted_bootstrap_applies: the one-pass weighted kernel for scalar Legendre bases of <= 51
+    moments in storage order when the replicates draw about as many rows as the chunk holds; the rule reads the expected
+    draws and the TOTAL replicate count, never this rank's share."""
+    import numpy as np
+    import torch
+    from mlmc_b200 import _native
+    from mlmc_b200.quantity import quantity_estimate as qe
+    leg = _native.make_basis(_native.LEGENDRE, 50, (-3.0, 3.0), (-1.0, 1.0))
+    rows = torch.zeros((1000, 2, 1), dtype=torch.float64)
+    x = rows.permute(2, 0, 1)
+    sizes = np.full(7, 1000)
+    assert qe._weighted_bootstrap_applies(None, leg, x, sizes, 1000, 1000.0, 100)
+    assert qe._weighted_bootstrap_applies(None, leg, x, sizes[:1], 1000, 1000.0, 100)      # a rank holding one replicate
+    assert not qe._weighted_bootstrap_applies(None, leg, x, np.full(7, 100), 1000, 100.0, 100)        # few draws: gather
+    assert qe._weighted_bootstrap_applies("weighted", leg, x, np.full(7, 100), 1000, 100.0, 100)
+    assert not qe._weighted_bootstrap_applies("gather", leg, x, sizes, 1000, 1000.0, 100)
+    assert not qe._weighted_bootstrap_applies("weighted", leg, x, np.full(7, 9000), 1000, 9000.0, 100)   # byte counters
+    wide = _native.make_basis(_native.LEGENDRE, 60, (-3.0, 3.0), (-1.0, 1.0))
+    four = _native.make_basis(_native.FOURIER, 9, (-3.0, 3.0), (0.0, 6.283185307179586))
+    assert not qe._weighted_bootstrap_applies("weighted", wide, x, sizes, 1000, 1000.0, 100)
+    assert not qe._weighted_bootstrap_applies("weighted", four, x, sizes, 1000, 1000.0, 100)
+    vec = torch.zeros((1000, 2, 3), dtype=torch.float64).permute(2, 0, 1)
+    assert not qe._weighted_bootstrap_applies("weighted", leg, vec, sizes, 1000, 1000.0, 100)
+    assert not qe._weighted_bootstrap_applies("weighted", leg, vec[1:2], sizes, 1000, 1000.0, 100)   # one component of a field
 
 
 def test_sass_contains_fp64_tensor_and_no_legacy_half_mma():
