@@ -103,3 +103,34 @@ def test_cfg3_full_size_properties():
     assert torch.equal(cov.acc[0, :2], half.acc[0, :2])
     scale = float(cov.acc[0, 2:2 + R * R].abs().max())
     assert float((cov.acc[0, 2:2 + R * R] - half.acc[0, 2:2 + R * R]).abs().max()) < 1e-10 * scale
+
+
+def test_cfg2_size_weighted_bootstrap_identity_and_linearity():
+    """One-pass bootstrap kernel (csrc/bootstrap.cu) at cfg2's level size, size-independent properties: multiplicity 1 for
+    every row reproduces the plain level sums of the fused moments kernel (counts exactly, sums to 1e-10); multiplicity 2
+    gives exactly twice that, bit for bit (scaling by two is exact in every partial sum); multiplicity 0 gives zeros;
+    a replicate that keeps only the first half of the rows equals the plain sums of that half."""
+    nat = native()
+    n, R = 10_000_000, 50
+    g = torch.Generator(device=dev()).manual_seed(7)
+    x0 = torch.randn(n, generator=g, device=dev(), dtype=torch.float64)
+    rows = torch.stack([x0, x0 + 0.05 * torch.randn(n, generator=g, device=dev(), dtype=torch.float64)], dim=1).contiguous()
+    x = rows.reshape(n, 2, 1).permute(2, 0, 1)
+    basis = to_struct(orc.Basis("legendre", R, (-3.719016485455709, 3.719016485455709)))
+    counts = torch.zeros((4, n), dtype=torch.uint8, device=dev())
+    counts[0] = 1
+    counts[1] = 2
+    counts[3, :n // 2] = 1
+    acc = torch.zeros((4, 2 + 2 * R), dtype=torch.float64, device=dev())
+    nat.moments_accumulate_weighted(basis, x, counts, acc)
+    plain = torch.zeros(2 + 2 * R, dtype=torch.float64, device=dev())
+    nat.moments_accumulate(basis, x, plain)
+    half = torch.zeros(2 + 2 * R, dtype=torch.float64, device=dev())
+    nat.moments_accumulate(basis, x[:, :n // 2], half)
+    a, p, h = acc.cpu().numpy(), plain.cpu().numpy(), half.cpu().numpy()
+    assert a[0, 0] == p[0] and a[0, 1] == p[1] and p[0] + p[1] == n and p[1] > 0
+    rel_close(a[0, 2:], p[2:], rtol=1e-10, atol_scale=1e-12)
+    assert np.array_equal(a[1], 2.0 * a[0])
+    assert not a[2].any()
+    assert a[3, 0] == h[0] and a[3, 1] == h[1]
+    rel_close(a[3, 2:], h[2:], rtol=1e-10, atol_scale=1e-12)
