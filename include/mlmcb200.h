@@ -130,8 +130,9 @@ int mlmcb200_moments_accumulate_resampled(const mlmcb200_basis_t* basis, const d
                                           void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
- * Bootstrap re-sampling of one level in ONE pass over its rows (scalar quantity, Legendre basis of at most
- * mlmcb200_moments_weighted_max_size() moments): the same replicate loop as above (mlmc/estimator.py:171-218,
+ * Bootstrap re-sampling of one level in ONE pass over its rows (scalar quantity, Legendre or Monomial basis of at most
+ * mlmcb200_moments_weighted_max_size() moments; bases of more than 51 moments take ceil((2 + 2 R) / 104) passes, one
+ * per group of 104 result columns): the same replicate loop as above (mlmc/estimator.py:171-218,
  * mlmc/quantity/quantity.py:307-322), written as the weighted sums
  *     acc[b][2 + r] += sum_i w_bi d_r(i),   acc[b][2 + R + r] += sum_i w_bi d_r(i)^2,   acc[b][0 / 1] += sum_i w_bi ok_i / rm_i
  * with w_bi = how many times replicate b drew row i: the dense product W^T [ok | rm | D | D.D] on FP64 tensor-core
@@ -153,7 +154,7 @@ int mlmcb200_resample_counts(uint64_t seed, uint64_t stream_id, int64_t n_rows, 
                              int32_t rep_offset, int32_t n_blocks, const int64_t* block_cum, uint8_t* counts,
                              int64_t counts_stride, void* stream);
 int32_t mlmcb200_moments_weighted_max_size(void);
-int64_t mlmcb200_moments_weighted_workspace_bytes(int64_t n_rows, int32_t n_rep);
+int64_t mlmcb200_moments_weighted_workspace_bytes(int64_t n_rows, int32_t n_rep, int32_t size);
 int mlmcb200_moments_accumulate_weighted(const mlmcb200_basis_t* basis, const double* pairs, int64_t n_rows,
                                          int64_t stride_n, int32_t has_coarse, const uint8_t* counts,
                                          int64_t counts_stride, int32_t n_rep, double* acc, int64_t acc_rep_stride,

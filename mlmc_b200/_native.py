@@ -56,7 +56,7 @@ _SIGNATURES = {
     "mlmcb200_resample_counts": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, _c_i64, _c_i64, _c_i32, _c_i32,
                                                 _c_i32, _c_vp, _c_vp, _c_i64, _c_vp]),
     "mlmcb200_moments_weighted_max_size": (_c_i32, []),
-    "mlmcb200_moments_weighted_workspace_bytes": (_c_i64, [_c_i64, _c_i32]),
+    "mlmcb200_moments_weighted_workspace_bytes": (_c_i64, [_c_i64, _c_i32, _c_i32]),
     "mlmcb200_moments_accumulate_weighted": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_i64, _c_i32,
                                                             _c_vp, _c_i64, _c_i32, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp]),
     "mlmcb200_gram_workspace_bytes": (_c_i64, [_c_i32]),
@@ -389,7 +389,8 @@ def weighted_max_size():
 
 
 def moments_accumulate_weighted(basis, x, counts, acc_level):
-    """All bootstrap replicates of one level in one pass (scalar quantity, Legendre, size <= ``weighted_max_size()``).
+    """All bootstrap replicates of one level in one pass (scalar quantity, Legendre / Monomial, size <=
+    ``weighted_max_size()``).
 
     x [1, n_rows, S] in storage order; counts [B, stride] uint8 (``resample_counts``); acc_level [B, 2 + 2 R] (rows
     contiguous, any replicate stride).  Adds what ``moments_accumulate_resampled`` adds for the rows behind the counts."""
@@ -408,7 +409,7 @@ def moments_accumulate_weighted(basis, x, counts, acc_level):
         return
     lib = load()
     with _on_device(x.device):
-        ws_bytes = lib.mlmcb200_moments_weighted_workspace_bytes(n_rows, B)
+        ws_bytes = lib.mlmcb200_moments_weighted_workspace_bytes(n_rows, B, basis.size)
         if ws_bytes < 0:
             raise NativeError("weighted moments workspace: %s" % lib.mlmcb200_last_error().decode())
         ws = _workspace(x.device, ws_bytes)

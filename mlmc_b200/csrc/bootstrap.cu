@@ -54,8 +54,8 @@ struct WeightedArgs {
     int64_t counts_stride;
     int32_t n_rep;              // all replicates of the call
     int32_t reps_per_group;     // multiple of 8, <= 128; group g = replicates [g * reps_per_group, ...)
-    int32_t n_col_blocks;       // ceil((2 + 2 R) / 8)
-    double* partial;            // [group][gridDim.x][128][104]
+    int32_t monomial;           // 1: Monomial basis (t^j: the same two-step recurrence with A = B = 0, no re-scaling)
+    double* partial;            // [column group][replicate group][gridDim.x][128][104]
 };
 
 // The contraction of one tile for a warp that owns NC column blocks of one replicate block.
@@ -85,35 +85,41 @@ __device__ __forceinline__ void contract_tile(double (&acc)[kBsMaxColBlocks][2],
 static __constant__ double kLegA2[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_A2_INIT;
 static __constant__ double kLegB2[MLMCB200_MAX_MOMENTS] = MLMCB200_LEG_B2_INIT;
 
-// d_j = W_j(fine) - W_j(coarse) and d_j^2 for j = PARITY, PARITY + 2, ... < R into pd[j], pq[j].  PARITY is a template
-// parameter and the caller branches warp-uniformly, so j and the coefficients stay in uniform registers.
-// tf = tc = 0 and good = false for a dropped sample: it starts from W = 0 and writes exact zeros.
-template <bool COARSE, int PARITY>
-__device__ __forceinline__ void produce_moments(int R, double tf, double tc, bool good, double* pd, double* pq) {
+// d_j = W_j(fine) - W_j(coarse) and d_j^2 for j = PARITY, PARITY + 2, ... < R into the columns 2 + j and 2 + R + j of the
+// sample's row.  PARITY is a template parameter and the caller branches warp-uniformly, so j and the coefficients stay in
+// uniform registers.  tf = tc = 0 and good = false for a dropped sample: it starts from W = 0 and writes exact zeros.
+// MULTI: more than 104 columns -- the CTA holds the column group [c0, c0 + 104) only (blockIdx.z), stores outside it
+// are dropped (the recurrence runs in full either way: the squares need every d_j).
+template <bool COARSE, int PARITY, bool MULTI>
+__device__ __forceinline__ void produce_moments(int R, bool mono, int c0, double tf, double tc, bool good, double* row) {
     if (PARITY >= R) return;
+    auto put = [&](int col, double v) {
+        if (!MULTI) row[col] = v;
+        else if ((unsigned)(col - c0) < (unsigned)kBsOutPitch) row[col - c0] = v;
+    };
     const double uf = tf * tf, uc = tc * tc;
-    double f0 = 0.0, c0 = 0.0;                                                   // W_{j-4}
+    double f0 = 0.0, c0v = 0.0;                                                  // W_{j-4}
     double f1 = good ? (PARITY ? tf : 1.0) : 0.0, c1 = good ? (PARITY ? tc : 1.0) : 0.0;   // W_{j-2}
     {
         const double d = COARSE ? f1 - c1 : f1;
-        pd[PARITY] = d;
-        pq[PARITY] = d * d;
+        put(2 + PARITY, d);
+        put(2 + R + PARITY, d * d);
     }
     for (int j = PARITY + 2; j < R; j += 2) {
-        const double a2 = kLegA2[j], b2 = kLegB2[j];
+        const double a2 = mono ? 0.0 : kLegA2[j], b2 = mono ? 0.0 : kLegB2[j];
         const double qf = fma(uf - a2, f1, -(b2 * f0));
-        const double qc = COARSE ? fma(uc - a2, c1, -(b2 * c0)) : 0.0;
+        const double qc = COARSE ? fma(uc - a2, c1, -(b2 * c0v)) : 0.0;
         f0 = f1;
         f1 = qf;
-        c0 = c1;
+        c0v = c1;
         c1 = qc;
         const double d = COARSE ? qf - qc : qf;
-        pd[j] = d;
-        pq[j] = d * d;
+        put(2 + j, d);
+        put(2 + R + j, d * d);
     }
 }
 
-template <bool COARSE>
+template <bool COARSE, bool MULTI>
 __global__ void __launch_bounds__(kBsThreads, 1)
 weighted_moments_kernel(const WeightedArgs a) {
     extern __shared__ __align__(16) double smem_d[];
@@ -121,7 +127,9 @@ weighted_moments_kernel(const WeightedArgs a) {
     uint8_t* const Wt = reinterpret_cast<uint8_t*>(smem_d + kBsTile * kBsLD + 8);  // [128][kBsPitch]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int R = a.basis.size;
-    const int ncb = a.n_col_blocks;
+    const int c0 = MULTI ? (int)blockIdx.z * kBsOutPitch : 0;                    // first column of this CTA's group
+    const int ncb = (min(kBsOutPitch, 2 + 2 * R - c0) + 7) >> 3;
+    const bool mono = a.monomial != 0;
     const int rep0 = blockIdx.y * a.reps_per_group;
     const int n_rep = min(a.reps_per_group, a.n_rep - rep0);                     // replicates of this group
     const int nbb = (n_rep + 7) >> 3;
@@ -204,11 +212,13 @@ weighted_moments_kernel(const WeightedArgs a) {
             tc = good ? tc : 0.0;
             double* const row = X + (size_t)ps * kBsLD + ((ps >> 2) & 3);
             if (parity == 0) {
-                row[0] = good ? 1.0 : 0.0;
-                row[1] = (in && !good) ? 1.0 : 0.0;
-                produce_moments<COARSE, 0>(R, tf, tc, good, row + 2, row + 2 + R);
+                if (c0 == 0) {
+                    row[0] = good ? 1.0 : 0.0;
+                    row[1] = (in && !good) ? 1.0 : 0.0;
+                }
+                produce_moments<COARSE, 0, MULTI>(R, mono, c0, tf, tc, good, row);
             } else {
-                produce_moments<COARSE, 1>(R, tf, tc, good, row + 2, row + 2 + R);
+                produce_moments<COARSE, 1, MULTI>(R, mono, c0, tf, tc, good, row);
             }
         }
         __syncthreads();
@@ -236,7 +246,8 @@ weighted_moments_kernel(const WeightedArgs a) {
 
     // per-CTA partial [128][104]: C fragment (lane l): row l/4, columns 2 (l%4), 2 (l%4) + 1
     if (brow >= 0) {
-        double* out = a.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (kBsMaxRepBlocks * 8 * kBsOutPitch) +
+        double* out = a.partial + (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) *
+                                      (kBsMaxRepBlocks * 8 * kBsOutPitch) +
                       (size_t)(brow * 8 + (lane >> 2)) * kBsOutPitch + 8 * c_lo + 2 * (lane & 3);
 #pragma unroll
         for (int j = 0; j < kBsMaxColBlocks; ++j) {
@@ -247,14 +258,16 @@ weighted_moments_kernel(const WeightedArgs a) {
 
 // acc[b][...] += (sum over the CTAs' partials, in CTA order) re-scaled to P_k = alpha_k W_k; one thread per (b, column)
 __global__ void weighted_finish_kernel(const double* __restrict__ partial, int n_partials, int n_rep, int reps_per_group,
-                                       int R, double* __restrict__ acc, int64_t acc_rep_stride) {
+                                       int n_rep_groups, int R, int mono, double* __restrict__ acc,
+                                       int64_t acc_rep_stride) {
     const int n_cols = 2 + 2 * R;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (int64_t)n_rep * n_cols) return;
     const int b = (int)(gid / n_cols), col = (int)(gid - (int64_t)b * n_cols);
     const int g = b / reps_per_group, bl = b - g * reps_per_group;
+    const int cg = col / kBsOutPitch, lc = col - cg * kBsOutPitch;
     const size_t per = (size_t)kBsMaxRepBlocks * 8 * kBsOutPitch;
-    const double* p = partial + (size_t)g * n_partials * per + (size_t)bl * kBsOutPitch + col;
+    const double* p = partial + ((size_t)cg * n_rep_groups + g) * n_partials * per + (size_t)bl * kBsOutPitch + lc;
     double s = 0.0;
     int i = 0;
     for (; i + 8 <= n_partials; i += 8) {
@@ -269,9 +282,9 @@ __global__ void weighted_finish_kernel(const double* __restrict__ partial, int n
     if (col < 2) {
         dst[col] += s;
     } else if (col < 2 + R) {
-        dst[col] += s * kLegAlpha[col - 2];
+        dst[col] += mono ? s : s * kLegAlpha[col - 2];
     } else {
-        const double al = kLegAlpha[col - 2 - R];
+        const double al = mono ? 1.0 : kLegAlpha[col - 2 - R];
         dst[col] += s * (al * al);
     }
 }
@@ -383,14 +396,20 @@ extern "C" int mlmcb200_resample_counts(uint64_t seed, uint64_t stream_id, int64
     return 0;
 }
 
-extern "C" int64_t mlmcb200_moments_weighted_workspace_bytes(int64_t n_rows, int32_t n_rep) {
-    if (n_rows < 0 || n_rep < 1) return -1;
+// column groups of 104: [ok, rm, d_0 .. d_{R-1}, d_0^2 .. d_{R-1}^2]
+static int weighted_col_groups(int size) { return (2 + 2 * size + kBsOutPitch - 1) / kBsOutPitch; }
+
+extern "C" int64_t mlmcb200_moments_weighted_workspace_bytes(int64_t n_rows, int32_t n_rep, int32_t size) {
+    if (n_rows < 0 || n_rep < 1 || size < 1) return -1;
     int groups = 0, per = 0;
     weighted_groups(n_rep, &groups, &per);
-    return (int64_t)groups * weighted_grid_x(n_rows) * (kBsMaxRepBlocks * 8 * kBsOutPitch) * (int64_t)sizeof(double);
+    return (int64_t)weighted_col_groups(size) * groups * weighted_grid_x(n_rows) * (kBsMaxRepBlocks * 8 * kBsOutPitch) *
+           (int64_t)sizeof(double);
 }
 
-extern "C" int32_t mlmcb200_moments_weighted_max_size(void) { return (8 * kBsMaxColBlocks - 2) / 2; }
+// the limit of the gather kernel for scalar quantities (one pass of 104 columns holds 51 moments, wider bases take
+// ceil((2 + 2 R) / 104) passes)
+extern "C" int32_t mlmcb200_moments_weighted_max_size(void) { return 226; }
 
 extern "C" int mlmcb200_moments_accumulate_weighted(const mlmcb200_basis_t* basis, const double* pairs, int64_t n_rows,
                                                     int64_t stride_n, int32_t has_coarse, const uint8_t* counts,
@@ -398,8 +417,9 @@ extern "C" int mlmcb200_moments_accumulate_weighted(const mlmcb200_basis_t* basi
                                                     int64_t acc_rep_stride, void* workspace, int64_t workspace_bytes,
                                                     void* stream) {
     if (check_basis(basis) != 0) return -1;
-    MB_REQUIRE(basis->kind == MLMCB200_LEGENDRE && basis->size <= mlmcb200_moments_weighted_max_size(),
-               "moments_accumulate_weighted: Legendre bases of at most %d moments (kind=%d size=%d)",
+    MB_REQUIRE((basis->kind == MLMCB200_LEGENDRE || basis->kind == MLMCB200_MONOMIAL) &&
+                   basis->size <= mlmcb200_moments_weighted_max_size(),
+               "moments_accumulate_weighted: Legendre / Monomial bases of at most %d moments (kind=%d size=%d)",
                mlmcb200_moments_weighted_max_size(), basis->kind, basis->size);
     MB_REQUIRE(n_rows >= 0 && n_rep >= 1 && acc != nullptr && workspace != nullptr && counts != nullptr,
                "moments_accumulate_weighted: bad arguments");
@@ -411,7 +431,7 @@ extern "C" int mlmcb200_moments_accumulate_weighted(const mlmcb200_basis_t* basi
                "aligned, stride_n=%lld)", (long long)stride_n);
     if (n_rows == 0) return 0;
     MB_REQUIRE(pairs != nullptr, "moments_accumulate_weighted: null pairs");
-    MB_REQUIRE(workspace_bytes >= mlmcb200_moments_weighted_workspace_bytes(n_rows, n_rep),
+    MB_REQUIRE(workspace_bytes >= mlmcb200_moments_weighted_workspace_bytes(n_rows, n_rep, basis->size),
                "moments_accumulate_weighted: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     WeightedArgs a;
@@ -424,24 +444,28 @@ extern "C" int mlmcb200_moments_accumulate_weighted(const mlmcb200_basis_t* basi
     a.n_rep = n_rep;
     int groups = 0;
     weighted_groups(n_rep, &groups, &a.reps_per_group);
-    a.n_col_blocks = (2 + 2 * basis->size + 7) / 8;
+    a.monomial = basis->kind == MLMCB200_MONOMIAL ? 1 : 0;
     a.partial = static_cast<double*>(workspace);
     const size_t smem = (size_t)(kBsTile * kBsLD + 8) * sizeof(double) + (size_t)kBsMaxRepBlocks * 8 * kBsPitch;
-    const dim3 grid((unsigned)weighted_grid_x(n_rows), (unsigned)groups);
-    if (has_coarse) {
-        MB_CUDA_OK(cudaFuncSetAttribute(weighted_moments_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-        weighted_moments_kernel<true><<<grid, kBsThreads, smem, st>>>(a);
-    } else {
-        MB_CUDA_OK(cudaFuncSetAttribute(weighted_moments_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-        weighted_moments_kernel<false><<<grid, kBsThreads, smem, st>>>(a);
+    const int col_groups = weighted_col_groups(basis->size);
+    const dim3 grid((unsigned)weighted_grid_x(n_rows), (unsigned)groups, (unsigned)col_groups);
+#define MB_LAUNCH(C, M)                                                                                          \
+    {                                                                                                            \
+        MB_CUDA_OK(cudaFuncSetAttribute(weighted_moments_kernel<C, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        (int)smem));                                                             \
+        weighted_moments_kernel<C, M><<<grid, kBsThreads, smem, st>>>(a);                                        \
     }
+    if (has_coarse) {
+        if (col_groups > 1) MB_LAUNCH(true, true) else MB_LAUNCH(true, false)
+    } else {
+        if (col_groups > 1) MB_LAUNCH(false, true) else MB_LAUNCH(false, false)
+    }
+#undef MB_LAUNCH
     MB_CUDA_OK(cudaGetLastError());
     const int64_t outs = (int64_t)n_rep * (2 + 2 * basis->size);
     weighted_finish_kernel<<<(unsigned)((outs + 127) / 128), 128, 0, st>>>(a.partial, (int)grid.x, n_rep,
-                                                                           a.reps_per_group, basis->size, acc,
-                                                                           acc_rep_stride);
+                                                                           a.reps_per_group, groups, basis->size,
+                                                                           a.monomial, acc, acc_rep_stride);
     MB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -51,14 +51,16 @@ def test_argument_errors_are_reported_without_a_gpu():
     rc = lib.mlmcb200_density_eval(ctypes.byref(good), one, 5, one, 8, one, None)
     assert rc < 0 and b"n_coef" in lib.mlmcb200_last_error()
     # one-pass bootstrap (csrc/bootstrap.cu)
-    assert lib.mlmcb200_moments_weighted_max_size() == 51 and 0 < lib.mlmcb200_resample_counts_block_rows() <= 196608
-    assert lib.mlmcb200_moments_weighted_workspace_bytes(10_000_000, 300) == \
-        3 * lib.mlmcb200_moments_weighted_workspace_bytes(10_000_000, 100) > 0
-    mono = _native.make_basis(_native.MONOMIAL, 7, (2.0, 6.0), (0.0, 1.0))
-    wide = _native.make_basis(_native.LEGENDRE, 52, (2.0, 6.0), (-1.0, 1.0))
-    for b in (mono, wide):
-        rc = lib.mlmcb200_moments_accumulate_weighted(ctypes.byref(b), one, 10, 2, 1, one, 16, 3, one, 200, one, 1 << 30, None)
-        assert rc < 0 and b"Legendre bases of at most 51" in lib.mlmcb200_last_error()
+    assert lib.mlmcb200_moments_weighted_max_size() == 226 and 0 < lib.mlmcb200_resample_counts_block_rows() <= 196608
+    assert lib.mlmcb200_moments_weighted_workspace_bytes(10_000_000, 300, 50) == \
+        3 * lib.mlmcb200_moments_weighted_workspace_bytes(10_000_000, 100, 50) > 0
+    assert lib.mlmcb200_moments_weighted_workspace_bytes(10_000_000, 100, 100) == \
+        2 * lib.mlmcb200_moments_weighted_workspace_bytes(10_000_000, 100, 51)         # 202 columns: two groups of 104
+    four = _native.make_basis(_native.FOURIER, 7, (2.0, 6.0), (0.0, 6.283185307179586))
+    wide = _native.make_basis(_native.LEGENDRE, 227, (2.0, 6.0), (-1.0, 1.0))
+    for b in (four, wide):
+        rc = lib.mlmcb200_moments_accumulate_weighted(ctypes.byref(b), one, 10, 2, 1, one, 16, 3, one, 600, one, 1 << 30, None)
+        assert rc < 0 and b"Monomial bases of at most 226" in lib.mlmcb200_last_error()
     rc = lib.mlmcb200_moments_accumulate_weighted(ctypes.byref(good), one, 10, 3, 1, ctypes.c_void_p(16), 16, 3, one, 200, one,
                                                   1 << 30, None)
     assert rc < 0 and b"storage order" in lib.mlmcb200_last_error()
@@ -90,8 +92,12 @@ def test_bootstrap_path_choice_is_world_size_independent():
     assert not qe._weighted_bootstrap_applies("gather", leg, x, sizes, 1000, 1000.0, 100)
     assert not qe._weighted_bootstrap_applies("weighted", leg, x, np.full(7, 9000), 1000, 9000.0, 100)   # byte counters
     wide = _native.make_basis(_native.LEGENDRE, 60, (-3.0, 3.0), (-1.0, 1.0))
+    huge = _native.make_basis(_native.LEGENDRE, 240, (-3.0, 3.0), (-1.0, 1.0))
+    mono = _native.make_basis(_native.MONOMIAL, 9, (-3.0, 3.0), (0.0, 1.0))
     four = _native.make_basis(_native.FOURIER, 9, (-3.0, 3.0), (0.0, 6.283185307179586))
-    assert not qe._weighted_bootstrap_applies("weighted", wide, x, sizes, 1000, 1000.0, 100)
+    assert qe._weighted_bootstrap_applies(None, wide, x, sizes, 1000, 1000.0, 100)           # two column groups
+    assert qe._weighted_bootstrap_applies(None, mono, x, sizes, 1000, 1000.0, 100)
+    assert not qe._weighted_bootstrap_applies("weighted", huge, x, sizes, 1000, 1000.0, 100)
     assert not qe._weighted_bootstrap_applies("weighted", four, x, sizes, 1000, 1000.0, 100)
     vec = torch.zeros((1000, 2, 3), dtype=torch.float64).permute(2, 0, 1)
     assert not qe._weighted_bootstrap_applies("weighted", leg, vec, sizes, 1000, 1000.0, 100)

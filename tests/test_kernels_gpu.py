@@ -596,10 +596,14 @@ def test_resample_counts_are_the_multiplicities_of_the_indices(n_rows, P, ks):
         assert np.array_equal(counts[b, :n_rows].cpu().numpy().astype(np.int64), want)
 
 
-@pytest.mark.parametrize("R,n_rep,level0,log,n_rows", [(50, 100, False, False, 300_001), (51, 13, True, False, 70_000),
-                                                       (7, 300, False, True, 20_011), (1, 5, False, False, 999),
-                                                       (25, 16, True, True, 4096), (12, 40, False, False, 100)])
-def test_weighted_sums_equal_the_gather_kernel(R, n_rep, level0, log, n_rows):
+@pytest.mark.parametrize("R,n_rep,level0,log,n_rows,kind", [
+    (50, 100, False, False, 300_001, "legendre"), (51, 13, True, False, 70_000, "legendre"),
+    (7, 300, False, True, 20_011, "legendre"), (1, 5, False, False, 999, "legendre"),
+    (25, 16, True, True, 4096, "legendre"), (12, 40, False, False, 100, "legendre"),
+    (100, 21, False, False, 50_001, "legendre"), (52, 9, True, False, 30_000, "legendre"),       # two column groups
+    (160, 10, False, False, 9_000, "legendre"),                                                  # four
+    (9, 24, False, False, 40_000, "monomial"), (60, 8, True, True, 20_000, "monomial")])
+def test_weighted_sums_equal_the_gather_kernel(R, n_rep, level0, log, n_rows, kind):
     """mlmcb200_moments_accumulate_weighted (all replicates in one pass: multiplicities x moment differences on DMMA tiles)
     adds what mlmcb200_moments_accumulate_resampled adds for the rows behind the multiplicities; samples outside the
     domain / NaN are counted as removed in both (mask_nan_samples, quantity_estimate.py:6-14)."""
@@ -614,7 +618,7 @@ def test_weighted_sums_equal_the_gather_kernel(R, n_rep, level0, log, n_rows):
     if level0:
         rows = rows[:, :1]
     domain = (0.05, 12.0) if log else (-3.0, 3.0)
-    basis = to_struct(orc.Basis("legendre", R, domain, log=log))
+    basis = to_struct(orc.Basis(kind, R, domain, log=log))
     x = torch.from_numpy(np.ascontiguousarray(rows)).to(dev()).reshape(n_rows, rows.shape[1], 1).permute(2, 0, 1)
     P = max(1, -(-n_rows // 131072))
     ks = rng.integers(max(1, n_rows // 2), 2 * n_rows, size=n_rep)
