@@ -130,7 +130,7 @@ int mlmcb200_moments_accumulate_resampled(const mlmcb200_basis_t* basis, const d
                                           void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
- * Bootstrap re-sampling of one level in ONE pass over its rows (scalar quantity, Legendre or Monomial basis of at most
+ * Bootstrap re-sampling of one level in ONE pass over its rows (scalar quantity; Legendre, Monomial or Fourier basis of at most
  * mlmcb200_moments_weighted_max_size() moments; bases of more than 51 moments take ceil((2 + 2 R) / 104) passes, one
  * per group of 104 result columns): the same replicate loop as above (mlmc/estimator.py:171-218,
  * mlmc/quantity/quantity.py:307-322), written as the weighted sums

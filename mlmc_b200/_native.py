@@ -389,7 +389,7 @@ def weighted_max_size():
 
 
 def moments_accumulate_weighted(basis, x, counts, acc_level):
-    """All bootstrap replicates of one level in one pass (scalar quantity, Legendre / Monomial, size <=
+    """All bootstrap replicates of one level in one pass (scalar quantity, any basis but RAW, size <=
     ``weighted_max_size()``).
 
     x [1, n_rows, S] in storage order; counts [B, stride] uint8 (``resample_counts``); acc_level [B, 2 + 2 R] (rows

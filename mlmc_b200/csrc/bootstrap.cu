@@ -54,7 +54,6 @@ struct WeightedArgs {
     int64_t counts_stride;
     int32_t n_rep;              // all replicates of the call
     int32_t reps_per_group;     // multiple of 8, <= 128; group g = replicates [g * reps_per_group, ...)
-    int32_t monomial;           // 1: Monomial basis (t^j: the same two-step recurrence with A = B = 0, no re-scaling)
     double* partial;            // [column group][replicate group][gridDim.x][128][104]
 };
 
@@ -119,6 +118,48 @@ __device__ __forceinline__ void produce_moments(int R, bool mono, int c0, double
     }
 }
 
+// Fourier basis (columns 1, cos t, sin t, cos 2t, sin 2t, ...: mlmc/moments.py Fourier.eval_all): the two threads of a
+// sample take the odd and the even harmonics, each rotating its (cos, sin) pair by the exact double angle 2t per step.
+template <bool COARSE, int PARITY, bool MULTI>
+__device__ __forceinline__ void produce_fourier(int R, int c0, double tf, double tc, bool good, double* row) {
+    auto put = [&](int col, double v) {
+        if (!MULTI) row[col] = v;
+        else if ((unsigned)(col - c0) < (unsigned)kBsOutPitch) row[col - c0] = v;
+    };
+    if (PARITY == 0) {                                   // column 0 is the literal 1: its difference vanishes
+        const double d = COARSE ? 0.0 : (good ? 1.0 : 0.0);
+        put(2, d);
+        put(2 + R, d * d);
+    }
+    if (R < 2) return;
+    double sf1 = 0.0, cf1 = 0.0, sc1 = 0.0, cc1 = 0.0;   // a dropped sample keeps zeros and so writes zeros
+    if (good) {
+        sincos_bounded(tf, &sf1, &cf1);
+        if (COARSE) sincos_bounded(tc, &sc1, &cc1);
+    }
+    const double cf2 = fma(cf1, cf1, -(sf1 * sf1)), sf2 = 2.0 * sf1 * cf1;
+    const double cc2 = fma(cc1, cc1, -(sc1 * sc1)), sc2 = 2.0 * sc1 * cc1;
+    double cf = PARITY ? cf2 : cf1, sf = PARITY ? sf2 : sf1, cc = PARITY ? cc2 : cc1, sc = PARITY ? sc2 : sc1;
+    for (int k = 1 + PARITY; 2 * k - 1 < R; k += 2) {     // harmonic k: columns 2k - 1 (cos), 2k (sin)
+        const double dcos = COARSE ? cf - cc : cf;
+        put(2 + 2 * k - 1, dcos);
+        put(2 + R + 2 * k - 1, dcos * dcos);
+        if (2 * k < R) {
+            const double dsin = COARSE ? sf - sc : sf;
+            put(2 + 2 * k, dsin);
+            put(2 + R + 2 * k, dsin * dsin);
+        }
+        const double nf = fma(cf, cf2, -(sf * sf2));
+        sf = fma(sf, cf2, cf * sf2);
+        cf = nf;
+        if (COARSE) {
+            const double nc = fma(cc, cc2, -(sc * sc2));
+            sc = fma(sc, cc2, cc * sc2);
+            cc = nc;
+        }
+    }
+}
+
 template <bool COARSE, bool MULTI>
 __global__ void __launch_bounds__(kBsThreads, 1)
 weighted_moments_kernel(const WeightedArgs a) {
@@ -129,7 +170,7 @@ weighted_moments_kernel(const WeightedArgs a) {
     const int R = a.basis.size;
     const int c0 = MULTI ? (int)blockIdx.z * kBsOutPitch : 0;                    // first column of this CTA's group
     const int ncb = (min(kBsOutPitch, 2 + 2 * R - c0) + 7) >> 3;
-    const bool mono = a.monomial != 0;
+    const bool mono = a.basis.kind == MLMCB200_MONOMIAL, fourier = a.basis.kind == MLMCB200_FOURIER;
     const int rep0 = blockIdx.y * a.reps_per_group;
     const int n_rep = min(a.reps_per_group, a.n_rep - rep0);                     // replicates of this group
     const int nbb = (n_rep + 7) >> 3;
@@ -207,18 +248,20 @@ weighted_moments_kernel(const WeightedArgs a) {
                                                     : moments_finite(a.basis, tc);
                 good = good && good_c;
             }
-            good = good && in;
+            good = (good || (fourier && R == 1)) && in;   // a Fourier basis of one function is the literal 1: nothing to drop
             tf = good ? tf : 0.0;
             tc = good ? tc : 0.0;
             double* const row = X + (size_t)ps * kBsLD + ((ps >> 2) & 3);
-            if (parity == 0) {
-                if (c0 == 0) {
-                    row[0] = good ? 1.0 : 0.0;
-                    row[1] = (in && !good) ? 1.0 : 0.0;
-                }
-                produce_moments<COARSE, 0, MULTI>(R, mono, c0, tf, tc, good, row);
+            if (parity == 0 && c0 == 0) {
+                row[0] = good ? 1.0 : 0.0;
+                row[1] = (in && !good) ? 1.0 : 0.0;
+            }
+            if (fourier) {                                // uniform
+                if (parity == 0) produce_fourier<COARSE, 0, MULTI>(R, c0, tf, tc, good, row);
+                else produce_fourier<COARSE, 1, MULTI>(R, c0, tf, tc, good, row);
             } else {
-                produce_moments<COARSE, 1, MULTI>(R, mono, c0, tf, tc, good, row);
+                if (parity == 0) produce_moments<COARSE, 0, MULTI>(R, mono, c0, tf, tc, good, row);
+                else produce_moments<COARSE, 1, MULTI>(R, mono, c0, tf, tc, good, row);
             }
         }
         __syncthreads();
@@ -256,9 +299,10 @@ weighted_moments_kernel(const WeightedArgs a) {
     }
 }
 
-// acc[b][...] += (sum over the CTAs' partials, in CTA order) re-scaled to P_k = alpha_k W_k; one thread per (b, column)
+// acc[b][...] += (sum over the CTAs' partials, in CTA order), Legendre re-scaled to P_k = alpha_k W_k; one thread per
+// (b, column)
 __global__ void weighted_finish_kernel(const double* __restrict__ partial, int n_partials, int n_rep, int reps_per_group,
-                                       int n_rep_groups, int R, int mono, double* __restrict__ acc,
+                                       int n_rep_groups, int R, int unscaled, double* __restrict__ acc,
                                        int64_t acc_rep_stride) {
     const int n_cols = 2 + 2 * R;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -282,9 +326,9 @@ __global__ void weighted_finish_kernel(const double* __restrict__ partial, int n
     if (col < 2) {
         dst[col] += s;
     } else if (col < 2 + R) {
-        dst[col] += mono ? s : s * kLegAlpha[col - 2];
+        dst[col] += unscaled ? s : s * kLegAlpha[col - 2];
     } else {
-        const double al = mono ? 1.0 : kLegAlpha[col - 2 - R];
+        const double al = unscaled ? 1.0 : kLegAlpha[col - 2 - R];
         dst[col] += s * (al * al);
     }
 }
@@ -417,9 +461,8 @@ extern "C" int mlmcb200_moments_accumulate_weighted(const mlmcb200_basis_t* basi
                                                     int64_t acc_rep_stride, void* workspace, int64_t workspace_bytes,
                                                     void* stream) {
     if (check_basis(basis) != 0) return -1;
-    MB_REQUIRE((basis->kind == MLMCB200_LEGENDRE || basis->kind == MLMCB200_MONOMIAL) &&
-                   basis->size <= mlmcb200_moments_weighted_max_size(),
-               "moments_accumulate_weighted: Legendre / Monomial bases of at most %d moments (kind=%d size=%d)",
+    MB_REQUIRE(basis->kind != MLMCB200_RAW && basis->size <= mlmcb200_moments_weighted_max_size(),
+               "moments_accumulate_weighted: Legendre / Monomial / Fourier bases of at most %d moments (kind=%d size=%d)",
                mlmcb200_moments_weighted_max_size(), basis->kind, basis->size);
     MB_REQUIRE(n_rows >= 0 && n_rep >= 1 && acc != nullptr && workspace != nullptr && counts != nullptr,
                "moments_accumulate_weighted: bad arguments");
@@ -444,7 +487,6 @@ extern "C" int mlmcb200_moments_accumulate_weighted(const mlmcb200_basis_t* basi
     a.n_rep = n_rep;
     int groups = 0;
     weighted_groups(n_rep, &groups, &a.reps_per_group);
-    a.monomial = basis->kind == MLMCB200_MONOMIAL ? 1 : 0;
     a.partial = static_cast<double*>(workspace);
     const size_t smem = (size_t)(kBsTile * kBsLD + 8) * sizeof(double) + (size_t)kBsMaxRepBlocks * 8 * kBsPitch;
     const int col_groups = weighted_col_groups(basis->size);
@@ -465,7 +507,8 @@ extern "C" int mlmcb200_moments_accumulate_weighted(const mlmcb200_basis_t* basi
     const int64_t outs = (int64_t)n_rep * (2 + 2 * basis->size);
     weighted_finish_kernel<<<(unsigned)((outs + 127) / 128), 128, 0, st>>>(a.partial, (int)grid.x, n_rep,
                                                                            a.reps_per_group, groups, basis->size,
-                                                                           a.monomial, acc, acc_rep_stride);
+                                                                           basis->kind != MLMCB200_LEGENDRE ? 1 : 0, acc,
+                                                                           acc_rep_stride);
     MB_CUDA_OK(cudaGetLastError());
     return 0;
 }

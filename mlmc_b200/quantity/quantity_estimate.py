@@ -393,7 +393,7 @@ def _weighted_bootstrap_applies(method, basis, x, sizes, n_chunk, expected_draws
         raise ValueError("bootstrap method must be None, 'weighted' or 'gather'")
     M, n, S = x.shape
     sn, ss = x.stride(1), x.stride(2)
-    ok = (basis.kind in (_native.LEGENDRE, _native.MONOMIAL) and basis.size <= _native.weighted_max_size() and M == 1 and n_chunk >= 1
+    ok = (basis.kind in (_native.LEGENDRE, _native.MONOMIAL, _native.FOURIER) and basis.size <= _native.weighted_max_size() and M == 1 and n_chunk >= 1
           and (S == 1 or (sn == 2 and ss == 1 and x.data_ptr() % 16 == 0))
           and expected_draws <= 6 * n_chunk and 0 < int(sizes.max()) <= 8 * n_chunk)
     if not ok or method == "weighted":
