@@ -498,7 +498,9 @@ def bootstrap_moments(quantity, moments_fn, sample_vector, n_subsamples, seed=No
             stride = -(-n_chunk // 16) * 16
             # multiplicities of as many replicates at a time as a quarter of the free device memory holds (>= 2 GB), in
             # whole groups of the kernel (104 replicates) where possible: few replicates per pass waste the tensor tiles
-            budget = max(2 << 30, torch.cuda.mem_get_info(device)[0] // 4)
+            budget = 2 << 30
+            if B * stride > budget:                                           # (the query synchronises: only when needed)
+                budget = max(budget, torch.cuda.mem_get_info(device)[0] // 4)
             group = min(B, max(8, (budget // stride) // 8 * 8))
             if group < B and group > 104:
                 group = group // 104 * 104
