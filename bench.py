@@ -838,6 +838,36 @@ def bench_bootstrap(ctx, storage, value, n_rep=100):
         finally:
             os.environ.pop("MLMCB200_BOOTSTRAP", None)
     out["replicate_sample_moments_per_s"] = n_rep * float(sum(n)) * N_MOMENTS / (out["weighted_ms"] * 1e-3)
+    # the two kernels of the one-pass path alone, on level 1 (fine + coarse): multiplicities, then the weighted sums
+    # against the FP64 tensor roofline measured in this run
+    torch, nat, dev = ctx.torch, ctx.nat, ctx.device
+    rows = next(r for l, r in storage.device_chunks([1], dev, keep_resident=True))
+    x = rows.permute(2, 0, 1)
+    n1 = int(rows.shape[0])
+    P = max(1, -(-n1 // 131072))
+    edges = (np.arange(P + 1, dtype=np.int64) * n1) // P
+    rng = np.random.default_rng(0)
+    cum_h = np.zeros((n_rep, P + 1), dtype=np.int64)
+    for b in range(n_rep):
+        np.cumsum(rng.multinomial(n1, np.diff(edges) / n1), out=cum_h[b, 1:])
+    cum = torch.from_numpy(cum_h).to(dev)
+    basis = est._moments_fn.basis_struct()
+    counts = nat.resample_counts(1, 1, n1, cum, n1, dev)
+    acc = torch.zeros((n_rep, 2 + 2 * N_MOMENTS), dtype=torch.float64, device=dev)
+    ms_counts = ctx.timed(lambda: nat.resample_counts(1, 1, n1, cum, n1, dev), 3, warmup=1)
+    ms_w = ctx.timed(lambda: nat.moments_accumulate_weighted(basis, x, counts, acc), 3, warmup=1)
+    peak = nat.fp64_peak(1)
+    cols, reps = 8 * (-(-(2 + 2 * N_MOMENTS) // 8)), 8 * (-(-n_rep // 8))
+    out["kernels_level1"] = {
+        "resample_counts_ms": ms_counts, "weighted_sums_ms": ms_w,
+        "roofline": {"bound": "fp64 tensor (DMMA m8n8k4)", "peak": peak / 1e12, "unit": "TFLOP/s",
+                     "executed": 2.0 * n1 * cols * reps / (ms_w * 1e-3) / 1e12,
+                     "useful": 2.0 * n1 * (2 * N_MOMENTS) * n_rep / (ms_w * 1e-3) / 1e12,
+                     "frac": 2.0 * n1 * cols * reps / (ms_w * 1e-3) / peak,
+                     "frac_useful": 2.0 * n1 * (2 * N_MOMENTS) * n_rep / (ms_w * 1e-3) / peak,
+                     "algorithmic_bytes": n1 * (16 + n_rep),
+                     "hbm_gbs": n1 * (16 + n_rep) / (ms_w * 1e-3) / 1e9,
+                     "note": "useful = 2 flop x rows x 2R columns x replicates; executed adds the padding to 104 x 104"}}
     return out
 
 
