@@ -938,6 +938,10 @@ def bench_cfg5(ctx):
     # two warm-up calls: the 30 MB result goes to pooled pinned buffers and two of them alternate (the previous result
     # is still referenced while the next call runs); pinning the second one inside the timed calls cost 10-20 ms
     ms_e2e, _ = ctx.timed_wall(staged, 3, warmup=2)
+    # the same estimate with the samples staged from an HDF5 file in the reference's layout (BASELINE configs[4]:
+    # "per-location mean/var from HDF-staged samples"): Levels/<l>/collected_values chunks -> two pinned staging buffers
+    # -> device -> kernels, nothing resident
+    hdf = hdf_staged_cfg5(ctx, levels, steps, spec, fn, qm)
     # oracle on 50 locations spread over the field (sample mask of all locations applied first)
     ob = orc.Basis("fourier", 32, dom)
     pick = np.arange(0, M, 200)
@@ -957,11 +961,42 @@ def bench_cfg5(ctx):
     return {"workload": "cfg5: field of 1e4 locations x 5 levels (4096..256 samples), Fourier R=32, per-location mean/var",
             "resident_ms": ms_res, "e2e_ms": ms_e2e, "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": (2 * 5 + 2) * M * 32 * 8,
             "sample_moments_per_s_resident": units / (ms_res * 1e-3), "sample_moments_per_s_e2e": units / (ms_e2e * 1e-3),
-            "hbm_gbs_resident": n_bytes / (ms_res * 1e-3) / 1e9,
+            "hbm_gbs_resident": n_bytes / (ms_res * 1e-3) / 1e9, "hdf_staged": hdf,
             "cpu": {"kind": "port", "cores": 1, "sample_moments_per_s": sum(len(s) for s in sl) * len(pick) * 32 / cpu_s,
                     "sample": "50 of the 1e4 locations, all samples (oracle port, 512-row chunks)"},
             "n_samples": [int(v) for v in qm.n_samples], "n_rm_samples": [int(v) for v in qm.n_rm_samples],
             "max_rel_l_means_vs_oracle": max_rel(got_means, o.l_means), "max_rel_l_vars_vs_oracle": max_rel(got_vars, o.l_vars)}
+
+
+def hdf_staged_cfg5(ctx, levels, steps, spec, fn, qm_resident):
+    """cfg5 read from an HDF5 sample file (written here in the reference's structure by the fixture writer, read by
+    ``SampleStorageHDF``: h5py when importable, else the built-in reader).  The file sits in the page cache: the number is
+    the read side's own cost (HDF5 chunk lookup + copy into pinned staging) plus the PCIe copy, not the disk's."""
+    import shutil
+    import tempfile
+    from mlmc_b200.sample_storage import SampleStorageHDF
+    from mlmc_b200.tool.hdf5_min import write_mlmc_file
+    from mlmc_b200.quantity.quantity import make_root_quantity
+    from mlmc_b200.quantity import quantity_estimate as qe
+    tmp = tempfile.mkdtemp(prefix="mlmcb200_bench_")
+    try:
+        t0 = time.perf_counter()
+        path = write_mlmc_file(os.path.join(tmp, "cfg5.hdf5"), [lv.numpy() for lv in levels], [[h] for h in steps])
+        write_s = time.perf_counter() - t0
+        storage = SampleStorageHDF(path)
+        storage.resident_fraction = 0.0
+        field = make_root_quantity(storage, spec)["field"][0.0]
+        ms, qm = ctx.timed_wall(lambda: qe.estimate_mean(qe.moments(field, fn)), 3, warmup=1)
+        size = os.path.getsize(path)
+        return {"ms": ms, "file_bytes": size, "file_gbs": size / (ms * 1e-3) / 1e9, "backend": storage.backend,
+                "fixture_write_s": write_s, "page_cache": True,
+                "max_rel_l_means_vs_resident": max_rel(qm.l_means, qm_resident.l_means),
+                "max_rel_l_vars_vs_resident": max_rel(qm.l_vars, qm_resident.l_vars),
+                "n_samples": [int(v) for v in qm.n_samples]}
+    except Exception as exc:                                  # an optional leg must not cost the bench line
+        return {"error": "%s: %s" % (type(exc).__name__, exc)}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def run_gpu_arm(args):

@@ -228,15 +228,60 @@ class RowSource:
         lo, hi = max(0, min(lo, len(self))), max(0, min(hi, len(self)))
         return RowSource(self._rows, self._drop, self._lo + lo, self._lo + max(lo, hi))
 
-    def read_into(self, lo, hi, out):
-        lo, hi = self._lo + lo, self._lo + hi
+    def _read_part(self, lo, hi, out):
         if hasattr(self._rows, "read_rows"):
-            if self._drop:
-                out[...] = self._rows.read_rows(lo, hi)[:, :1, :]
+            if self._drop and getattr(self._rows, "keeps_items", False):
+                self._rows.read_rows(lo, hi, out=out, keep_items=self.shape[2])    # fine row only, straight from the file
+            elif self._drop:
+                # the stored zero coarse row is skipped block by block (a temporary of a few MB, not of the whole piece)
+                step = max(1, (4 << 20) // (16 * self.shape[2]))
+                for a in range(lo, hi, step):
+                    b = min(hi, a + step)
+                    out[a - lo:b - lo] = self._rows.read_rows(a, b)[:, :1, :]
             else:
                 self._rows.read_rows(lo, hi, out=out)
         else:
             out[...] = self._rows[lo:hi, :1, :] if self._drop else self._rows[lo:hi]
+
+    def read_into(self, lo, hi, out):
+        """Copies out of the page cache run at a few GB/s per thread -- a tenth of the PCIe rate behind them -- so a
+        piece is cut into row ranges that a small thread pool copies concurrently (NumPy releases the GIL in the copy
+        loops; the h5py backend serialises on its own lock and stays single-threaded)."""
+        lo, hi = self._lo + lo, self._lo + hi
+        n_bytes = (hi - lo) * self.shape[1] * self.shape[2] * 8
+        threads = _read_threads()
+        if threads <= 1 or n_bytes < (8 << 20) or not getattr(self._rows, "parallel_reads", True):
+            self._read_part(lo, hi, out)
+            return
+        parts = min(threads, max(1, n_bytes // (4 << 20)), hi - lo)
+        edges = [lo + (hi - lo) * i // parts for i in range(parts + 1)]
+        futures = [_read_pool().submit(self._read_part, edges[i], edges[i + 1], out[edges[i] - lo:edges[i + 1] - lo])
+                   for i in range(parts) if edges[i + 1] > edges[i]]
+        for f in futures:
+            f.result()
+
+
+_pool = {}
+
+
+def _read_threads():
+    """Threads of the file -> pinned staging copy (``MLMCB200_READ_THREADS``; default: up to 16, at most the cores)."""
+    n = os.environ.get("MLMCB200_READ_THREADS")
+    if n is not None:
+        return max(1, int(n))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    return max(1, min(16, cores))
+
+
+def _read_pool():
+    n = _read_threads()
+    if _pool.get("n") != n:
+        from concurrent.futures import ThreadPoolExecutor
+        _pool["pool"], _pool["n"] = ThreadPoolExecutor(max_workers=n, thread_name_prefix="mlmcb200-read"), n
+    return _pool["pool"]
 
 
 _staging = {}
@@ -523,6 +568,7 @@ class NpyStorage(SampleStorage):
 
 class _H5pyRows:
     """``read_rows`` over an h5py dataset of one level (the file is opened per read, like the reference does)."""
+    parallel_reads = False          # libhdf5 serialises on a global lock
 
     def __init__(self, h5py, path, name, shape):
         self._h5py, self._path, self._name, self.shape = h5py, path, name, shape
@@ -552,12 +598,14 @@ class _H5pyRows:
 
 class _MinRows(_H5pyRows):
     """The same over ``mlmc_b200.tool.hdf5_min`` (memory-mapped file, no h5py)."""
+    parallel_reads = True
 
     def __init__(self, dataset, shape):
         self._dset, self.shape = dataset, shape
+        self.keeps_items = not dataset._filters       # level 0 without its zero coarse row, straight from the mapping
 
-    def read_rows(self, lo=0, hi=None, out=None):
-        return self._dset.read_rows(lo, hi, out=out)
+    def read_rows(self, lo=0, hi=None, out=None, keep_items=None):
+        return self._dset.read_rows(lo, hi, out=out, keep_items=keep_items)
 
 
 class SampleStorageHDF(SampleStorage):

@@ -19,6 +19,7 @@ chunk).  ``SampleStorageHDF`` prefers h5py when it is importable.
 ``write_mlmc_file`` writes the reference's file structure for tests and benchmarks (old-style groups, chunked
 ``collected_values``, ``level_parameters`` / ``n_ops_estimate`` attributes).
 """
+import bisect
 import mmap
 import struct
 import zlib
@@ -283,6 +284,7 @@ class Dataset(_Object):
             if self._layout[1] != UNDEF:
                 self._f._walk_chunk_btree(self._layout[1], len(self._layout[2]) + 1, entries)
             entries.sort()
+            self._index_firsts = [e[0] for e in entries]
             self._chunk_index = entries
         return self._chunk_index
 
@@ -301,9 +303,12 @@ class Dataset(_Object):
                 raise Unsupported("HDF5 filter %d" % fid)
         return raw
 
-    def read_rows(self, lo=0, hi=None, out=None):
+    def read_rows(self, lo=0, hi=None, out=None, keep_items=None):
         """Elements ``[lo, hi)`` along the first axis as an array ``[hi - lo, *shape[1:], *element subarray shape]``.
-        ``out``: optional C-contiguous array of that shape and base dtype (e.g. a pinned staging buffer) to fill."""
+        ``out``: optional C-contiguous array of that shape and base dtype (e.g. a pinned staging buffer) to fill.
+        ``keep_items`` (with ``out``; unfiltered chunked or contiguous data): only the first ``keep_items`` base items of
+        every element are copied, ``out`` holds ``(hi - lo) * keep_items`` items -- level 0 of an MLMC file without its
+        stored zero coarse row, straight from the file mapping."""
         n = self.shape[0]
         hi = n if hi is None else min(hi, n)
         lo = max(0, min(lo, hi))
@@ -312,38 +317,71 @@ class Dataset(_Object):
         row_items = int(np.prod(tail, dtype=np.int64)) if tail else 1
         row_bytes = row_items * base.itemsize
         if out is None:
+            if keep_items is not None:
+                raise ValueError("keep_items needs an output array")
             out = np.empty((hi - lo,) + tail, dtype=base)
         flat = out.reshape(-1).view(np.uint8) if out.size else np.empty(0, dtype=np.uint8)
         buf = self._f._buf
         kind = self._layout[0]
         if hi == lo:
             return out
+        keep_bytes = row_bytes if keep_items is None else int(keep_items) * base.itemsize
+        if keep_bytes != row_bytes and (self._filters or not 0 < keep_bytes < row_bytes):
+            raise Unsupported("keep_items on filtered chunks / out of range")
+        if flat.size != (hi - lo) * keep_bytes:
+            raise ValueError("output array of the wrong size")
+        rows_out = flat.reshape(hi - lo, keep_bytes)              # one row of kept bytes per element
+
+        def put(a, b, src, first):
+            """rows [a, b) from ``src`` = the stored bytes of the elements first, first + 1, ..."""
+            if keep_bytes == row_bytes:
+                flat[(a - lo) * row_bytes:(b - lo) * row_bytes] = src[(a - first) * row_bytes:(b - first) * row_bytes]
+            else:
+                rows_out[a - lo:b - lo] = src.reshape(-1, row_bytes)[a - first:b - first, :keep_bytes]
+
         if kind in ("contiguous", "compact"):
             start = self._layout[1] if kind == "compact" else self._f._base + self._layout[1]
             if kind == "contiguous" and self._layout[1] == UNDEF:
                 flat[:] = 0
             else:
-                flat[:] = np.frombuffer(buf, dtype=np.uint8, count=(hi - lo) * row_bytes, offset=start + lo * row_bytes)
+                put(lo, hi, np.frombuffer(buf, dtype=np.uint8, count=(hi - lo) * row_bytes, offset=start + lo * row_bytes), lo)
             return out
         chunk_dims = self._layout[2]
         if any(c != s for c, s in zip(chunk_dims[1:], self.shape[1:])):
             raise Unsupported("chunks that split trailing dimensions")
         c_rows = chunk_dims[0]
-        filled = np.zeros(hi - lo, dtype=bool) if len(self._index()) * c_rows < n else None
-        for first, address, stored, mask in self._index():
-            a, b = max(first, lo), min(first + c_rows, hi, n)
-            if a >= b:
-                continue
+        index = self._index()
+        filled = np.zeros(hi - lo, dtype=bool) if len(index) * c_rows < n else None
+        base_off = self._f._base
+        # first chunk that can overlap [lo, hi): the index is sorted by first row
+        k = max(0, bisect.bisect_right(self._index_firsts, lo) - 1)
+        while k < len(index) and index[k][0] < hi:
+            first, address, stored, mask = index[k]
             if self._filters:
-                raw = self._decode_chunk(bytes(buf[self._f._base + address:self._f._base + address + stored]), mask)
-                src = np.frombuffer(raw, dtype=np.uint8)
-            else:
-                src = np.frombuffer(buf, dtype=np.uint8, count=c_rows * row_bytes, offset=self._f._base + address)
-            flat[(a - lo) * row_bytes:(b - lo) * row_bytes] = src[(a - first) * row_bytes:(b - first) * row_bytes]
-            if filled is not None:
-                filled[a - lo:b - lo] = True
+                a, b = max(first, lo), min(first + c_rows, hi, n)
+                if a < b:
+                    raw = self._decode_chunk(bytes(buf[base_off + address:base_off + address + stored]), mask)
+                    put(a, b, np.frombuffer(raw, dtype=np.uint8), first)
+                    if filled is not None:
+                        filled[a - lo:b - lo] = True
+                k += 1
+                continue
+            # unfiltered chunks written one after the other (the usual case) are ONE copy: a run of chunks that are
+            # consecutive in rows and in the file
+            run_rows = c_rows
+            k2 = k + 1
+            while (k2 < len(index) and index[k2][0] < hi and index[k2][0] == first + run_rows
+                   and index[k2][1] == address + run_rows * row_bytes):
+                run_rows += c_rows
+                k2 += 1
+            a, b = max(first, lo), min(first + run_rows, hi, n)
+            if a < b:
+                put(a, b, np.frombuffer(buf, dtype=np.uint8, count=run_rows * row_bytes, offset=base_off + address), first)
+                if filled is not None:
+                    filled[a - lo:b - lo] = True
+            k = k2
         if filled is not None and not filled.all():                  # unallocated chunks read as the fill value (0)
-            out[~filled] = 0
+            rows_out[~filled] = 0
         return out
 
     def __getitem__(self, key):

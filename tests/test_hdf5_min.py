@@ -155,3 +155,38 @@ def test_h5py_written_file_reads_identically(tmp_path):
         for l, rows in enumerate(levels):
             assert np.array_equal(np.asarray(st.level_rows(l)), rows)
             assert np.array_equal(st.level_rows(l)[100:300], rows[100:300])
+
+
+@pytest.mark.parametrize("chunk_rows", [1, 7, 64])
+def test_row_source_reads_in_parallel_and_skips_the_coarse_row(tmp_path, monkeypatch, chunk_rows):
+    """The staged feed's CPU stage (``RowSource.read_into``): a piece is cut into row ranges copied by a thread pool,
+    runs of file-contiguous chunks are one copy each, and level 0 is read without its stored zero coarse row straight
+    from the file mapping (``read_rows(keep_items=...)``) -- same bytes as a plain slice, for unaligned ranges too."""
+    from mlmc_b200.sample_storage import RowSource, SampleStorageHDF
+    from mlmc_b200.tool.hdf5_min import write_mlmc_file
+    rng = np.random.default_rng(chunk_rows)
+    m = 3000                                                       # 48 kB per row: pieces above the 8 MB threshold
+    levels = [rng.normal(size=(400, 2, m)), rng.normal(size=(333, 2, m))]
+    levels[0][:, 1] = 0.0
+    path = write_mlmc_file(str(tmp_path / "s.hdf5"), levels, [[0.5], [0.1]], chunk_rows=chunk_rows)
+    storage = SampleStorageHDF(path, backend="min")
+    for threads in ("1", "5"):
+        monkeypatch.setenv("MLMCB200_READ_THREADS", threads)
+        for level, drop in ((0, True), (0, False), (1, False)):
+            src = RowSource(storage.level_rows(level), drop_coarse=drop)
+            want = levels[level][:, :1] if drop else levels[level]
+            assert src.shape == want.shape
+            for lo, hi in ((0, len(want)), (3, len(want) - 5), (17, 18), (len(want) - 1, len(want))):
+                out = np.full((hi - lo,) + want.shape[1:], np.nan)
+                src.read_into(lo, hi, out)
+                assert np.array_equal(out, want[lo:hi])
+            part = src.slice_rows(10, 300)
+            out = np.empty((290,) + want.shape[1:])
+            part.read_into(0, 290, out)
+            assert np.array_equal(out, want[10:300])
+    dset = storage.level_rows(1)._dset
+    from mlmc_b200.tool.hdf5_min import Unsupported
+    with pytest.raises(Unsupported):
+        dset.read_rows(0, 4, out=np.empty((4, m)), keep_items=2 * m + 1)
+    with pytest.raises(ValueError):
+        dset.read_rows(0, 4, out=np.empty((3, m)), keep_items=m)
