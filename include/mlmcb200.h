@@ -314,6 +314,15 @@ int mlmcb200_density_eval(const mlmcb200_basis_t* basis, const double* x, int64_
  * kind >> 4: resident warps per SM to run with (0 = full occupancy). */
 int mlmcb200_fp64_peak(int32_t kind, double* flops_per_s, void* stream);
 
+/*
+ * Host helper of the staged feed (SampleStorageHDF / NpyStorage -> pinned staging buffer -> device; the read side of
+ * mlmc/sample_storage_hdf.py:169-184, mlmc/tool/hdf5.py:353-376): n_rows rows of keep_bytes bytes, src_pitch bytes apart
+ * in src (a file mapping), packed into dst by n_threads host threads.  keep_bytes < src_pitch drops the tail of every
+ * row (level 0 without its stored zero coarse row).  No device work.
+ */
+int mlmcb200_host_copy_rows(void* dst, const void* src, int64_t n_rows, int64_t keep_bytes, int64_t src_pitch,
+                            int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,7 @@ _SIGNATURES = {
                                            _c_i64, _c_vp]),
     "mlmcb200_density_eval": (ctypes.c_int, [ctypes.POINTER(BasisStruct), _c_vp, _c_i64, _c_vp, _c_i32, _c_vp, _c_vp]),
     "mlmcb200_fp64_peak": (ctypes.c_int, [_c_i32, ctypes.POINTER(_c_dbl), _c_vp]),
+    "mlmcb200_host_copy_rows": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i32]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -615,6 +616,14 @@ def density_eval(basis, x, coef):
                                             _ptr(out), _stream()), "density_eval")
     launch_count += 1
     return out
+
+
+def host_copy_rows(dst_address, src_address, n_rows, keep_bytes, src_pitch, n_threads):
+    """Host copy of the staged feed: ``n_rows`` rows of ``keep_bytes`` (``src_pitch`` apart in the source) packed into
+    ``dst`` by ``n_threads`` native threads (the call releases the interpreter lock).  Addresses are plain integers."""
+    _check(load().mlmcb200_host_copy_rows(ctypes.c_void_p(int(dst_address)), ctypes.c_void_p(int(src_address)),
+                                          int(n_rows), int(keep_bytes), int(src_pitch), int(n_threads)),
+           "host_copy_rows")
 
 
 def fp64_peak(kind):

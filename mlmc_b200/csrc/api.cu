@@ -1,6 +1,8 @@
 // Library-wide pieces of the C ABI: error text, device query, FP64 pipe micro-benchmarks.
 #include <stdarg.h>
 #include <string.h>
+#include <thread>
+#include <vector>
 #include "common.cuh"
 
 namespace mlmcb200 {
@@ -159,6 +161,53 @@ extern "C" int mlmcb200_abi_version(void) { return MLMCB200_ABI_VERSION; }
 extern "C" const char* mlmcb200_last_error(void) { return g_error; }
 
 extern "C" int mlmcb200_sm_count(void) { return sm_count(); }
+
+// The CPU stage of the staged feed (file mapping -> pinned staging buffer): n_rows rows of keep_bytes each, src_pitch
+// bytes apart in the source, packed densely into dst, cut over n_threads host threads.  One thread copies a few GB/s out
+// of the page cache, a tenth of the PCIe rate behind it; Python threads lose most of the gain to the interpreter lock.
+extern "C" int mlmcb200_host_copy_rows(void* dst, const void* src, int64_t n_rows, int64_t keep_bytes,
+                                       int64_t src_pitch, int32_t n_threads) {
+    MB_REQUIRE(n_rows >= 0 && keep_bytes >= 0 && src_pitch >= keep_bytes && n_threads >= 1 && n_threads <= 256,
+               "host_copy_rows: bad arguments (n_rows=%lld keep_bytes=%lld src_pitch=%lld n_threads=%d)",
+               (long long)n_rows, (long long)keep_bytes, (long long)src_pitch, n_threads);
+    if (n_rows == 0 || keep_bytes == 0) return 0;
+    MB_REQUIRE(dst != nullptr && src != nullptr, "host_copy_rows: null buffer");
+    char* const d = static_cast<char*>(dst);
+    const char* const s = static_cast<const char*>(src);
+    const bool dense = keep_bytes == src_pitch;
+    const int64_t total = n_rows * keep_bytes;
+    int64_t parts = total / (1 << 20);                               // at least 1 MB per thread
+    if (parts > n_threads) parts = n_threads;
+    if (!dense && parts > n_rows) parts = n_rows;
+    if (parts < 1) parts = 1;
+    auto work = [=](int64_t p) {
+        if (dense) {                                                 // one range of bytes, cut at 64-byte multiples
+            const int64_t lo = (total * p / parts) & ~int64_t(63), hi = p + 1 == parts ? total : (total * (p + 1) / parts) & ~int64_t(63);
+            memcpy(d + lo, s + lo, (size_t)(hi - lo));
+        } else {
+            const int64_t r_lo = n_rows * p / parts, r_hi = n_rows * (p + 1) / parts;
+            for (int64_t r = r_lo; r < r_hi; ++r) memcpy(d + r * keep_bytes, s + r * src_pitch, (size_t)keep_bytes);
+        }
+    };
+    if (parts == 1) {
+        work(0);
+        return 0;
+    }
+    std::vector<std::thread> pool;
+    pool.reserve((size_t)parts - 1);
+    try {
+        for (int64_t p = 1; p < parts; ++p) pool.emplace_back(work, p);
+    } catch (...) {                                                  // could not start a thread: finish what is missing here
+        const int64_t started = (int64_t)pool.size();
+        work(0);
+        for (int64_t p = started + 1; p < parts; ++p) work(p);
+        for (auto& t : pool) t.join();
+        return 0;
+    }
+    work(0);
+    for (auto& t : pool) t.join();
+    return 0;
+}
 
 extern "C" int mlmcb200_fp64_peak(int32_t kind, double* flops_per_s, void* stream) {
     // kind & 15: 0 DFMA (2 loop-invariant operands), 1 DMMA m8n8k4, 2 DFMA with 3 distinct register operands,

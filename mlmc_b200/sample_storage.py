@@ -241,7 +241,15 @@ class RowSource:
             else:
                 self._rows.read_rows(lo, hi, out=out)
         else:
-            out[...] = self._rows[lo:hi, :1, :] if self._drop else self._rows[lo:hi]
+            rows = self._rows
+            copy = _native_copy()
+            n_bytes = (hi - lo) * self.shape[1] * self.shape[2] * 8
+            if (copy is not None and n_bytes >= (2 << 20) and isinstance(rows, np.ndarray) and rows.flags.c_contiguous
+                    and out.flags.c_contiguous and rows.dtype == np.float64 and out.dtype == np.float64):
+                pitch = rows.shape[1] * rows.shape[2] * 8            # memory map of a .npy file: rows `pitch` bytes apart
+                copy(out.ctypes.data, rows[lo:hi].ctypes.data, hi - lo, self.shape[1] * self.shape[2] * 8, pitch)
+            else:
+                out[...] = rows[lo:hi, :1, :] if self._drop else rows[lo:hi]
 
     def read_into(self, lo, hi, out):
         """Copies out of the page cache run at a few GB/s per thread -- a tenth of the PCIe rate behind them -- so a
@@ -250,7 +258,10 @@ class RowSource:
         lo, hi = self._lo + lo, self._lo + hi
         n_bytes = (hi - lo) * self.shape[1] * self.shape[2] * 8
         threads = _read_threads()
-        if threads <= 1 or n_bytes < (8 << 20) or not getattr(self._rows, "parallel_reads", True):
+        native = _native_copy() is not None and (isinstance(self._rows, np.ndarray) or
+                                                 getattr(self._rows, "native_copy", False))
+        if native or threads <= 1 or n_bytes < (8 << 20) or not getattr(self._rows, "parallel_reads", True):
+            # (native: the copy itself is cut over host threads inside the library, without the interpreter lock)
             self._read_part(lo, hi, out)
             return
         parts = min(threads, max(1, n_bytes // (4 << 20)), hi - lo)
@@ -264,8 +275,22 @@ class RowSource:
 _pool = {}
 
 
+def _native_copy():
+    """``f(dst, src, n_rows, keep_bytes, src_pitch)`` over ``mlmcb200_host_copy_rows`` with the configured number of
+    threads, or None when the library cannot be loaded (the readers then copy with NumPy)."""
+    if "copy" not in _pool:
+        try:
+            from . import _native
+            _native.load()
+            _pool["copy"] = lambda d, s, n, k, p: _native.host_copy_rows(d, s, n, k, p, _read_threads())
+        except Exception:
+            _pool["copy"] = None
+    return _pool["copy"]
+
+
 def _read_threads():
-    """Threads of the file -> pinned staging copy (``MLMCB200_READ_THREADS``; default: up to 16, at most the cores)."""
+    """Threads of the file -> pinned staging copy (``MLMCB200_READ_THREADS``; default: up to 8, at most the cores --
+    one thread copies ~11 GB/s out of the page cache, eight ~45 GB/s; more than that did not help the pipeline)."""
     n = os.environ.get("MLMCB200_READ_THREADS")
     if n is not None:
         return max(1, int(n))
@@ -273,7 +298,7 @@ def _read_threads():
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
-    return max(1, min(16, cores))
+    return max(1, min(8, cores))
 
 
 def _read_pool():
@@ -334,19 +359,27 @@ def stream_levels(segments, device, chunk_bytes=32 << 20):
     consumed = [torch.cuda.Event() for _ in range(2)]
     copy_stream.wait_stream(compute)          # the buffers may be recycled memory still in use on the compute stream
 
-    def issue(k):
-        b = k % 2
+    def geometry(k):
         level_id, host, lo, hi = pieces[k]
         shape = (hi - lo,) + tuple(int(d) for d in host.shape[1:])
-        n_elems = shape[0] * shape[1] * shape[2]
-        view = bufs[b][:n_elems].view(shape)
+        return level_id, host, lo, hi, shape, shape[0] * shape[1] * shape[2]
+
+    def read(k):
+        """CPU stage (file-backed pieces; runs on the reader thread): fill staging buffer k % 2 with piece k."""
+        b = k % 2
+        level_id, host, lo, hi, shape, n_elems = geometry(k)
         if isinstance(host, torch.Tensor):
-            src = host[lo:hi]
-        else:
-            if k >= 2:
-                copied[b].synchronize()       # the copy that last read this staging buffer has finished
-            src = stage[b][:n_elems].view(shape)
-            host.read_into(lo, hi, src.numpy())
+            return
+        if k >= 2:
+            copied[b].synchronize()           # the copy that last read this staging buffer has finished
+        host.read_into(lo, hi, stage[b][:n_elems].view(shape).numpy())
+
+    def enqueue(k):
+        """Copy stage: piece k (pinned rows or its staging buffer) -> device buffer k % 2 on the copy stream."""
+        b = k % 2
+        level_id, host, lo, hi, shape, n_elems = geometry(k)
+        view = bufs[b][:n_elems].view(shape)
+        src = host[lo:hi] if isinstance(host, torch.Tensor) else stage[b][:n_elems].view(shape)
         with torch.cuda.stream(copy_stream):
             if k >= 2:
                 copy_stream.wait_event(consumed[b])
@@ -354,19 +387,57 @@ def stream_levels(segments, device, chunk_bytes=32 << 20):
             copied[b].record(copy_stream)
         return level_id, view
 
-    nxt = issue(0)
+    # The CPU stage of piece k + 2 runs right before piece k is handed to the consumer (the copy engine then moves piece
+    # k + 1 and the kernels of piece k - 1 may still run); MLMCB200_FEED_THREAD=1 moves it to a background thread instead.
+    # Measured on cfg5 from an HDF5 file (profiles/r2_feed_probe.txt): the background thread gains nothing (39.0 against
+    # 38.0 ms; in the bench it lost) -- it and the consumer hand the interpreter lock back and forth around every call.
+    pending = {}
+
+    background = staged and os.environ.get("MLMCB200_FEED_THREAD", "0") == "1"
+
+    def submit(k):
+        if staged and k < len(pieces):
+            if background:
+                pending[k] = _reader().submit(read, k)
+            else:
+                read(k)
+
+    def collect(k):
+        f = pending.pop(k, None)
+        if f is not None:
+            f.result()
+
     try:
+        submit(0)
+        collect(0)
+        nxt = enqueue(0)
+        submit(1)
         for k in range(len(pieces)):
             cur = nxt
             if k + 1 < len(pieces):
-                nxt = issue(k + 1)
+                collect(k + 1)
+                nxt = enqueue(k + 1)
+            submit(k + 2)                     # staging buffer k % 2 again: its last reader is the copy of piece k, enqueued
             b = k % 2
             compute.wait_event(copied[b])
             yield cur
             consumed[b].record(compute)
     finally:
-        if staged:                            # the staging buffers are shared: nothing may still be reading them
+        for f in list(pending.values()):      # nobody may still be writing the shared staging buffers ...
+            try:
+                f.result()
+            except Exception:
+                pass
+        pending.clear()
+        if staged:                            # ... or reading them
             copy_stream.synchronize()
+
+
+def _reader():
+    if "reader" not in _pool:
+        from concurrent.futures import ThreadPoolExecutor
+        _pool["reader"] = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mlmcb200-feed")
+    return _pool["reader"]
 
 
 _copy_streams = {}
@@ -603,6 +674,10 @@ class _MinRows(_H5pyRows):
     def __init__(self, dataset, shape):
         self._dset, self.shape = dataset, shape
         self.keeps_items = not dataset._filters       # level 0 without its zero coarse row, straight from the mapping
+        from .tool import hdf5_min
+        if hdf5_min.parallel_copy is None and _native_copy() is not None:
+            hdf5_min.parallel_copy = _native_copy()
+        self.native_copy = hdf5_min.parallel_copy is not None and not dataset._filters
 
     def read_rows(self, lo=0, hi=None, out=None, keep_items=None):
         return self._dset.read_rows(lo, hi, out=out, keep_items=keep_items)

@@ -30,6 +30,11 @@ SIGNATURE = b"\x89HDF\r\n\x1a\n"
 UNDEF = 0xFFFFFFFFFFFFFFFF
 
 
+#: optional ``f(dst_address, src_address, n_rows, keep_bytes, src_pitch)``: a multi-threaded host copy for large runs of
+#: rows (set by ``mlmc_b200.sample_storage`` to the native helper; this module itself has no dependency but NumPy)
+parallel_copy = None
+
+
 class Unsupported(NotImplementedError):
     pass
 
@@ -334,7 +339,10 @@ class Dataset(_Object):
 
         def put(a, b, src, first):
             """rows [a, b) from ``src`` = the stored bytes of the elements first, first + 1, ..."""
-            if keep_bytes == row_bytes:
+            if parallel_copy is not None and (b - a) * keep_bytes >= (2 << 20):
+                parallel_copy(rows_out.ctypes.data + (a - lo) * keep_bytes, src.ctypes.data + (a - first) * row_bytes,
+                              b - a, keep_bytes, row_bytes)
+            elif keep_bytes == row_bytes:
                 flat[(a - lo) * row_bytes:(b - lo) * row_bytes] = src[(a - first) * row_bytes:(b - first) * row_bytes]
             else:
                 rows_out[a - lo:b - lo] = src.reshape(-1, row_bytes)[a - first:b - first, :keep_bytes]
