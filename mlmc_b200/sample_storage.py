@@ -289,8 +289,8 @@ def _native_copy():
 
 
 def _read_threads():
-    """Threads of the file -> pinned staging copy (``MLMCB200_READ_THREADS``; default: up to 8, at most the cores --
-    one thread copies ~11 GB/s out of the page cache, eight ~45 GB/s; more than that did not help the pipeline)."""
+    """Threads of the file -> pinned staging copy (``MLMCB200_READ_THREADS``; default: up to 16, at most the cores --
+    one thread copies ~11 GB/s out of the page cache, sixteen 40-58 GB/s: profiles/r2_feed_probe.txt)."""
     n = os.environ.get("MLMCB200_READ_THREADS")
     if n is not None:
         return max(1, int(n))
@@ -298,7 +298,7 @@ def _read_threads():
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
-    return max(1, min(8, cores))
+    return max(1, min(16, cores))
 
 
 def _read_pool():
